@@ -1,0 +1,215 @@
+"""Pins the CPU oracle against the reference's own golden vectors (CPU only, no GPU, no /root/reference).
+
+Fixtures under tests/golden/ were produced by tests/golden/make_golden.py from the reference checkout:
+EMX1.output (md5 895e282b..., test_data/integration_test.sh:81), EMX1.output.scored (md5 804bf3c1..., :84),
+reference_unit_vectors.json (ScalaTest known answers), fake.sites.gz (TabDelimitedHanderTest.scala:40-51).
+"""
+import gzip
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def vec():
+    return json.load(open(os.path.join(GOLDEN, "reference_unit_vectors.json")))
+
+
+def test_golden_files_keep_their_pinned_md5():
+    pins = json.load(open(os.path.join(GOLDEN, "pins.json")))
+    md5 = lambda p: hashlib.md5(open(os.path.join(GOLDEN, p), "rb").read()).hexdigest()
+    assert md5("EMX1.output") == pins["md5_discover"] == "895e282bf486c359667e2c3e0e0e0260"
+    assert md5("EMX1.output.scored") == pins["md5_scored"] == "804bf3c1ff38b077f31f12f51d733aa4"
+
+
+def test_encode_decode_round_trip(oracle):
+    # BitEncodingTest.scala:20-64
+    rng = np.random.default_rng(7)
+    for L in (20, 22, 23, 24):
+        for _ in range(200):
+            s = "".join("ACGT"[i] for i in rng.integers(0, 4, L))
+            c = int(rng.integers(1, 32768))
+            enc = oracle.encode(s, c)
+            assert oracle.decode(enc, L) == (s, c)
+    assert oracle.encode("ACGT", 1) == (1 << 48) | 0b00011011
+    with pytest.raises(ValueError):
+        oracle.encode("ACGN")
+    with pytest.raises(ValueError):
+        oracle.encode("A" * 25)
+
+
+def test_mismatch_known_answers(oracle, vec):
+    # BitEncodingTest.scala:79-151,296-307
+    for c in vec["mismatch_cases"]:
+        p = oracle.pack_by_name(c["pack"])
+        assert oracle.mismatches(p, oracle.encode(c["a"], c["ca"]), oracle.encode(c["b"], c["cb"])) == c["mm"], c
+
+
+def test_mismatch_random_vs_naive(oracle):
+    # BitEncodingTest.scala:153-200 (10k random pairs, Cas9 bases 0..20 and Cpf1 bases 4..24)
+    rng = np.random.default_rng(11)
+    for name, lo, hi in (("SPCAS9", 0, 20), ("CPF1", 4, 24), ("SPCAS9NGG19", 0, 19)):
+        p = oracle.pack_by_name(name)
+        for _ in range(3000):
+            a = "".join("ACGT"[i] for i in rng.integers(0, 4, p.scan_len))
+            b = "".join("ACGT"[i] for i in rng.integers(0, 4, p.scan_len))
+            naive = sum(1 for x, y in zip(a[lo:hi], b[lo:hi]) if x != y)
+            assert oracle.mismatches(p, oracle.encode(a, int(rng.integers(1, 30000))), oracle.encode(b)) == naive
+
+
+def test_bin_prefix_known_answers(oracle, vec):
+    # BitEncodingTest.scala:236-359
+    for c in vec["bin_cases"]:
+        p = oracle.pack_by_name(c["pack"])
+        assert oracle.mismatch_bin(p, c["bin"], oracle.encode(c["guide"])) == c["mm"], c
+
+
+def test_cfd_known_answers(oracle, vec):
+    # Doench2016CFDScoreTest.scala:32-84 ; tolerances are the reference's (1e-3); restated exact values from SURVEY 8c.4
+    g20 = vec["cfd_pairs"]["guide20"]
+    exact = [0.2492374732932462, 0.2445141064537618, 0.23518099545763574, 0.18765610861813575, 0.1423628278388532]
+    for (ot20, expect), ex in zip(vec["cfd_pairs"]["cases"], exact):
+        got = oracle.cfd_pair(oracle.encode(g20 + "AGG"), oracle.encode(ot20 + "AGG"))
+        assert abs(got - expect) < 1e-3
+        assert got == ex
+    exact_max = [0.0, 0.5238095242619047, 0.302521008307563]
+    for case, ex in zip(vec["cfd_guides"], exact_max):
+        ots = np.asarray([oracle.encode(s) for s in case["off_targets"]], np.uint64)
+        mx, spec, per = oracle.cfd_guide(oracle.encode(case["guide"]), ots)
+        assert abs(mx - case["expected_max"]) < 1e-3
+        assert mx == ex
+        assert 0.0 < spec <= 1.0
+
+
+def test_hsu_known_answers(oracle, vec):
+    # CrisprMitEduOffTargetTest.scala:54-70
+    p = oracle.pack_by_name("SPCAS9")
+    h = vec["hsu"]
+    ots = np.asarray([oracle.encode(s) for s in h["off_targets"]], np.uint64)
+    got = oracle.hsu_guide(p, oracle.encode(h["guide"]), ots)
+    assert abs(got - h["expected"]) <= h["tol"]
+    assert got == 96.0618868577998
+    s = h["single"]
+    one = oracle.hsu_offtarget(oracle.encode(s["guide"]), oracle.encode(s["ot"]))
+    assert abs(one - s["expected"]) <= s["tol"]
+    assert one == 0.3640387298259494
+
+
+def test_scored_golden_columns(oracle):
+    """Re-score the pinned discover TSV and compare with the pinned scored TSV column by column (text-exact)."""
+    pack = oracle.pack_by_name("SPCAS9NGG")
+    guides = oracle.read_discover_tsv(os.path.join(GOLDEN, "EMX1.output"), pack)
+    lines = open(os.path.join(GOLDEN, "EMX1.output.scored")).read().strip().split("\n")
+    hdr = lines[0].split("\t")
+    rows = {r.split("\t")[3]: dict(zip(hdr, r.split("\t"))) for r in lines[1:]}
+    assert len(guides) == 3
+    for g in guides:
+        ots = np.asarray(g.targets, np.uint64)
+        mx, spec, _ = oracle.cfd_guide(g.encoding, ots)
+        hs = oracle.hsu_guide(pack, g.encoding, ots)
+        row = rows[g.site.bases]
+        assert oracle.java_double_str(mx) == row["DoenchCFD_maxOT"]
+        assert oracle.java_double_str(spec) == row["DoenchCFD_specificityscore"]
+        assert oracle.java_double_str(hs) == row["Hsu2013"]
+        assert oracle.minot(pack, g.encoding, ots) == (row["basesDiffToClosestHit"], row["closestHitCount"], row["0-1-2-3-4_mismatch"])
+        assert oracle.dangerous(pack, g.site.bases, g.encoding, ots) == (row["dangerous_GC"], row["dangerous_polyT"], row["dangerous_in_genome"])
+    # values quoted in BASELINE.md section 2
+    assert rows["GAGTCCGAGCAGAAGAAGAAGGG"]["DoenchCFD_maxOT"] == "0.30014429994302205"
+    assert rows["AGAGTCCGAGCAGAAGAAGAAGG"]["Hsu2013"] == "98.41774847095192"
+
+
+def test_fake_sites_tokens_are_mismatch_known_answers(oracle):
+    """Every SEQ_count_mm token of test_data/fake.sites is a known answer for BitEncoding.mismatches."""
+    pack = oracle.pack_by_name("SPCAS9")
+    path = os.path.join(GOLDEN, "fake.sites.gz")
+    guides = oracle.read_discover_tsv(path, pack, filter_overflow=False)
+    assert len(guides) == 99
+    n = 0
+    for g in guides:
+        for t, mm in zip(g.targets, g.recorded_mm):
+            assert oracle.mismatches(pack, g.encoding, t) == mm
+            n += 1
+    assert n > 5000
+
+
+def test_fake_sites_round_trip(oracle, tmp_path):
+    """TabDelimitedHanderTest.scala:40-51: read fake.sites, write it back, byte-identical."""
+    pack = oracle.pack_by_name("SPCAS9")
+    raw = gzip.open(os.path.join(GOLDEN, "fake.sites.gz"), "rt").read()
+    lines = raw.rstrip("\n").split("\n")
+    hdr = lines[0].split("\t")
+    guides = oracle.read_discover_tsv(os.path.join(GOLDEN, "fake.sites.gz"), pack, filter_overflow=False)
+    contigs = []
+    row_ptr, targets, mms, pos_ptr, positions = [0], [], [], [0], []
+    for g in guides:
+        for t, mm, pl in zip(g.targets, g.recorded_mm, g.positions):
+            targets.append(t)
+            mms.append(mm)
+            for (ctg, st, fwd) in (pl or []):
+                if ctg not in contigs:
+                    contigs.append(ctg)
+                positions.append(oracle.pos_encode(contigs.index(ctg) + 1, st, 23, fwd))
+            pos_ptr.append(len(positions))
+        row_ptr.append(len(targets))
+    hits = oracle.Hits(np.asarray(row_ptr), np.asarray(targets, np.uint64), np.asarray(mms, np.uint8),
+                       np.zeros(len(guides), np.int32),
+                       np.asarray([g.inherited_overflow for g in guides], np.uint8),
+                       np.asarray(pos_ptr), np.asarray(positions, np.uint64))
+    out = tmp_path / "fake.out"
+    ann = hdr[7:-2]
+    oracle.write_discover_tsv(str(out), pack, [oracle.Guide(g.site, g.encoding) for g in guides], hits, contigs,
+                              with_positions=True, score_columns=ann,
+                              score_values=[[g.annotations[a] for a in ann] for g in guides])
+    assert open(out).read() == raw
+
+
+def test_block_manager_linear_vs_indexed(oracle):
+    """BlockManagerTest.scala:29-63 on test_blockAACCTTGG.binary (10 130 targets x 1 position, big-endian):
+    the same targets laid out as a linear and as an indexed block give identical hits (the reference test only
+    compares sizes; here the full hit lists are compared)."""
+    pack = oracle.pack_by_name("SPCAS9")
+    raw = np.fromfile(os.path.join(GOLDEN, "test_blockAACCTTGG.binary"), dtype=">u8").astype(np.uint64)
+    assert int(raw[0]) == 2 * 10130 == len(raw) - 1  # leading long = number of longs (BlockManagerTest.scala:118-131)
+    targets, pos = raw[1::2], raw[2::2]
+    assert ((targets >> np.uint64(48)) == 1).all()
+    uniq, counts, p2 = oracle.collapse_sites(targets & np.uint64(oracle.STRING_MASK), pos)
+    blocks_idx, nt = oracle.make_blocks(pack, 7, uniq, counts, p2)
+    b = oracle.bin_code("AACCTTG")
+    assert nt[b] == len(uniq) and int(blocks_idx[b][0]) == 2
+    # the same bin as a linear block
+    body = blocks_idx[b][257:]
+    lin = np.concatenate([np.asarray([1], np.uint64), body])
+    rng = np.random.default_rng(5)
+    guides = [oracle.encode("AACCTTGG" + "".join("ACGT"[i] for i in rng.integers(0, 4, 12)) + "TGG") for _ in range(1000)]
+
+    def run(block_for_bin):
+        blocks = [np.asarray([1], np.uint64)] * (4 ** 7)
+        blocks[b] = block_for_bin
+        off = np.zeros(4 ** 7 + 1, np.int64)
+        np.cumsum([len(x) for x in blocks], out=off[1:])
+        db = oracle.Database(pack, 7, np.concatenate(blocks), off, np.zeros(4 ** 7, np.int32), ["c"])
+        return oracle.discover_blocks(db, guides, 1, 2000)
+
+    a, c = run(blocks_idx[b]), run(lin)
+    assert (a.row_ptr == c.row_ptr).all() and (a.targets == c.targets).all() and (a.mismatches == c.mismatches).all()
+    assert int(a.row_ptr[-1]) > 0
+
+
+def test_discover_chr22_emx1_reproduces_pinned_tsv(oracle, chr22_db_path, tmp_path):
+    """index -> discover on the quick-start data == md5 895e282b... (needs the locally built chr22 DB)."""
+    db = oracle.read_database(chr22_db_path)
+    guides = oracle.guides_from_fasta(os.path.join(GOLDEN, "EMX1_GAGTCCGAGCAGAAGAAGAAGGG.fasta"), db.pack, 6)
+    for force_linear in (False, True):
+        hits = oracle.discover_blocks(db, [g.encoding for g in guides], 4, 2000, force_linear=force_linear)
+        out = tmp_path / "EMX1.output"
+        oracle.write_discover_tsv(str(out), db.pack, guides, hits, db.contigs)
+        assert oracle.md5_file(str(out)) == "895e282bf486c359667e2c3e0e0e0260"
+    # and the SoA walk gives the same rows
+    t, bo, _po, _pp = db.soa()
+    soa = oracle.discover_soa(db.pack, 7, t, bo, [g.encoding for g in guides], 4, 2000, n_threads=2)
+    assert (soa.row_ptr == hits.row_ptr).all() and (soa.targets == hits.targets).all()
