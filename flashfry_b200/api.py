@@ -1,0 +1,164 @@
+"""Thin Python harness over the C ABI, used by the tests and bench.py.  The product is the C ABI + CUDA library;
+this module adds no computation of its own (and never touches oracle/)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from ._native import FF_METRIC_CFD, FF_METRIC_HSU2013, FlashFryError  # noqa: F401
+
+
+@dataclass
+class Hits:
+    """Copy of an ff_hits (CSR over guides; see include/flashfry_b200.h)."""
+    row_ptr: np.ndarray
+    targets: np.ndarray
+    mismatches: np.ndarray
+    total_count: np.ndarray
+    overflowed: np.ndarray
+    pos_ptr: Optional[np.ndarray]
+    positions: Optional[np.ndarray]
+    n_compares: int
+    n_candidate_hits: int
+
+    @property
+    def n_guides(self) -> int:
+        return len(self.row_ptr) - 1
+
+    def row(self, g: int):
+        lo, hi = int(self.row_ptr[g]), int(self.row_ptr[g + 1])
+        return self.targets[lo:hi], self.mismatches[lo:hi]
+
+
+def _arr(ptr, n, dtype):
+    if n <= 0 or not ptr:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+def _take_hits(hp) -> Hits:
+    h = hp.contents
+    G, H = int(h.n_guides), int(h.n_hits)
+    row_ptr = _arr(h.row_ptr, G + 1, np.int64)
+    pos_ptr = positions = None
+    if h.pos_ptr:
+        pos_ptr = _arr(h.pos_ptr, H + 1, np.int64)
+        positions = _arr(h.positions, int(pos_ptr[-1]), np.uint64)
+    out = Hits(row_ptr, _arr(h.targets, H, np.uint64), _arr(h.mismatches, H, np.uint8), _arr(h.total_count, G, np.int32),
+               _arr(h.overflowed, G, np.uint8), pos_ptr, positions, int(h.n_compares), int(h.n_candidate_hits))
+    N.lib().ff_hits_free(hp)
+    return out
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+class Context:
+    """One GPU, one resident database (ff_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        N.check(N.lib().ff_create(C.byref(self._h), device))
+
+    def close(self):
+        if self._h:
+            N.lib().ff_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- database
+    def set_stream(self, cuda_stream: int):
+        N.check(N.lib().ff_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def load_database(self, db_path: str, header_path: Optional[str] = None):
+        N.check(N.lib().ff_load_database(self._h, db_path.encode(), header_path.encode() if header_path else None))
+
+    def load_database_arrays(self, enzyme_index: int, targets, positions=None, contigs: Sequence[str] = (), bin_width: int = 7):
+        t = _u64(targets)
+        p = _u64(positions) if positions is not None else None
+        names = (C.c_char_p * max(len(contigs), 1))(*[c.encode() for c in contigs])
+        N.check(N.lib().ff_load_database_arrays(
+            self._h, enzyme_index, bin_width, t.ctypes.data_as(C.POINTER(C.c_uint64)), len(t),
+            p.ctypes.data_as(C.POINTER(C.c_uint64)) if p is not None else None, len(p) if p is not None else 0,
+            names, len(contigs)))
+
+    def synth_database(self, enzyme_index: int, n_targets: int, seed: int):
+        N.check(N.lib().ff_synth_database(self._h, enzyme_index, n_targets, seed))
+
+    def info(self) -> N.FFDbInfo:
+        i = N.FFDbInfo()
+        N.check(N.lib().ff_db_info(self._h, C.byref(i)))
+        return i
+
+    def contigs(self) -> List[str]:
+        return [N.lib().ff_db_contig(self._h, k + 1).decode() for k in range(self.info().n_contigs)]
+
+    def copy_targets(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = int(self.info().n_targets) - first
+        out = np.empty(n, np.uint64)
+        N.check(N.lib().ff_db_copy_targets(self._h, first, n, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    # ---- discover / score
+    def discover(self, guides, max_mismatch: int = 4, maximum_off_targets: int = 2000, positions: bool = False) -> Hits:
+        g = _u64(guides)
+        hp = C.POINTER(N.FFHits)()
+        N.check(N.lib().ff_discover(self._h, g.ctypes.data_as(C.POINTER(C.c_uint64)), len(g), max_mismatch,
+                                    maximum_off_targets, int(positions), C.byref(hp)))
+        return _take_hits(hp)
+
+    def discover_score(self, guides, max_mismatch: int = 4, maximum_off_targets: int = 2000, positions: bool = False,
+                       metrics: int = FF_METRIC_CFD | FF_METRIC_HSU2013):
+        g = _u64(guides)
+        n = max(len(g), 1)
+        cmax, cspec, hsu = np.full(n, np.nan), np.full(n, np.nan), np.full(n, np.nan)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        hp = C.POINTER(N.FFHits)()
+        N.check(N.lib().ff_discover_score(self._h, g.ctypes.data_as(C.POINTER(C.c_uint64)), len(g), max_mismatch,
+                                          maximum_off_targets, int(positions), metrics, C.byref(hp), dp(cmax), dp(cspec), dp(hsu)))
+        return _take_hits(hp), cmax[:len(g)], cspec[:len(g)], hsu[:len(g)]
+
+    def score(self, guides, row_ptr, targets, metrics: int = FF_METRIC_CFD | FF_METRIC_HSU2013):
+        """ff_score over a host CSR hit list -> (cfd_max, cfd_specificity, hsu2013, per_ot_cfd)."""
+        g = _u64(guides)
+        rp = np.ascontiguousarray(np.asarray(row_ptr, dtype=np.int64))
+        t = _u64(targets)
+        h = N.FFHits()
+        h.n_guides, h.n_hits = len(g), len(t)
+        h.row_ptr = rp.ctypes.data_as(C.POINTER(C.c_int64))
+        h.targets = t.ctypes.data_as(C.POINTER(C.c_uint64))
+        n = max(len(g), 1)
+        cmax, cspec, hsu, per = np.full(n, np.nan), np.full(n, np.nan), np.full(n, np.nan), np.full(max(len(t), 1), np.nan)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        N.check(N.lib().ff_score(self._h, g.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(h), metrics, dp(cmax), dp(cspec),
+                                 dp(hsu), dp(per)))
+        return cmax[:len(g)], cspec[:len(g)], hsu[:len(g)], per[:len(t)]
+
+    def discover_device(self, d_guides_ptr: int, n_guides: int, max_mismatch: int = 4, maximum_off_targets: int = 2000,
+                        metrics: int = 0) -> N.FFDeviceResult:
+        r = N.FFDeviceResult()
+        N.check(N.lib().ff_discover_device(self._h, C.c_void_p(d_guides_ptr), n_guides, max_mismatch, maximum_off_targets,
+                                           metrics, C.byref(r)))
+        return r
+
+    def timings(self) -> N.FFTimings:
+        t = N.FFTimings()
+        N.check(N.lib().ff_last_timings(self._h, C.byref(t)))
+        return t

@@ -1,0 +1,320 @@
+// C ABI of libflashfry_b200 (include/flashfry_b200.h): context, error plumbing, host <-> device staging.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "ff_common.cuh"
+#include "ff_kernels.cuh"
+
+namespace ff {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+  return e == cudaErrorMemoryAllocation ? FF_ENOMEM : FF_ECUDA;
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap && p) return FF_OK;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) { want = bytes + 256; e = cudaMalloc(&p, want); }
+  if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc(workspace)", __FILE__, __LINE__); }
+  cap = want;
+  return FF_OK;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+int HostBuf::reserve(size_t bytes) {
+  if (bytes <= cap && p) return FF_OK;
+  if (p) cudaFreeHost(p);
+  p = nullptr; cap = 0;
+  const size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+  if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__); }
+  cap = want;
+  return FF_OK;
+}
+void HostBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+
+// Host-side owner of an ff_hits: pinned buffers recycled through a small process-wide free list so that steady-state
+// discover calls do not pay cudaHostAlloc.
+struct HitsOwner {
+  ff_hits pub;
+  HostBuf row_ptr, targets, mm, pos_ptr, positions, total, ovf;
+};
+static std::mutex g_pool_mu;
+static std::vector<HitsOwner *> g_pool;
+
+static HitsOwner *owner_get() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pool.empty()) { HitsOwner *o = g_pool.back(); g_pool.pop_back(); return o; }
+  return new (std::nothrow) HitsOwner();
+}
+static void owner_put(HitsOwner *o) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool.size() < 4) { g_pool.push_back(o); return; }
+  o->row_ptr.release(); o->targets.release(); o->mm.release(); o->pos_ptr.release(); o->positions.release();
+  o->total.release(); o->ovf.release();
+  delete o;
+}
+
+static int copy_out(ff_ctx *ctx, const DeviceResult &r, ff_hits **out) {
+  HitsOwner *o = owner_get();
+  if (!o) { set_error("out of host memory"); return FF_ENOMEM; }
+  const int64_t G = r.n_guides, H = r.n_hits, P = r.n_positions;
+  int rc = FF_OK;
+  auto fail = [&](int code) { owner_put(o); return code; };
+  if ((rc = o->row_ptr.reserve((G + 1) * 8)) || (rc = o->targets.reserve((H + 1) * 8)) || (rc = o->mm.reserve(H + 1)) ||
+      (rc = o->total.reserve((G + 1) * 4)) || (rc = o->ovf.reserve(G + 1)))
+    return fail(rc);
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaMemcpyAsync(o->row_ptr.p, r.d_row_ptr, (G + 1) * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->targets.p, r.d_targets, H * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->mm.p, r.d_mismatches, H, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && G > 0) e = cudaMemcpyAsync(o->total.p, r.d_total_count, G * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && G > 0) e = cudaMemcpyAsync(o->ovf.p, r.d_overflowed, G, cudaMemcpyDeviceToHost, st);
+  const bool with_pos = r.d_pos_ptr != nullptr;
+  if (e == cudaSuccess && with_pos) {
+    if ((rc = o->pos_ptr.reserve((H + 1) * 8)) || (rc = o->positions.reserve((P + 1) * 8))) return fail(rc);
+    e = cudaMemcpyAsync(o->pos_ptr.p, r.d_pos_ptr, (H + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && P > 0) e = cudaMemcpyAsync(o->positions.p, r.d_positions, P * 8, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "D2H of discover results", __FILE__, __LINE__));
+  ff_hits &h = o->pub;
+  h.n_guides = G; h.n_hits = H;
+  h.row_ptr = o->row_ptr.as<int64_t>(); h.targets = o->targets.as<uint64_t>(); h.mismatches = o->mm.as<uint8_t>();
+  h.pos_ptr = with_pos ? o->pos_ptr.as<int64_t>() : nullptr;
+  h.positions = with_pos ? o->positions.as<uint64_t>() : nullptr;
+  h.total_count = o->total.as<int32_t>(); h.overflowed = o->ovf.as<uint8_t>();
+  h.n_compares = r.n_compares; h.n_candidate_hits = r.n_candidate_hits;
+  h.opaque = o;
+  *out = &h;
+  return FF_OK;
+}
+
+static int run_scores(ff_ctx *ctx, const uint64_t *d_guides, const DeviceResult &r, uint32_t metrics) {
+  if (!metrics) return FF_OK;
+  const int64_t Gp = r.n_guides > 0 ? r.n_guides : 1;
+  FF_TRY(ctx->cfd_max.reserve(Gp * 8));
+  FF_TRY(ctx->cfd_spec.reserve(Gp * 8));
+  FF_TRY(ctx->hsu.reserve(Gp * 8));
+  cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
+  FF_CUDA(cudaEventRecord(e0, ctx->stream));
+  FF_TRY(score_on_device(ctx, d_guides, r.n_guides, r.d_row_ptr, r.d_targets, r.n_hits, metrics, ctx->cfd_max.as<double>(),
+                         ctx->cfd_spec.as<double>(), ctx->hsu.as<double>(), nullptr));
+  FF_CUDA(cudaEventRecord(e1, ctx->stream));
+  FF_CUDA(cudaStreamSynchronize(ctx->stream));
+  FF_CUDA(cudaEventElapsedTime(&ctx->last.score_ms, e0, e1));
+  ctx->last.total_ms += ctx->last.score_ms;
+  return FF_OK;
+}
+
+}  // namespace ff
+
+using namespace ff;
+
+extern "C" {
+
+int ff_abi_version(void) { return 1; }
+const char *ff_last_error(void) { return g_err; }
+
+int ff_create(ff_ctx **out, int device_id) {
+  if (!out) { set_error("null out pointer"); return FF_EINVAL; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s); libflashfry_b200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return FF_ENODEVICE;
+  }
+  if (device_id < 0 || device_id >= n) { set_error("device %d out of range (0..%d)", device_id, n - 1); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(device_id));
+  ff_ctx *c = new (std::nothrow) ff_ctx();
+  if (!c) { set_error("out of host memory"); return FF_ENOMEM; }
+  c->device = device_id;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+  c->stream = c->own_stream;
+  for (auto &ev : c->ev) {
+    e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+  }
+  *out = c;
+  return FF_OK;
+}
+
+void ff_destroy(ff_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->db.release();
+  DevBuf *bufs[] = {&c->guides, &c->gkeys, &c->gkeys_sorted, &c->gentry, &c->gentry_sorted, &c->goff, &c->cub_tmp, &c->hit_keys,
+                    &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->row_ptr, &c->total_count, &c->overflowed,
+                    &c->out_targets, &c->out_mm, &c->out_tidx, &c->pos_cnt, &c->pos_ptr, &c->out_positions, &c->cfd_per_ot,
+                    &c->hsu_per_ot, &c->cfd_max, &c->cfd_spec, &c->hsu, &c->scratch_guides};
+  for (DevBuf *b : bufs) b->release();
+  for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int ff_set_stream(ff_ctx *c, void *cuda_stream) {
+  if (!c) { set_error("null context"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  FF_CUDA(cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return FF_OK;
+}
+
+int ff_load_database(ff_ctx *c, const char *db_path, const char *header_path) {
+  if (!c || !db_path) { set_error("null argument"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  std::string hp = header_path ? header_path : std::string(db_path) + ".header";  // BinaryHeader.headerExtension
+  return db_load_files(c, db_path, hp.c_str());
+}
+
+int ff_load_database_arrays(ff_ctx *c, int enzyme_index, int bin_width, const uint64_t *targets, uint64_t n_targets,
+                            const uint64_t *positions, uint64_t n_positions, const char *const *contigs, int n_contigs) {
+  if (!c || (!targets && n_targets)) { set_error("null argument"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  Pack pack;
+  FF_TRY(pack_from_index(enzyme_index, &pack));
+  std::vector<std::string> names;
+  for (int i = 0; contigs && i < n_contigs; ++i) names.push_back(contigs[i] ? contigs[i] : "");
+  return db_from_host_arrays(c, pack, bin_width, targets, n_targets, positions, n_positions, names);
+}
+
+int ff_synth_database(ff_ctx *c, int enzyme_index, uint64_t n_targets, uint64_t seed) {
+  if (!c) { set_error("null context"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  Pack pack;
+  FF_TRY(pack_from_index(enzyme_index, &pack));
+  return db_synth(c, pack, n_targets, seed);
+}
+
+int ff_db_info(const ff_ctx *c, ff_db_info_t *o) {
+  if (!c || !o) { set_error("null argument"); return FF_EINVAL; }
+  if (!c->db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
+  const Database &d = c->db;
+  o->enzyme_index = d.pack.enzyme_index; o->bin_width = d.bin_width; o->scan_len = d.pack.scan_len; o->pam_len = d.pack.pam_len;
+  o->five_prime_pam = d.pack.five_prime; o->cmp_mask = d.pack.cmp_mask; o->n_targets = d.n_targets; o->n_positions = d.n_positions;
+  o->n_contigs = (int)d.contigs.size(); o->sub_index_bases = d.sub_bases; o->device_bytes = d.device_bytes;
+  return FF_OK;
+}
+
+const char *ff_db_contig(const ff_ctx *c, int contig_id) {
+  if (!c || contig_id < 1 || contig_id > (int)c->db.contigs.size()) return nullptr;
+  return c->db.contigs[contig_id - 1].c_str();
+}
+
+int ff_db_copy_targets(ff_ctx *c, uint64_t first, uint64_t n, uint64_t *out) {
+  if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+  if (!c->db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
+  if (first + n > c->db.n_targets) { set_error("target range out of bounds"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  FF_CUDA(cudaMemcpy(out, c->db.d_targets + first, n * 8, cudaMemcpyDeviceToHost));
+  return FF_OK;
+}
+
+static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions,
+                         uint32_t metrics, ff_hits **out, double *cfd_max, double *cfd_spec, double *hsu) {
+  if (!c || !out || (n_guides > 0 && !guides)) { set_error("null argument"); return FF_EINVAL; }
+  *out = nullptr;
+  FF_CUDA(cudaSetDevice(c->device));
+  FF_TRY(c->scratch_guides.reserve((n_guides > 0 ? n_guides : 1) * 8));
+  if (n_guides > 0) FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, n_guides * 8, cudaMemcpyHostToDevice, c->stream));
+  DeviceResult r;
+  FF_TRY(discover_on_device(c, c->scratch_guides.as<uint64_t>(), n_guides, max_mm, max_ot, want_positions != 0, &r));
+  if (metrics) {
+    FF_TRY(run_scores(c, c->scratch_guides.as<uint64_t>(), r, metrics));
+    if (n_guides > 0) {
+      if (cfd_max && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_max, c->cfd_max.p, n_guides * 8, cudaMemcpyDeviceToHost, c->stream));
+      if (cfd_spec && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_spec, c->cfd_spec.p, n_guides * 8, cudaMemcpyDeviceToHost, c->stream));
+      if (hsu && (metrics & FF_METRIC_HSU2013)) FF_CUDA(cudaMemcpyAsync(hsu, c->hsu.p, n_guides * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  return copy_out(c, r, out);
+}
+
+int ff_discover(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions, ff_hits **out) {
+  return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, 0, out, nullptr, nullptr, nullptr);
+}
+
+int ff_discover_score(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions,
+                      uint32_t metrics, ff_hits **out, double *cfd_max, double *cfd_spec, double *hsu) {
+  return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, metrics, out, cfd_max, cfd_spec, hsu);
+}
+
+void ff_hits_free(ff_hits *h) {
+  if (!h || !h->opaque) return;
+  owner_put(static_cast<HitsOwner *>(h->opaque));
+}
+
+int ff_score(ff_ctx *c, const uint64_t *guides, const ff_hits *hits, uint32_t metrics, double *cfd_max, double *cfd_spec,
+             double *hsu, double *per_ot_cfd) {
+  if (!c || !hits || (!guides && hits->n_guides > 0)) { set_error("null argument"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  const int64_t G = hits->n_guides;
+  if (G <= 0 || !metrics) return FF_OK;
+  const int64_t H = hits->row_ptr[G];
+  cudaStream_t st = c->stream;
+  FF_TRY(c->scratch_guides.reserve(G * 8));
+  FF_TRY(c->row_ptr.reserve((G + 1) * 8));
+  FF_TRY(c->out_targets.reserve((H + 1) * 8));
+  FF_TRY(c->cfd_max.reserve(G * 8));
+  FF_TRY(c->cfd_spec.reserve(G * 8));
+  FF_TRY(c->hsu.reserve(G * 8));
+  FF_TRY(c->cfd_per_ot.reserve((H + 1) * 8));
+  FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, G * 8, cudaMemcpyHostToDevice, st));
+  FF_CUDA(cudaMemcpyAsync(c->row_ptr.p, hits->row_ptr, (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (H > 0) FF_CUDA(cudaMemcpyAsync(c->out_targets.p, hits->targets, H * 8, cudaMemcpyHostToDevice, st));
+  FF_TRY(score_on_device(c, c->scratch_guides.as<uint64_t>(), G, c->row_ptr.as<int64_t>(), c->out_targets.as<uint64_t>(), H, metrics,
+                         c->cfd_max.as<double>(), c->cfd_spec.as<double>(), c->hsu.as<double>(), c->cfd_per_ot.as<double>()));
+  if (cfd_max && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_max, c->cfd_max.p, G * 8, cudaMemcpyDeviceToHost, st));
+  if (cfd_spec && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_spec, c->cfd_spec.p, G * 8, cudaMemcpyDeviceToHost, st));
+  if (hsu && (metrics & FF_METRIC_HSU2013)) FF_CUDA(cudaMemcpyAsync(hsu, c->hsu.p, G * 8, cudaMemcpyDeviceToHost, st));
+  if (per_ot_cfd && (metrics & FF_METRIC_CFD) && H > 0) FF_CUDA(cudaMemcpyAsync(per_ot_cfd, c->cfd_per_ot.p, H * 8, cudaMemcpyDeviceToHost, st));
+  FF_CUDA(cudaStreamSynchronize(st));
+  FF_CUDA(cudaGetLastError());
+  return FF_OK;
+}
+
+int ff_discover_device(ff_ctx *c, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot, uint32_t metrics,
+                       ff_device_result *out) {
+  if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  DeviceResult r;
+  FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, &r));
+  FF_TRY(run_scores(c, d_guides, r, metrics));
+  out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
+  out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
+  out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
+  out->d_cfd_max = (metrics & FF_METRIC_CFD) ? c->cfd_max.as<double>() : nullptr;
+  out->d_cfd_specificity = (metrics & FF_METRIC_CFD) ? c->cfd_spec.as<double>() : nullptr;
+  out->d_hsu2013 = (metrics & FF_METRIC_HSU2013) ? c->hsu.as<double>() : nullptr;
+  return FF_OK;
+}
+
+int ff_last_timings(const ff_ctx *c, ff_timings *out) {
+  if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+  *out = c->last;
+  return FF_OK;
+}
+
+}  // extern "C"

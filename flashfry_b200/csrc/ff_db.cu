@@ -1,0 +1,471 @@
+// Database residency: FlashFry's on-disk format -> SoA image in HBM + the device-side prefix index.
+//
+// Replaces (FlashFry, src/main/scala/...):
+//   BinaryHeader.readHeader                 reference/binary/BinaryHeader.scala:115-160
+//   SeekTraverser.fillBlock (BGZF seek+read) reference/traverser/SeekTraverser.scala:113-121  (htsjdk 2.8.1
+//                                           BlockCompressedInputStream, build.sbt:17 -- BGZF per SAM spec 4.1)
+//   Utils.byteArrayToLong                   utils/Utils.scala:167-186 (native = little-endian longs)
+//   block decoders                          reference/binary/blocks/BlockManager.scala:266-351
+//
+// HBM layout (all in database order, which for 3'-PAM enzymes is the lexicographic order of the target string):
+//   targets  u64[N_t]            the reference's target longs (2-bit bases in bits 0..47, occurrence count in 48..63)
+//   tlow     u32[N_t]            their low words = every base below the 7-mer prefix (+PAM): all the scan kernel reads
+//   sub_off  u32[4^(7+s)+1]      first target of every (7+s)-mer prefix; s is chosen from N_t so that a sub-bin holds
+//                                a handful of targets (s=6 at human-genome size, s=3 for chr22)
+//   pos_off  u64[N_t+1], positions u64[N_p]   only touched for emitted hits when positions are requested
+#include <cub/cub.cuh>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <thread>
+
+#include "ff_common.cuh"
+#include "ff_kernels.cuh"
+
+namespace ff {
+
+// standards/StandardScanParameters.scala:61-70 + the constants of :90-215
+int pack_from_index(int idx, Pack *o) {
+  o->enzyme_index = idx;
+  switch (idx) {
+    case 1: o->scan_len = 24; o->pam_len = 4; o->five_prime = 1; o->cmp_mask = 0x00FFFFFFFFFFull; return FF_OK;
+    case 2: case 3: case 4: o->scan_len = 23; o->pam_len = 3; o->five_prime = 0; o->cmp_mask = 0x3FFFFFFFFFC0ull; return FF_OK;
+    case 5: case 6: o->scan_len = 22; o->pam_len = 3; o->five_prime = 0; o->cmp_mask = 0x0FFFFFFFFFC0ull; return FF_OK;
+    default: set_error("Unable to find the correct parameter pack for enzyme: %d", idx); return FF_EINVAL;
+  }
+}
+
+void Database::release() {
+  cudaFree(d_targets); cudaFree(d_tlow); cudaFree(d_sub_off); cudaFree(d_pos_off); cudaFree(d_positions);
+  cudaFree(d_mask7); cudaFree(d_submask);
+  *this = Database();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_low_words(const uint64_t *__restrict__ t, uint64_t n, uint32_t *__restrict__ lo) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) lo[i] = (uint32_t)t[i];
+}
+
+// strictly increasing over the 48 sequence bits?  (what makes database order == index order for 3'-PAM enzymes)
+__global__ void k_check_sorted(const uint64_t *__restrict__ t, uint64_t n, unsigned int *__restrict__ bad) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i == 0 || i >= n) return;
+  const uint64_t m = 0xFFFFFFFFFFFFull;
+  if ((t[i - 1] & m) >= (t[i] & m)) atomicAdd(bad, 1u);
+  if ((t[i] >> 48) == 0 || (t[i] >> 63)) atomicAdd(bad + 1, 1u);
+}
+
+// sub_off[j] = first target whose (7+s)-mer prefix >= j.  One thread per target boundary.
+__global__ void k_sub_offsets(const uint64_t *__restrict__ t, uint64_t n, int shift, uint32_t n_keys, uint32_t *__restrict__ off) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint64_t m = 0xFFFFFFFFFFFFull;
+  const int64_t prev = i == 0 ? -1 : (int64_t)((t[i - 1] & m) >> shift);
+  const int64_t cur = i == n ? (int64_t)n_keys : (int64_t)((t[i] & m) >> shift);
+  for (int64_t j = prev + 1; j <= cur; ++j) off[j] = (uint32_t)i;
+}
+
+__global__ void k_counts(const uint64_t *__restrict__ t, uint64_t n, uint64_t *__restrict__ c) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) c[i] = t[i] >> 48;
+  if (i == n) c[i] = 0;
+}
+
+static int base_distance(uint32_t m) { return __builtin_popcount((m | (m >> 1)) & 0x55555555u); }
+
+// XOR masks over `bases` bases, sorted by (distance, value); off[d] = first mask at distance d, off[bases+1] = 4^bases
+static void make_masks(int bases, std::vector<uint16_t> *out, int *off) {
+  const uint32_t n = 1u << (2 * bases);
+  out->clear();
+  for (int d = 0; d <= bases; ++d) {
+    off[d] = (int)out->size();
+    for (uint32_t m = 0; m < n; ++m)
+      if (base_distance(m) == d) out->push_back((uint16_t)m);
+  }
+  off[bases + 1] = (int)out->size();
+}
+
+static int choose_sub_bases(const Pack &pack, uint64_t n_targets) {
+  if (const char *e = getenv("FF_SUB_BASES")) {
+    int v = atoi(e);
+    if (v >= 0 && v <= kMaxSubBases) return v;
+  }
+  // aim at <= ~4 targets per (7+s)-mer sub-bin
+  int s = 0;
+  double per = (double)n_targets / (double)kNumBins;
+  while (s < kMaxSubBases && per > 4.0) { per /= 4.0; ++s; }
+  const int max_s = pack.scan_len - pack.pam_len - kPrefixBases - 1;  // leave at least one compared base below the sub key
+  return std::min(s, std::max(0, max_s));
+}
+
+int db_build_index(ff_ctx *ctx) {
+  Database &db = ctx->db;
+  cudaStream_t st = ctx->stream;
+  const uint64_t n = db.n_targets;
+  if (n >= 0xFFFFFFF0ull) { set_error("database too large for 32-bit target indices"); return FF_EUNSUPPORTED; }
+  if (!db.pack.five_prime) {
+    unsigned int *d_bad = nullptr, h_bad[2] = {0, 0};
+    FF_CUDA(cudaMalloc(&d_bad, 8));
+    FF_CUDA(cudaMemsetAsync(d_bad, 0, 8, st));
+    if (n > 0) k_check_sorted<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(db.d_targets, n, d_bad);
+    FF_CUDA(cudaMemcpyAsync(h_bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_bad);
+    if (h_bad[0] || h_bad[1]) {
+      set_error("database targets are not strictly sorted / have invalid counts (%u order, %u count violations)", h_bad[0], h_bad[1]);
+      return FF_EFORMAT;
+    }
+  }
+  db.sub_bases = db.pack.five_prime ? 0 : choose_sub_bases(db.pack, n);
+  const int s = db.sub_bases;
+  const uint32_t n_keys = 1u << (2 * (kPrefixBases + s));
+  FF_CUDA(cudaMalloc(&db.d_tlow, (n + 16) * 4));
+  FF_CUDA(cudaMalloc(&db.d_sub_off, ((size_t)n_keys + 1) * 4));
+  if (n > 0) k_low_words<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(db.d_targets, n, db.d_tlow);
+  if (!db.pack.five_prime) {
+    const int shift = 2 * (db.pack.scan_len - kPrefixBases - s);
+    k_sub_offsets<<<(unsigned int)((n + 1 + 255) / 256), 256, 0, st>>>(db.d_targets, n, shift, n_keys, db.d_sub_off);
+  }
+  db.device_bytes = n * 8 + (n + 16) * 4 + ((size_t)n_keys + 1) * 4;
+  if (db.d_positions) {
+    FF_CUDA(cudaMalloc(&db.d_pos_off, (n + 1) * 8));
+    uint64_t *d_c = nullptr;
+    FF_CUDA(cudaMalloc(&d_c, (n + 1) * 8));
+    k_counts<<<(unsigned int)((n + 1 + 255) / 256), 256, 0, st>>>(db.d_targets, n, d_c);
+    size_t tmp = 0;
+    FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_c, db.d_pos_off, n + 1, st));
+    FF_TRY(ctx->cub_tmp.reserve(tmp));
+    FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, d_c, db.d_pos_off, n + 1, st));
+    uint64_t total = 0;
+    FF_CUDA(cudaMemcpyAsync(&total, db.d_pos_off + n, 8, cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_c);
+    if (total != db.n_positions) {
+      set_error("position count %llu does not match the sum of target counts %llu", (unsigned long long)db.n_positions, (unsigned long long)total);
+      return FF_EFORMAT;
+    }
+    db.device_bytes += (n + 1) * 8 + db.n_positions * 8;
+  }
+  // mask tables
+  std::vector<uint16_t> m7, ms;
+  int off7[kPrefixBases + 2], offs[kMaxSubBases + 2];
+  make_masks(kPrefixBases, &m7, off7);
+  for (int i = 0; i < kPrefixBases + 2; ++i) db.m7off[i] = off7[i];
+  make_masks(s, &ms, offs);
+  for (int r = 0; r <= kMaxSubBases; ++r) db.nsub[r] = offs[std::min(r, s) + 1];
+  db.nsub[kMaxSubBases + 1] = offs[s + 1];
+  FF_CUDA(cudaMalloc(&db.d_mask7, m7.size() * 2));
+  FF_CUDA(cudaMalloc(&db.d_submask, std::max<size_t>(ms.size(), 1) * 2));
+  FF_CUDA(cudaMemcpyAsync(db.d_mask7, m7.data(), m7.size() * 2, cudaMemcpyHostToDevice, st));
+  FF_CUDA(cudaMemcpyAsync(db.d_submask, ms.data(), ms.size() * 2, cudaMemcpyHostToDevice, st));
+  FF_CUDA(cudaStreamSynchronize(st));
+  FF_CUDA(cudaGetLastError());
+  db.resident = true;
+  return FF_OK;
+}
+
+int db_from_host_arrays(ff_ctx *ctx, const Pack &pack, int bin_width, const uint64_t *targets, uint64_t n_targets,
+                        const uint64_t *positions, uint64_t n_positions, const std::vector<std::string> &contigs) {
+  ctx->db.release();
+  Database &db = ctx->db;
+  db.pack = pack; db.bin_width = bin_width; db.n_targets = n_targets; db.n_positions = positions ? n_positions : 0;
+  db.contigs = contigs;
+  FF_CUDA(cudaMalloc(&db.d_targets, (n_targets + 1) * 8));
+  FF_CUDA(cudaMemcpyAsync(db.d_targets, targets, n_targets * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (positions) {
+    FF_CUDA(cudaMalloc(&db.d_positions, (n_positions + 1) * 8));
+    FF_CUDA(cudaMemcpyAsync(db.d_positions, positions, n_positions * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  FF_CUDA(cudaStreamSynchronize(ctx->stream));
+  int rc = db_build_index(ctx);
+  if (rc != FF_OK) db.release();
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FlashFry files
+struct HeaderInfo {
+  int enzyme = 0, bin_width = 0;
+  std::vector<uint64_t> vptr;
+  std::vector<int64_t> nbytes, ntargets;
+  std::vector<std::string> contigs;
+};
+
+// BinaryHeader.readHeader :115-160 (text: magic, version, enzyme index, bin count, BIN=vptr,bytes,targets lines, contigs)
+static int read_header(const char *path, HeaderInfo *h) {
+  std::ifstream in(path);
+  if (!in) { set_error("cannot open header %s", path); return FF_EIO; }
+  std::string line;
+  auto next = [&](std::string *s) { return (bool)std::getline(in, *s); };
+  if (!next(&line) || strtoull(line.c_str(), nullptr, 10) != 0x1234ABCDE123890ull) {
+    set_error("Binary file %s doesn't have the magic number expected at the top of the file", path);
+    return FF_EFORMAT;
+  }
+  if (!next(&line) || strtoll(line.c_str(), nullptr, 10) != 1) {
+    set_error("Binary file %s doesn't have the correct version, expecting 1", path);
+    return FF_EFORMAT;
+  }
+  if (!next(&line)) { set_error("truncated header %s", path); return FF_EFORMAT; }
+  h->enzyme = atoi(line.c_str());
+  if (!next(&line)) { set_error("truncated header %s", path); return FF_EFORMAT; }
+  const long long bin_count = strtoll(line.c_str(), nullptr, 10);
+  h->bin_width = (int)(std::log((double)bin_count) / std::log(4.0));  // :131-132
+  if (bin_count <= 0 || (1ll << (2 * h->bin_width)) != bin_count) { set_error("bad bin count %lld in %s", bin_count, path); return FF_EFORMAT; }
+  h->vptr.resize(bin_count); h->nbytes.resize(bin_count); h->ntargets.resize(bin_count);
+  for (long long b = 0; b < bin_count; ++b) {
+    if (!next(&line)) { set_error("Missing line for bin %lld in %s", b, path); return FF_EFORMAT; }
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos || (int)eq != h->bin_width) { set_error("Failed to verify bin name in header line: %s", line.c_str()); return FF_EFORMAT; }
+    long long code = 0;
+    for (size_t i = 0; i < eq; ++i) {
+      const char *p = strchr("ACGT", line[i]);
+      if (!p) { set_error("bad bin name in header line: %s", line.c_str()); return FF_EFORMAT; }
+      code = code * 4 + (p - "ACGT");
+    }
+    if (code != b) { set_error("Failed to verify bin name, line %s is not bin %lld", line.c_str(), b); return FF_EFORMAT; }
+    unsigned long long v = 0; long long nb = 0, nt = 0;
+    if (sscanf(line.c_str() + eq + 1, "%llu,%lld,%lld", &v, &nb, &nt) != 3) { set_error("bad header line: %s", line.c_str()); return FF_EFORMAT; }
+    h->vptr[b] = v; h->nbytes[b] = nb; h->ntargets[b] = nt;
+  }
+  while (next(&line)) {
+    if (line.empty()) continue;
+    h->contigs.push_back(line.substr(0, line.find('=')));
+  }
+  return FF_OK;
+}
+
+static int read_file(const char *path, std::vector<uint8_t> *out) {
+  FILE *f = fopen(path, "rb");
+  if (!f) { set_error("cannot open %s", path); return FF_EIO; }
+  fseek(f, 0, SEEK_END);
+  const long long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out->resize((size_t)n);
+  const size_t got = n > 0 ? fread(out->data(), 1, (size_t)n, f) : 0;
+  fclose(f);
+  if ((long long)got != n) { set_error("short read on %s", path); return FF_EIO; }
+  return FF_OK;
+}
+
+struct Member { size_t off, len, hdr, isize, out_off; };
+
+// Walk the BGZF members through their BSIZE fields (SAM spec 4.1).
+static int scan_members(const std::vector<uint8_t> &raw, std::vector<Member> *ms) {
+  size_t off = 0, out = 0;
+  while (off < raw.size()) {
+    if (off + 18 > raw.size() || raw[off] != 0x1f || raw[off + 1] != 0x8b || raw[off + 2] != 8 || !(raw[off + 3] & 4)) {
+      set_error("not a BGZF member at byte %zu", off);
+      return FF_EFORMAT;
+    }
+    const size_t xlen = raw[off + 10] | (raw[off + 11] << 8);
+    size_t p = off + 12, end = off + 12 + xlen;
+    long bsize = -1;
+    while (p + 4 <= end) {
+      const size_t slen = raw[p + 2] | (raw[p + 3] << 8);
+      if (raw[p] == 'B' && raw[p + 1] == 'C' && slen == 2) bsize = raw[p + 4] | (raw[p + 5] << 8);
+      p += 4 + slen;
+    }
+    if (bsize < 0 || off + bsize + 1 > raw.size()) { set_error("BGZF member without a valid BC field at byte %zu", off); return FF_EFORMAT; }
+    Member m;
+    m.off = off; m.len = (size_t)bsize + 1; m.hdr = 12 + xlen;
+    const uint8_t *tail = raw.data() + off + m.len - 4;
+    m.isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((size_t)tail[3] << 24);
+    m.out_off = out;
+    out += m.isize;
+    ms->push_back(m);
+    off += m.len;
+  }
+  return FF_OK;
+}
+
+int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
+  HeaderInfo h;
+  FF_TRY(read_header(header_path, &h));
+  Pack pack;
+  FF_TRY(pack_from_index(h.enzyme, &pack));
+  std::vector<uint8_t> raw;
+  FF_TRY(read_file(db_path, &raw));
+  std::vector<Member> ms;
+  FF_TRY(scan_members(raw, &ms));
+  const size_t total = ms.empty() ? 0 : ms.back().out_off + ms.back().isize;
+  std::vector<uint8_t> payload(total + 8);
+
+  // inflate members on all host threads (they are independent gzip members)
+  unsigned nthreads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  std::vector<int> err(nthreads, 0);
+  {
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < nthreads; ++w) {
+      pool.emplace_back([&, w]() {
+        z_stream zs;
+        for (size_t i = w; i < ms.size(); i += nthreads) {
+          const Member &m = ms[i];
+          if (m.isize == 0) continue;
+          memset(&zs, 0, sizeof zs);
+          if (inflateInit2(&zs, -15) != Z_OK) { err[w] = 1; return; }
+          zs.next_in = const_cast<Bytef *>(raw.data() + m.off + m.hdr);
+          zs.avail_in = (uInt)(m.len - m.hdr - 8);
+          zs.next_out = payload.data() + m.out_off;
+          zs.avail_out = (uInt)m.isize;
+          const int rc = inflate(&zs, Z_FINISH);
+          inflateEnd(&zs);
+          if (rc != Z_STREAM_END || zs.total_out != m.isize) { err[w] = 1; return; }
+        }
+      });
+    }
+    for (auto &t : pool) t.join();
+  }
+  for (int e : err) if (e) { set_error("BGZF inflate failed for %s", db_path); return FF_EFORMAT; }
+
+  // virtual pointer -> payload offset (member file offset << 16 | offset inside the member's payload)
+  const size_t n_bins = h.vptr.size();
+  std::vector<size_t> bin_start(n_bins);
+  {
+    size_t mi = 0;
+    for (size_t b = 0; b < n_bins; ++b) {
+      const uint64_t coff = h.vptr[b] >> 16, uoff = h.vptr[b] & 0xFFFF;
+      while (mi < ms.size() && ms[mi].off < coff) ++mi;
+      size_t k = mi;
+      if (k >= ms.size() || ms[k].off != coff) {  // header order is normally monotone; fall back to a search
+        auto it = std::lower_bound(ms.begin(), ms.end(), coff, [](const Member &m, uint64_t v) { return m.off < v; });
+        if (it == ms.end() || it->off != coff) { set_error("bin %zu: virtual pointer does not address a BGZF member", b); return FF_EFORMAT; }
+        k = (size_t)(it - ms.begin());
+      }
+      bin_start[b] = ms[k].out_off + uoff;
+      if (h.nbytes[b] < 8 || (h.nbytes[b] & 7) || bin_start[b] + (size_t)h.nbytes[b] > total) {
+        set_error("bin %zu: block of %lld bytes does not fit the inflated database", b, (long long)h.nbytes[b]);
+        return FF_EFORMAT;
+      }
+    }
+  }
+
+  // pass 1: per-bin target / position counts (walk [target, pos x count]*, BlockManager.scala:225-253)
+  std::vector<uint64_t> bin_t(n_bins + 1, 0), bin_p(n_bins + 1, 0);
+  std::vector<int> bad(nthreads, 0);
+  auto for_bins = [&](auto fn) {
+    std::vector<std::thread> pool;
+    for (unsigned w = 0; w < nthreads; ++w)
+      pool.emplace_back([&, w]() {
+        const size_t lo = n_bins * w / nthreads, hi = n_bins * (w + 1) / nthreads;
+        for (size_t b = lo; b < hi; ++b) fn(b, w);
+      });
+    for (auto &t : pool) t.join();
+  };
+  auto block_body = [&](size_t b, const uint64_t **body, size_t *n_longs) -> bool {
+    const uint64_t *blk = reinterpret_cast<const uint64_t *>(payload.data() + bin_start[b]);  // little-endian host
+    uint64_t first;
+    memcpy(&first, blk, 8);
+    const size_t nl = (size_t)h.nbytes[b] / 8;
+    if (first == 1) { *body = blk + 1; *n_longs = nl - 1; return true; }
+    if (first == 2 && nl >= 257) { *body = blk + 257; *n_longs = nl - 257; return true; }  // 256-entry sub-bin table skipped
+    return false;  // "Invalid bin type" BlockManager.scala:85-87
+  };
+  for_bins([&](size_t b, unsigned w) {
+    const uint64_t *body; size_t nl;
+    if (!block_body(b, &body, &nl)) { bad[w] = 1; return; }
+    uint64_t nt = 0, np = 0, v;
+    for (size_t i = 0; i < nl;) {
+      memcpy(&v, body + i, 8);
+      const uint64_t c = v >> 48;
+      if (c == 0 || c > 32767 || i + 1 + c > nl) { bad[w] = 2; return; }
+      nt++; np += c; i += 1 + c;
+    }
+    bin_t[b + 1] = nt; bin_p[b + 1] = np;
+  });
+  for (int e : bad) if (e) { set_error(e == 1 ? "Invalid bin type, unknown value in a block header" : "Failed to correctly parse block: position entries exceed the block"); return FF_EFORMAT; }
+  for (size_t b = 0; b < n_bins; ++b) {
+    if ((int64_t)bin_t[b + 1] != h.ntargets[b]) { set_error("bin %zu: header says %lld targets, block holds %llu", b, (long long)h.ntargets[b], (unsigned long long)bin_t[b + 1]); return FF_EFORMAT; }
+    bin_t[b + 1] += bin_t[b]; bin_p[b + 1] += bin_p[b];
+  }
+  const uint64_t n_targets = bin_t[n_bins], n_positions = bin_p[n_bins];
+  std::vector<uint64_t> targets(n_targets + 1), positions(n_positions + 1);
+  // pass 2: fill
+  for_bins([&](size_t b, unsigned) {
+    const uint64_t *body; size_t nl;
+    block_body(b, &body, &nl);
+    uint64_t ti = bin_t[b], pi = bin_p[b], v;
+    for (size_t i = 0; i < nl;) {
+      memcpy(&v, body + i, 8);
+      const uint64_t c = v >> 48;
+      targets[ti++] = v;
+      memcpy(&positions[pi], body + i + 1, c * 8);
+      pi += c; i += 1 + c;
+    }
+  });
+  return db_from_host_arrays(ctx, pack, h.bin_width, targets.data(), n_targets, positions.data(), n_positions, h.contigs);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// synthetic database for benchmarks (SURVEY.md 8(d) cfg 3): uniform random protospacer + N, fixed PAM
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void k_synth_values(uint64_t n, uint64_t seed, int random_bits, uint64_t pam_bits, uint64_t *__restrict__ out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t r = splitmix64(seed * 0x2545F4914F6CDD1Dull + i);
+  out[i] = ((r >> (64 - random_bits)) << 4) | pam_bits;
+}
+
+// occurrence counts: 94 % = 1, else 1 + Geometric(0.3); ~2000 "repeat families" with count U[500, 32767]
+__global__ void k_synth_counts(uint64_t n, uint64_t seed, uint64_t family_every, uint64_t *__restrict__ t) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t v = t[i];
+  const uint64_t h = splitmix64(v ^ (seed << 1));
+  uint64_t c = 1;
+  if ((h % 100) >= 94) {
+    uint64_t g = splitmix64(h);
+    while (c < 64 && (g & 1023) >= 307) { c++; g = splitmix64(g); }  // continue with p = 0.7
+    c += 1;
+  }
+  if (family_every && (splitmix64(h ^ 0xABCDEF) % family_every) == 0) c = 500 + splitmix64(h ^ 0x123457) % 32268;
+  t[i] = v | (c << 48);
+}
+
+int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed) {
+  if (pack.five_prime) { set_error("synthetic databases are spCas9-family only"); return FF_EUNSUPPORTED; }
+  if (n_targets == 0 || n_targets > 3000000000ull) { set_error("bad synthetic database size"); return FF_EINVAL; }
+  ctx->db.release();
+  Database &db = ctx->db;
+  cudaStream_t st = ctx->stream;
+  const int random_bits = 2 * (pack.scan_len - 2);                     // protospacer + N
+  const uint64_t pam_bits = pack.enzyme_index == 4 ? 0x2ull : 0xAull;  // AG : GG
+  uint64_t *d_a = nullptr, *d_b = nullptr, *d_n = nullptr;
+  FF_CUDA(cudaMalloc(&d_a, (n_targets + 1) * 8));
+  FF_CUDA(cudaMalloc(&d_b, (n_targets + 1) * 8));
+  FF_CUDA(cudaMalloc(&d_n, 8));
+  k_synth_values<<<(unsigned int)((n_targets + 255) / 256), 256, 0, st>>>(n_targets, seed, random_bits, pam_bits, d_a);
+  size_t tmp = 0;
+  FF_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_a, d_b, n_targets, 0, 2 * pack.scan_len, st));
+  FF_TRY(ctx->cub_tmp.reserve(tmp));
+  FF_CUDA(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp, d_a, d_b, n_targets, 0, 2 * pack.scan_len, st));
+  FF_CUDA(cub::DeviceSelect::Unique(nullptr, tmp, d_b, d_a, d_n, n_targets, st));
+  FF_TRY(ctx->cub_tmp.reserve(tmp));
+  FF_CUDA(cub::DeviceSelect::Unique(ctx->cub_tmp.p, tmp, d_b, d_a, d_n, n_targets, st));
+  uint64_t n_unique = 0;
+  FF_CUDA(cudaMemcpyAsync(&n_unique, d_n, 8, cudaMemcpyDeviceToHost, st));
+  FF_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_b); cudaFree(d_n);
+  const uint64_t family_every = n_unique > 4000 ? n_unique / 2000 : 0;
+  k_synth_counts<<<(unsigned int)((n_unique + 255) / 256), 256, 0, st>>>(n_unique, seed, family_every, d_a);
+  FF_CUDA(cudaStreamSynchronize(st));
+  FF_CUDA(cudaGetLastError());
+  db.pack = pack; db.bin_width = kPrefixBases; db.n_targets = n_unique; db.n_positions = 0;
+  db.d_targets = d_a;
+  int rc = db_build_index(ctx);
+  if (rc != FF_OK) db.release();
+  return rc;
+}
+
+}  // namespace ff

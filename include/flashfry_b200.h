@@ -1,0 +1,160 @@
+/*
+ * flashfry_b200.h -- C ABI of libflashfry_b200.so: FlashFry's off-target discovery + CFD / Hsu2013 scoring
+ * hot path on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference (mckennalab/FlashFry, Scala/JVM) has no FFI; the two seams
+ * this ABI replaces are
+ *   - trait Traverser.scan            src/main/scala/reference/traverser/Traverser.scala:52-59
+ *       (SeekTraverser.scan  reference/traverser/SeekTraverser.scala:58-104,
+ *        LinearTraverser.scan reference/traverser/LinearTraverser.scala:59-112; called from
+ *        modules/OffTargetDiscovery.scala:124,130)
+ *   - trait ScoreModel.scoreGuides    src/main/scala/scoring/ScoreModel.scala:31-89,113-132
+ *       (Doench2016CFDScore.scoreGuide scoring/Doench2016CFDScore.scala:53-88,
+ *        CrisprMitEduOffTarget.score_crispr scoring/CrisprMitEduOffTarget.scala:60-148; selected in
+ *        modules/ScoreResults.scala:159-226)
+ * INTEGRATION.md shows the JNI stub + Scala glue a FlashFry maintainer would add on top of these symbols.
+ *
+ * Conventions: every call returns 0 on success or a negative FF_E* code; ff_last_error() gives the message of
+ * the last failure on the calling thread.  No exceptions cross the boundary.  Plain pointers and sizes only.
+ * All pointers are HOST pointers unless the parameter name starts with d_ (device).  One ff_ctx is bound to one
+ * GPU and may be used by one host thread at a time; contexts are independent (one per GPU / per rank).
+ * There is no CPU fallback: without a CUDA device ff_create fails with FF_ENODEVICE.
+ */
+#ifndef FLASHFRY_B200_H
+#define FLASHFRY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FF_OK 0
+#define FF_EINVAL (-1)    /* bad argument (the reference would fail a require/assert) */
+#define FF_ENODEVICE (-2) /* no usable CUDA device */
+#define FF_ECUDA (-3)     /* CUDA runtime error, see ff_last_error() */
+#define FF_EIO (-4)       /* cannot read / parse the database or header */
+#define FF_EFORMAT (-5)   /* bad magic/version (BinaryHeader.scala:121-124) or invalid bin type (BlockManager.scala:85-87) */
+#define FF_ENODB (-6)     /* no database resident in the context */
+#define FF_EUNSUPPORTED (-7)
+#define FF_ENOMEM (-8)
+
+#define FF_METRIC_CFD 1u      /* Doench2016CFDScore: DoenchCFD_maxOT, DoenchCFD_specificityscore */
+#define FF_METRIC_HSU2013 2u  /* CrisprMitEduOffTarget: Hsu2013 */
+
+typedef struct ff_ctx ff_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int ff_create(ff_ctx **out, int device_id);
+void ff_destroy(ff_ctx *ctx);
+const char *ff_last_error(void);
+int ff_abi_version(void);
+/* Run the context's work on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL = the context's own
+ * stream).  Lets a host runtime (torch, JCuda ...) order/time the library's kernels with its own events. */
+int ff_set_stream(ff_ctx *ctx, void *cuda_stream);
+
+/* ---- database (replaces BinaryHeader.readHeader + the BGZF seek/inflate of SeekTraverser.fillBlock) ------ */
+/* Reads FlashFry's own on-disk format unchanged: BGZF body (reference/binary/DatabaseWriter.scala:78-97, both
+ * block types of reference/binary/blocks/BlockManager.scala:362-442) + text side-car
+ * (reference/binary/BinaryHeader.scala:115-160); inflates on host threads and makes it resident in HBM. */
+int ff_load_database(ff_ctx *ctx, const char *db_path, const char *header_path);
+/* Same residency from caller-provided arrays in database order (targets carry their 16-bit count; positions may be
+ * NULL).  contigs may be NULL.  Used by tests and by hosts that already hold the decoded blocks. */
+int ff_load_database_arrays(ff_ctx *ctx, int enzyme_index, int bin_width, const uint64_t *targets,
+                            uint64_t n_targets, const uint64_t *positions, uint64_t n_positions,
+                            const char *const *contigs, int n_contigs);
+/* Bench support: generate a synthetic spCas9-family database of ~n_targets distinct sorted targets directly in HBM
+ * (uniform random protospacer+N, PAM per enzyme, count model of SURVEY.md 8(d) cfg 3).  No positions. */
+int ff_synth_database(ff_ctx *ctx, int enzyme_index, uint64_t n_targets, uint64_t seed);
+
+typedef struct {
+  int enzyme_index;      /* standards/StandardScanParameters.scala:61-80 */
+  int bin_width;         /* header bin count = 4^bin_width (BinaryHeader.scala:131-132) */
+  int scan_len;          /* totalScanLength */
+  int pam_len;
+  int five_prime_pam;
+  uint64_t cmp_mask;     /* comparisonBitEncoding */
+  uint64_t n_targets;
+  uint64_t n_positions;  /* 0 when the image has no positions */
+  int n_contigs;
+  int sub_index_bases;   /* depth of the device-side sub-bin index below the bin prefix */
+  uint64_t device_bytes; /* HBM held by the resident image */
+} ff_db_info_t;
+int ff_db_info(const ff_ctx *ctx, ff_db_info_t *out);
+const char *ff_db_contig(const ff_ctx *ctx, int contig_id /* 1-based, BitPosition.scala:37-44 */);
+/* Copy targets[first, first+n) of the resident image back to the host (test/bench cross-checks). */
+int ff_db_copy_targets(ff_ctx *ctx, uint64_t first, uint64_t n, uint64_t *out);
+
+/* ---- discover (replaces Traverser.scan) ----------------------------------------------------------------- */
+/* CSR over guides, library-owned host memory (pinned), free with ff_hits_free.  Row g holds what the reference
+ * leaves in aggregator.wrappedGuides(g).otSite.offTargets: CRISPRHit(target long, positions) in DATABASE ORDER,
+ * truncated by the overflow rule "append while currentTotal < maximumOffTargets; currentTotal += count"
+ * (crispr/ResultsAggregator.scala:61-69, crispr/CRISPRSiteOT.scala:39-46). */
+typedef struct ff_hits {
+  int64_t n_guides;
+  int64_t n_hits;
+  const int64_t *row_ptr;      /* [n_guides+1] */
+  const uint64_t *targets;     /* [n_hits] target long incl. 16-bit count */
+  const uint8_t *mismatches;   /* [n_hits] == BitEncoding.mismatches(guide, target) (bitcoding/BitEncoding.scala:127-132) */
+  const int64_t *pos_ptr;      /* [n_hits+1] or NULL when positions were not requested / not resident */
+  const uint64_t *positions;   /* BitPosition longs (bitcoding/BitPosition.scala:51-92) */
+  const int32_t *total_count;  /* [n_guides] CRISPRSiteOT.currentTotal */
+  const uint8_t *overflowed;   /* [n_guides] CRISPRSiteOT.full -> "OVERFLOW" in the TSV */
+  uint64_t n_compares;         /* guide x target comparisons the kernels performed (for the log line of
+                                  modules/OffTargetDiscovery.scala:137; NOT equal to the reference's count: pruning differs) */
+  uint64_t n_candidate_hits;   /* hits before the overflow cut */
+  void *opaque;
+} ff_hits;
+
+/* guides: BitEncoding.bitEncodeString(bases, count = 1) longs in ResultsAggregator order (any order is accepted;
+ * rows come back in the same order).  max_mismatch >= 0, max_off_targets >= 0. */
+int ff_discover(ff_ctx *ctx, const uint64_t *guides, int64_t n_guides, int max_mismatch, int max_off_targets,
+                int want_positions, ff_hits **out);
+void ff_hits_free(ff_hits *hits);
+
+/* ---- score (replaces ScoreModel.scoreGuides for Doench2016CFDScore and CrisprMitEduOffTarget) ------------ */
+/* hits: row g = the off-targets of guides[g] (from ff_discover or re-read from a discover TSV; only n_guides,
+ * row_ptr and targets are read).  Outputs are [n_guides] (per_ot_cfd: [n_hits], NaN for on-target copies that
+ * Doench2016CFDScore.scala:67 skips); any output pointer may be NULL.  cfd_max already carries the 0.023
+ * threshold of :83-87.  Valid only for 23-bp Cas9 packs (validOverEnzyme); otherwise FF_EUNSUPPORTED and the
+ * host prints "NA" (scoring/ScoreModel.scala:125-128). */
+int ff_score(ff_ctx *ctx, const uint64_t *guides, const ff_hits *hits, uint32_t metrics, double *cfd_max,
+             double *cfd_specificity, double *hsu2013, double *per_ot_cfd);
+
+/* Fused discover + score: the hit list is scored while still in HBM, then both come back in one D2H. */
+int ff_discover_score(ff_ctx *ctx, const uint64_t *guides, int64_t n_guides, int max_mismatch, int max_off_targets,
+                      int want_positions, uint32_t metrics, ff_hits **out, double *cfd_max,
+                      double *cfd_specificity, double *hsu2013);
+
+/* ---- device-resident path (kernel-only timing, multi-GPU plumbing) --------------------------------------- */
+typedef struct {
+  int64_t n_guides;
+  int64_t n_hits;             /* after the overflow cut */
+  uint64_t n_candidate_hits;
+  uint64_t n_compares;
+  const int64_t *d_row_ptr;   /* device pointers owned by the context, valid until its next discover call */
+  const uint64_t *d_targets;
+  const uint8_t *d_mismatches;
+  const int32_t *d_total_count;
+  const uint8_t *d_overflowed;
+  const double *d_cfd_max, *d_cfd_specificity, *d_hsu2013; /* NULL unless metrics requested */
+} ff_device_result;
+/* d_guides already in HBM; results stay in HBM.  metrics may be 0. */
+int ff_discover_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mismatch,
+                       int max_off_targets, uint32_t metrics, ff_device_result *out);
+
+/* Device-time of the kernels of the last discover call on this context, from CUDA events recorded on the
+ * context's stream (ms).  scan = the bin-scan kernel (dominant), prep = guide sort/bucketing, order = hit sort,
+ * cut = overflow cut + gather, score = CFD/Hsu kernels, total = first to last event. */
+typedef struct {
+  float prep_ms, scan_ms, order_ms, cut_ms, score_ms, total_ms;
+  int scan_launches;          /* >1 when the hit buffer had to grow and the scan was repeated */
+  int kernel_launches;        /* kernels of this library launched by the call */
+  uint64_t scan_bytes_read;   /* algorithmic bytes of the scan kernel for this call */
+} ff_timings;
+int ff_last_timings(const ff_ctx *ctx, ff_timings *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLASHFRY_B200_H */

@@ -1,0 +1,249 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same inputs.
+Bit-exact for hit sets, database order, mismatch integers, overflow cut, positions; bit-exact doubles for the scorers
+(contract: 1e-6).  Run on the B200 box:  python -m pytest tests -m gpu -x -q
+"""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ff():
+    import flashfry_b200.api as api
+    return api
+
+
+@pytest.fixture(scope="module")
+def small_db(oracle, tmp_path_factory):
+    """A 400 kb random genome with a repeat family, indexed into FlashFry's own format by the oracle."""
+    d = tmp_path_factory.mktemp("smalldb")
+    contigs = helpers.random_genome(101, 200_000, repeat_unit=60, n_repeats=400, n_contigs=2)
+    fa = str(d / "genome.fa")
+    helpers.write_fasta(fa, contigs, lower_fraction=0.2)
+    dbp = str(d / "small_cas9ngg_database")
+    stats = oracle.build_database(fa, dbp, "spcas9ngg")
+    db = oracle.read_database(dbp)
+    return dbp, db, stats
+
+
+@pytest.fixture(scope="module")
+def small_ctx(ff, small_db):
+    ctx = ff.Context(0)
+    ctx.load_database(small_db[0])
+    yield ctx
+    ctx.close()
+
+
+def test_loader_reads_flashfry_format(small_ctx, small_db, oracle):
+    dbp, db, stats = small_db
+    info = small_ctx.info()
+    targets, bin_off, pos_off, positions = db.soa()
+    assert info.enzyme_index == 3 and info.scan_len == 23 and info.cmp_mask == 0x3FFFFFFFFFC0
+    assert info.n_targets == len(targets) == stats["targets"]
+    assert info.n_positions == len(positions) == stats["sites"]
+    assert (small_ctx.copy_targets() == targets).all()
+    assert small_ctx.contigs() == db.contigs == ["ctg1_test", "ctg2_test"]
+    assert stats["max_count"] > 100  # the repeat family made it in
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4, 5])
+def test_discover_matches_oracle_small(small_ctx, small_db, oracle, k):
+    _, db, _ = small_db
+    targets = db.soa()[0]
+    guides = np.concatenate([helpers.random_guides(oracle, db.pack, 7 + k, 150),
+                             helpers.planted_guides(db.pack, targets, 70 + k, 150, max_subs=5)])
+    ref = oracle.discover_blocks(db, guides, k, 2000)
+    got = small_ctx.discover(guides, k, 2000, positions=True)
+    helpers.assert_hits_equal(got, ref, check_positions=True)
+    if k >= 3:
+        assert int(ref.row_ptr[-1]) > 150
+
+
+@pytest.mark.parametrize("max_ot", [0, 1, 3, 50, 2000])
+def test_overflow_cut_matches_reference_rule(small_ctx, small_db, oracle, max_ot):
+    """Guides planted in the repeat family overflow; the kept list is the shortest database-order prefix whose
+    summed occurrence count reaches maximumOffTargets (ResultsAggregator.scala:61-69, CRISPRSiteOT.scala:39-46)."""
+    _, db, _ = small_db
+    targets = db.soa()[0]
+    heavy = targets[(targets >> np.uint64(48)) > 50]
+    assert len(heavy) > 10
+    guides = np.concatenate([helpers.planted_guides(db.pack, heavy, 5, 60, max_subs=2),
+                             helpers.planted_guides(db.pack, targets, 6, 60, max_subs=3)])
+    ref = oracle.discover_blocks(db, guides, 4, max_ot)
+    got = small_ctx.discover(guides, 4, max_ot, positions=True)
+    helpers.assert_hits_equal(got, ref, check_positions=True)
+    if 0 < max_ot <= 50:
+        assert ref.overflowed.sum() > 30
+        # a guide whose first hit alone exceeds the limit keeps exactly that hit
+        firsts = [g for g in range(len(guides)) if ref.row_ptr[g + 1] - ref.row_ptr[g] == 1 and ref.total_count[g] > max_ot]
+        assert len(firsts) > 0
+    if max_ot == 0:
+        assert int(got.row_ptr[-1]) == 0 and got.overflowed.all()
+
+
+def test_edge_cases(small_ctx, small_db, oracle):
+    _, db, _ = small_db
+    # empty guide list
+    got = small_ctx.discover(np.zeros(0, np.uint64), 4, 2000)
+    assert got.n_guides == 0 and len(got.targets) == 0
+    # duplicated guides each get their own identical row; a far-away guide gets an empty row
+    t = db.soa()[0]
+    g0 = (int(t[1234]) & 0xFFFFFFFFFFFF) | (1 << 48)
+    lonely = oracle.encode("ACGTACGTACGTACGTACGTAGG")
+    guides = np.asarray([g0, lonely, g0, g0], np.uint64)
+    ref = oracle.discover_blocks(db, guides, 2, 2000)
+    got = small_ctx.discover(guides, 2, 2000)
+    helpers.assert_hits_equal(got, ref)
+    assert (got.row(0)[0] == got.row(2)[0]).all() and int(got.row(0)[1].min()) == 0
+    # a single guide
+    one = small_ctx.discover(guides[:1], 4, 2000)
+    helpers.assert_hits_equal(one, oracle.discover_blocks(db, guides[:1], 4, 2000))
+
+
+def test_errors_are_loud(ff, tmp_path):
+    ctx = ff.Context(0)
+    with pytest.raises(ff.FlashFryError) as e:
+        ctx.discover(np.asarray([1 << 48], np.uint64))
+    assert e.value.code == -6  # FF_ENODB
+    bad = tmp_path / "bad.header"
+    bad.write_text("12345\n1\n3\n16384\n")
+    (tmp_path / "bad").write_bytes(b"")
+    with pytest.raises(ff.FlashFryError) as e:
+        ctx.load_database(str(tmp_path / "bad"), str(bad))
+    assert e.value.code == -5 and "magic number" in str(e.value)
+    with pytest.raises(ff.FlashFryError):
+        ctx.load_database(str(tmp_path / "missing"))
+    # unsorted arrays are rejected instead of silently mis-indexed
+    with pytest.raises(ff.FlashFryError):
+        ctx.load_database_arrays(3, np.asarray([(1 << 48) | 50, (1 << 48) | 40], np.uint64))
+    ctx.close()
+
+
+def test_arrays_loader_and_other_enzymes(ff, oracle, tmp_path):
+    """spCas9 (NGG+NAG) and the 19-mer pack (scan length 22) through the same kernels."""
+    for enzyme, seed in (("spcas9", 31), ("spcas9ngg19", 32), ("spcas9nag", 33)):
+        contigs = helpers.random_genome(seed, 120_000, repeat_unit=50, n_repeats=100)
+        fa = str(tmp_path / (enzyme + ".fa"))
+        helpers.write_fasta(fa, contigs)
+        dbp = str(tmp_path / (enzyme + "_db"))
+        oracle.build_database(fa, dbp, enzyme)
+        db = oracle.read_database(dbp)
+        targets, _bo, _po, positions = db.soa()
+        with ff.Context(0) as ctx:
+            ctx.load_database_arrays(db.pack.index, targets, positions, db.contigs)
+            guides = helpers.planted_guides(db.pack, targets, seed, 200, max_subs=4)
+            for k in (2, 4):
+                ref = oracle.discover_blocks(db, guides, k, 2000)
+                got = ctx.discover(guides, k, 2000, positions=True)
+                helpers.assert_hits_equal(got, ref, check_positions=True)
+
+
+def test_chr22_emx1_golden_tsv(ff, oracle, chr22_db_path, tmp_path):
+    """configs[0]: EMX1 vs the chr22 spCas9-NGG database -> the md5-pinned discover TSV, hits from the GPU."""
+    with ff.Context(0) as ctx:
+        ctx.load_database(chr22_db_path)
+        info = ctx.info()
+        assert info.n_targets == 4189398 and info.n_positions == 4966778
+        pack = oracle.PACK_BY_INDEX[info.enzyme_index]
+        guides = oracle.guides_from_fasta(os.path.join(GOLDEN, "EMX1_GAGTCCGAGCAGAAGAAGAAGGG.fasta"), pack, 6)
+        got = ctx.discover([g.encoding for g in guides], 4, 2000, positions=True)
+        out = tmp_path / "EMX1.output"
+        oracle.write_discover_tsv(str(out), pack, guides, got, ctx.contigs())
+        assert oracle.md5_file(str(out)) == "895e282bf486c359667e2c3e0e0e0260"
+        assert open(out).read() == open(os.path.join(GOLDEN, "EMX1.output")).read()
+        out2 = tmp_path / "EMX1.pos"
+        oracle.write_discover_tsv(str(out2), pack, guides, got, ctx.contigs(), with_positions=True)
+        assert open(out2).read() == open(os.path.join(GOLDEN, "EMX1.output.with_positions")).read()
+        # fused scores == the md5-pinned scored TSV columns
+        hits, cmax, cspec, hsu = ctx.discover_score([g.encoding for g in guides], 4, 2000)
+        lines = open(os.path.join(GOLDEN, "EMX1.output.scored")).read().strip().split("\n")
+        hdr = lines[0].split("\t")
+        rows = {r.split("\t")[3]: dict(zip(hdr, r.split("\t"))) for r in lines[1:]}
+        for i, g in enumerate(guides):
+            row = rows[g.site.bases]
+            assert oracle.java_double_str(cmax[i]) == row["DoenchCFD_maxOT"]
+            assert oracle.java_double_str(cspec[i]) == row["DoenchCFD_specificityscore"]
+            assert oracle.java_double_str(hsu[i]) == row["Hsu2013"]
+
+
+def test_chr22_1000_guides_config(ff, oracle, chr22_db_path):
+    """configs[1]: 1 000 synthetic (seed 1001) + 100 planted (seed 1002) guides vs chr22, <=4 mismatches."""
+    db = oracle.read_database(chr22_db_path)
+    targets, bin_off, _po, _pp = db.soa()
+    guides = np.concatenate([helpers.random_guides(oracle, db.pack, 1001, 1000),
+                             helpers.planted_guides(db.pack, targets, 1002, 100, max_subs=4)])
+    ref = oracle.discover_soa(db.pack, 7, targets, bin_off, guides, 4, 2000, n_threads=os.cpu_count() or 1)
+    with ff.Context(0) as ctx:
+        ctx.load_database(chr22_db_path)
+        got = ctx.discover(guides, 4, 2000)
+        helpers.assert_hits_equal(got, ref)
+        assert ref.overflowed.sum() >= 1 or int(ref.total_count.max()) > 100
+
+
+def test_scorers_bit_exact_on_fake_sites(ff, oracle):
+    """99 guides with real hg19 hit lists (test_data/fake.sites): CFD max / specificity / per-OT and Hsu2013 from the
+    GPU equal the oracle's doubles bit for bit (contract: 1e-6)."""
+    pack = oracle.pack_by_name("SPCAS9")
+    guides = oracle.read_discover_tsv(os.path.join(GOLDEN, "fake.sites.gz"), pack, filter_overflow=False)
+    enc = np.asarray([g.encoding for g in guides], np.uint64)
+    row_ptr, targets = [0], []
+    for g in guides:
+        targets += g.targets
+        row_ptr.append(len(targets))
+    with ff.Context(0) as ctx:
+        cmax, cspec, hsu, per = ctx.score(enc, row_ptr, targets)
+    t = np.asarray(targets, np.uint64)
+    for i, g in enumerate(guides):
+        ots = t[row_ptr[i]:row_ptr[i + 1]]
+        mx, sp, p = oracle.cfd_guide(g.encoding, ots)
+        hs = oracle.hsu_guide(pack, g.encoding, ots)
+        assert abs(cmax[i] - mx) <= 1e-6 and abs(cspec[i] - sp) <= 1e-6 and abs(hsu[i] - hs) <= 1e-6
+        assert cmax[i] == mx and cspec[i] == sp and hsu[i] == hs
+        got_p = per[row_ptr[i]:row_ptr[i + 1]]
+        assert ((got_p == p) | (np.isnan(got_p) & np.isnan(p))).all()
+
+
+def test_scorers_reference_unit_vectors(ff, oracle):
+    vec = json.load(open(os.path.join(GOLDEN, "reference_unit_vectors.json")))
+    with ff.Context(0) as ctx:
+        for case, exact in zip(vec["cfd_guides"], [0.0, 0.5238095242619047, 0.302521008307563]):
+            ots = [oracle.encode(s) for s in case["off_targets"]]
+            cmax, _sp, _h, _p = ctx.score([oracle.encode(case["guide"])], [0, len(ots)], ots)
+            assert abs(cmax[0] - case["expected_max"]) < 1e-3 and cmax[0] == exact
+        h = vec["hsu"]
+        ots = [oracle.encode(s) for s in h["off_targets"]]
+        _a, _b, hsu, _p = ctx.score([oracle.encode(h["guide"])], [0, len(ots)], ots)
+        assert abs(hsu[0] - 96.0) <= 1.0 and hsu[0] == 96.0618868577998
+        # guides with no off-targets: specificity 1.0, max 0.0, Hsu 100.0
+        cmax, cspec, hsu, _ = ctx.score([oracle.encode(h["guide"])], [0, 0], [])
+        assert (cmax[0], cspec[0], hsu[0]) == (0.0, 1.0, 100.0)
+
+
+def test_synthetic_database_properties(ff, oracle):
+    """The on-device generator used by bench.py: sorted, distinct, NGG, counts in range; discover on it agrees with the
+    oracle's reference-order walk over the same targets."""
+    with ff.Context(0) as ctx:
+        ctx.synth_database(3, 2_000_000, 3001)
+        info = ctx.info()
+        t = ctx.copy_targets()
+        assert len(t) == info.n_targets and 1_990_000 < len(t) <= 2_000_000
+        seq = t & np.uint64(0xFFFFFFFFFFFF)
+        assert (np.diff(seq.astype(np.int64)) > 0).all()
+        assert ((seq & np.uint64(0xF)) == 0xA).all()
+        cnt = (t >> np.uint64(48)).astype(np.int64)
+        assert cnt.min() >= 1 and cnt.max() <= 32767 and 0.92 < (cnt == 1).mean() < 0.96 and (cnt >= 500).sum() > 500
+        pack = oracle.PACK_BY_INDEX[3]
+        guides = np.concatenate([helpers.random_guides(oracle, pack, 3002, 300), helpers.planted_guides(pack, t, 3003, 100)])
+        bin_off = oracle.bin_offsets_from_sorted(pack, 7, t)
+        ref = oracle.discover_soa(pack, 7, t, bin_off, guides, 4, 2000, n_threads=os.cpu_count() or 1)
+        got = ctx.discover(guides, 4, 2000)
+        helpers.assert_hits_equal(got, ref)
+        assert ref.overflowed.sum() > 0
