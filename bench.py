@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""bench.py -- guides/sec of FlashFry's off-target discovery hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W]             # this repo's CUDA path
+    python bench.py --impl reference [...]                      # the reference's CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[2], named in config.workload): 100 000 synthetic 20-bp NGG guides (+10 % planted
+near real targets) against a synthetic human-genome-sized (3e8 distinct targets) spCas9-NGG index, <= 4 mismatches,
+maximumOffTargets 2000.  The index is generated in HBM from a seed (it would be ~5 GB on disk); one replica per GPU.
+A "step" = one discover call over one batch of guides per GPU; with N GPUs every rank processes its own batch
+(guide-sharded, no data-path collective) and the ranks all-gather the per-guide hit counts at the end of the step.
+
+`value`  : whole-job guides/s with guides already in HBM and results left in HBM (CUDA events, max over ranks).
+`e2e`    : the same metric through the C ABI with HOST buffers (ff_discover: H2D of the guides, D2H of the hit lists).
+`roofline`: the dominant kernel (k_scan) against the measured HBM copy bandwidth; see DESIGN.md section 4 for why the
+            100k-guide configuration is integer-pipe bound and what `roofline.streaming` (a 256-guide pass) shows.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_DB, SEED_GUIDES, SEED_PLANTED = 3001, 3002, 3003
+ENZYME = 3  # spCas9-NGG
+
+
+def make_guides(n, seed, planted_from=None, planted_seed=0, planted_frac=0.10):
+    """20 uniform bases + uniform N + GG, de-duplicated on the protospacer, count=1."""
+    rng = np.random.default_rng(seed)
+    n_pl = int(n * planted_frac) if planted_from is not None and len(planted_from) else 0
+    n_rand = n - n_pl
+    vals = np.zeros(0, np.uint64)
+    while len(vals) < n_rand:
+        v = rng.integers(0, 1 << 42, size=int((n_rand - len(vals)) * 1.05) + 16, dtype=np.uint64)
+        vals = np.concatenate([vals, v])
+        _, idx = np.unique(vals >> np.uint64(2), return_index=True)
+        vals = vals[np.sort(idx)]
+    g = (vals[:n_rand] << np.uint64(4)) | np.uint64(0xA)
+    if n_pl:
+        prng = np.random.default_rng(planted_seed)
+        t = planted_from[prng.integers(0, len(planted_from), n_pl)] & np.uint64(0xFFFFFFFFFFFF)
+        nsub = prng.integers(0, 5, n_pl)
+        for j in range(4):
+            pos = prng.integers(0, 20, n_pl)
+            x = prng.integers(1, 4, n_pl).astype(np.uint64) << (np.uint64(2) * (np.uint64(22) - pos.astype(np.uint64)))
+            t = np.where(nsub > j, t ^ x, t)
+        g = np.concatenate([g, t])
+        g = g[rng.permutation(len(g))]
+    return (g | (np.uint64(1) << np.uint64(48))).astype(np.uint64)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per k_scan launch from the committed ncu --set full summary, if one exists for this workload."""
+    p = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import flashfry_b200.api as ff
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    ctx = ff.Context(local)
+    t0 = time.perf_counter()
+    ctx.synth_database(ENZYME, args.targets, SEED_DB)
+    torch.cuda.synchronize()
+    db_s = time.perf_counter() - t0
+    info = ctx.info()
+    n_t = int(info.n_targets)
+    # planted guides are drawn from a few slices of the resident database
+    rng = np.random.default_rng(17)
+    slices = [ctx.copy_targets(int(s), 2048) for s in rng.integers(0, max(1, n_t - 2048), 16)]
+    pool = np.concatenate(slices)
+    guides = make_guides(args.guides, SEED_GUIDES + 1000 * rank, pool, SEED_PLANTED + rank)
+    G = len(guides)
+
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    d_guides = torch.from_numpy(guides.view(np.int64)).to(dev)
+    counts_all = torch.empty(world * G, dtype=torch.int32, device=dev) if world > 1 else None
+
+    class _DevView:  # wrap a context-owned device pointer for torch without copying
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+    def step():
+        r = ctx.discover_device(d_guides.data_ptr(), G, args.k, args.max_ot, 0)
+        if world > 1:  # the one collective of the path: every rank learns every guide's total count
+            mine = torch.as_tensor(_DevView(r.d_total_count, G), device=dev)
+            dist.all_gather_into_tensor(counts_all, mine)
+        return r
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        r = step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms, launches, cand, compares, scan_bytes = [], 0, 0, 0, 0
+    sync_all()
+    e0.record(stream)
+    for _ in range(args.steps):
+        r = step()
+        tm = ctx.timings()
+        scan_ms.append(tm.scan_ms); launches += tm.kernel_launches + (1 if world > 1 else 0)
+        cand, compares, scan_bytes = int(r.n_candidate_hits), int(r.n_compares), int(tm.scan_bytes_read)
+        scan_launches = tm.scan_launches
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    ms_per_step = ms / args.steps
+    value = world * G / (ms_per_step / 1e3)
+    n_hits = int(r.n_hits)
+
+    # ---- e2e through the C ABI with host buffers (H2D guides, D2H hit lists), same steps
+    pinned = torch.from_numpy(guides.view(np.int64)).pin_memory()
+    g_host = pinned.numpy().view(np.uint64)
+    import ctypes as C
+    from flashfry_b200 import _native as N
+    hp = C.POINTER(N.FFHits)()
+    gp = g_host.ctypes.data_as(C.POINTER(C.c_uint64))
+
+    def e2e_step():
+        N.check(N.lib().ff_discover(ctx._h, gp, G, args.k, args.max_ot, 0, C.byref(hp)))
+        nh = int(hp.contents.n_hits)
+        N.lib().ff_hits_free(hp)
+        return nh
+    for _ in range(max(1, args.warmup // 2 + 1)):
+        nh = e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nh = e2e_step()
+    sync_all()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e = {"value": world * G / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": 8 * G,
+           "d2h_bytes_per_step": (G + 1) * 8 + nh * 9 + G * 5, "ms_per_step": e2e_s * 1e3}
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        scan_avg_ms = float(np.mean(scan_ms))
+        achieved = scan_bytes / (scan_avg_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "alg_bytes_per_launch": scan_bytes, "kernel_ms": scan_avg_ms,
+                "kernel_share_of_step": scan_avg_ms / ms_per_step, "traffic": None,
+                "note": "100k guides per pass is integer-pipe bound (DESIGN.md s4); see compare_rate and streaming"}
+        tr = ncu_traffic()
+        if tr and tr.get("guides") == G and tr.get("targets") == n_t:
+            roof["traffic"] = tr.get("dram_bytes_per_launch")
+        roof["compare_rate"] = {"guide_target_compares_per_launch": compares, "per_s": compares / (scan_avg_ms / 1e3)}
+        # the HBM-streaming regime of the same kernel: one pass over the whole index for a 256-guide batch
+        small = d_guides[:256].contiguous()
+        for _ in range(3):
+            ctx.discover_device(small.data_ptr(), 256, args.k, args.max_ot, 0)
+        sm = []
+        for _ in range(10):
+            ctx.discover_device(small.data_ptr(), 256, args.k, args.max_ot, 0)
+            t = ctx.timings()
+            sm.append((t.scan_ms, t.scan_bytes_read))
+        s_ms = float(np.median([a for a, _ in sm]))
+        roof["streaming"] = {"guides": 256, "kernel_ms": s_ms, "alg_bytes": int(sm[0][1]),
+                             "achieved": sm[0][1] / (s_ms / 1e3) / 1e9, "frac": sm[0][1] / (s_ms / 1e3) / 1e9 / peak}
+        out = {"metric": "guides/sec at <=4 mismatches vs hg38-sized index", "value": value, "unit": "guides/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": value / 53.7, "dtype": "u64", "data": "synthetic",
+               "config": {"workload": "configs[2]: %d synthetic NGG guides per GPU (+10%% planted) vs synthetic %d-target spCas9-NGG index, "
+                                      "k<=%d, maxOT %d" % (G, n_t, args.k, args.max_ot),
+                          "guides_per_gpu": G, "targets": n_t, "max_mismatch": args.k, "maximum_off_targets": args.max_ot,
+                          "parallelism": "guide-sharded x%d, one index replica per GPU" % world,
+                          "l2": "index (%.1f GB) is larger than L2, re-streamed every step" % (info.device_bytes / 1e9),
+                          "sub_index_bases": int(info.sub_index_bases), "db_build_s": db_s},
+               "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+               "hits_per_step": n_hits, "candidate_hits_per_step": cand, "scan_launches_last_step": scan_launches,
+               "baseline_note": "vs_baseline = value / 53.7 guides/s (published single-core JVM, 100k guides, hg38, k<=4; BASELINE.md)"}
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(ctx, guides, args, threads=1, budget_guides=args.cpu_guides)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def cpu_baseline(ctx, guides, args, threads, budget_guides):
+    """The oracle's restatement of the reference loop order (bin -> 256 sub-bin filters -> target x guide), timed on
+    this box's host cores on a bounded sample of the same workload."""
+    from oracle import ff_oracle as o
+    pack = o.PACK_BY_INDEX[ENZYME]
+    t = ctx.copy_targets()
+    bin_off = o.bin_offsets_from_sorted(pack, 7, t)
+    sample = guides[:budget_guides]
+    t0 = time.perf_counter()
+    ref = o.discover_soa(pack, 7, t, bin_off, sample, args.k, args.max_ot, n_threads=threads)
+    dt = time.perf_counter() - t0
+    # the sample doubles as a parity check of the timed GPU path
+    got = ctx.discover(sample, args.k, args.max_ot)
+    ok = bool((got.row_ptr == ref.row_ptr).all() and (got.targets == ref.targets).all() and (got.mismatches == ref.mismatches).all()
+              and (got.overflowed == ref.overflowed).all())
+    return {"value": len(sample) / dt, "unit": "guides/s", "cores": threads, "kind": "port",
+            "sample": "%d of the %d guides vs the full %d-target index, oracle/ff_oracle.c ffo_discover_soa (C restatement of the "
+                      "reference loop order, not the JVM), %.1f s" % (len(sample), len(guides), len(t), dt),
+            "parity_with_gpu_on_sample": ok, "reference_compares": int(ref.n_compares)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the JVM cannot run here) on all host threads.
+    Needs the GPU only to materialise the same synthetic index the native arm uses."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import flashfry_b200.api as ff
+    from oracle import ff_oracle as o
+    threads = os.cpu_count() or 1
+    try:
+        ctx = ff.Context(int(os.environ.get("LOCAL_RANK", "0")))
+        ctx.synth_database(ENZYME, args.targets, SEED_DB)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"impl": "reference", "unavailable": "cannot materialise the synthetic index: %s" % e}))
+        return
+    t = ctx.copy_targets()
+    n_t = len(t)
+    rng = np.random.default_rng(17)
+    pool = np.concatenate([t[int(s):int(s) + 2048] for s in rng.integers(0, max(1, n_t - 2048), 16)])
+    guides = make_guides(args.guides, SEED_GUIDES, pool, SEED_PLANTED)
+    ctx.close()
+    pack = o.PACK_BY_INDEX[ENZYME]
+    bin_off = o.bin_offsets_from_sorted(pack, 7, t)
+    n = min(len(guides), args.ref_guides)
+    times = []
+    for i in range(args.warmup + args.steps):
+        sample = guides[(i * n) % max(1, len(guides) - n):][:n]
+        t0 = time.perf_counter()
+        o.discover_soa(pack, 7, t, bin_off, sample, args.k, args.max_ot, n_threads=threads)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = float(np.mean(times)) * 1e3
+    v = n / (ms / 1e3)
+    sample_txt = ("%d-guide batches of the same %d-guide workload vs the full %d-target index per step, oracle port of the "
+                  "reference loop order on %d host threads" % (n, len(guides), n_t, threads))
+    print(json.dumps({"impl": "reference", "metric": "guides/sec at <=4 mismatches vs hg38-sized index", "value": v, "unit": "guides/s",
+                      "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": v / 53.7, "dtype": "u64", "data": "synthetic",
+                      "config": {"workload": "configs[2] bounded sample: " + sample_txt, "targets": n_t, "max_mismatch": args.k,
+                                 "maximum_off_targets": args.max_ot},
+                      "cpu_baseline": {"value": v, "unit": "guides/s", "cores": threads, "kind": "port", "sample": sample_txt},
+                      "e2e": {"value": v, "unit": "guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--targets", type=int, default=300_000_000)
+    ap.add_argument("--guides", type=int, default=100_000)
+    ap.add_argument("--k", type=int, default=4)
+    ap.add_argument("--max-ot", dest="max_ot", type=int, default=2000)
+    ap.add_argument("--cpu-guides", type=int, default=512, help="guides in the cpu_baseline sample (single thread)")
+    ap.add_argument("--ref-guides", type=int, default=2048, help="guides per step of the --impl reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()
