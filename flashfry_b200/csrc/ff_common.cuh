@@ -54,7 +54,7 @@ int pack_from_index(int enzyme_index, Pack *out);  // StandardScanParameters.sca
 
 constexpr int kPrefixBases = 7;             // device-side first-level prefix (the reference's default bin width)
 constexpr int kNumBins = 1 << (2 * kPrefixBases);
-constexpr int kMaxSubBases = 6;
+constexpr int kMaxSubBases = 7;
 
 struct Database {
   bool resident = false;
@@ -69,6 +69,7 @@ struct Database {
   uint64_t *d_positions = nullptr; // [n_positions]
   uint16_t *d_mask7 = nullptr;     // 4^7 XOR masks sorted by Hamming distance (in bases)
   uint16_t *d_submask = nullptr;   // 4^s XOR masks sorted by Hamming distance
+  uint32_t *d_submask32 = nullptr; // the same, packed as mask | distance << 16
   int m7off[kPrefixBases + 2] = {0};   // m7off[d] .. m7off[d+1] = masks at distance exactly d
   int nsub[kMaxSubBases + 2] = {0};    // nsub[r] = # sub masks at distance <= r
   uint64_t device_bytes = 0;

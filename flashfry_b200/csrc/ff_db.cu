@@ -42,7 +42,7 @@ int pack_from_index(int idx, Pack *o) {
 
 void Database::release() {
   cudaFree(d_targets); cudaFree(d_tlow); cudaFree(d_sub_off); cudaFree(d_pos_off); cudaFree(d_positions);
-  cudaFree(d_mask7); cudaFree(d_submask);
+  cudaFree(d_mask7); cudaFree(d_submask); cudaFree(d_submask32);
   *this = Database();
 }
 
@@ -55,9 +55,9 @@ __global__ void k_low_words(const uint64_t *__restrict__ t, uint64_t n, uint32_t
 // strictly increasing over the 48 sequence bits?  (what makes database order == index order for 3'-PAM enzymes)
 __global__ void k_check_sorted(const uint64_t *__restrict__ t, uint64_t n, unsigned int *__restrict__ bad) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i == 0 || i >= n) return;
+  if (i >= n) return;
   const uint64_t m = 0xFFFFFFFFFFFFull;
-  if ((t[i - 1] & m) >= (t[i] & m)) atomicAdd(bad, 1u);
+  if (i > 0 && (t[i - 1] & m) >= (t[i] & m)) atomicAdd(bad, 1u);
   if ((t[i] >> 48) == 0 || (t[i] >> 63)) atomicAdd(bad + 1, 1u);
 }
 
@@ -99,7 +99,7 @@ static int choose_sub_bases(const Pack &pack, uint64_t n_targets) {
   // aim at <= ~4 targets per (7+s)-mer sub-bin
   int s = 0;
   double per = (double)n_targets / (double)kNumBins;
-  while (s < kMaxSubBases && per > 4.0) { per /= 4.0; ++s; }
+  while (s < 6 && per > 4.0) { per /= 4.0; ++s; }
   const int max_s = pack.scan_len - pack.pam_len - kPrefixBases - 1;  // leave at least one compared base below the sub key
   return std::min(s, std::max(0, max_s));
 }
@@ -164,6 +164,10 @@ int db_build_index(ff_ctx *ctx) {
   FF_CUDA(cudaMalloc(&db.d_submask, std::max<size_t>(ms.size(), 1) * 2));
   FF_CUDA(cudaMemcpyAsync(db.d_mask7, m7.data(), m7.size() * 2, cudaMemcpyHostToDevice, st));
   FF_CUDA(cudaMemcpyAsync(db.d_submask, ms.data(), ms.size() * 2, cudaMemcpyHostToDevice, st));
+  std::vector<uint32_t> ms32(ms.size());
+  for (size_t i = 0; i < ms.size(); ++i) ms32[i] = (uint32_t)ms[i] | ((uint32_t)base_distance(ms[i]) << 16);
+  FF_CUDA(cudaMalloc(&db.d_submask32, std::max<size_t>(ms32.size(), 1) * 4));
+  FF_CUDA(cudaMemcpyAsync(db.d_submask32, ms32.data(), ms32.size() * 4, cudaMemcpyHostToDevice, st));
   FF_CUDA(cudaStreamSynchronize(st));
   FF_CUDA(cudaGetLastError());
   db.resident = true;

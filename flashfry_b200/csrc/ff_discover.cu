@@ -20,6 +20,9 @@
 // Hits are emitted as (guide, target index) keys, radix-sorted, and cut per guide in database order.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "ff_common.cuh"
 #include "ff_kernels.cuh"
 
@@ -68,6 +71,11 @@ struct ScanParams {
   int k;                // max mismatches
   int sub_shift;        // bit offset of the sub key inside the low word
   uint32_t rem_mask;    // compared bits below the sub key (low word)
+  // staged kernel only
+  const uint32_t *submask32;  // sub masks sorted by distance: mask | distance << 16
+  int cap;                    // targets per staged segment
+  int n_tiles;                // 32-mask tiles over all distance classes 0..min(k,7)
+  int tile_start[kPrefixBases + 3];
 };
 
 constexpr int kScanThreads = 256;
@@ -78,7 +86,7 @@ __device__ __forceinline__ int base_dist16(uint32_t m) {  // # non-zero 2-bit di
   return __popc((m | (m >> 1)) & 0x55555555u);
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan(ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_direct(ScanParams p) {
   using BlockScan = cub::BlockScan<uint32_t, kScanThreads>;
   __shared__ typename BlockScan::TempStorage scan_tmp;
   __shared__ uint64_t s_list[kListCap];
@@ -179,6 +187,239 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(ScanParams p) {
   // one atomic per warp for the comparison counter
   for (int o = 16; o > 0; o >>= 1) my_compares += __shfl_down_sync(0xffffffffu, my_compares, o);
   if ((tid & 31) == 0 && my_compares) atomicAdd(p.n_compares, my_compares);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// v2: the same enumeration, with the bin's low words and its slice of the sub-bin index staged in shared memory.
+//
+// One CTA owns one 7-mer bin at a time (dynamic bin cursor).  Thread 0 arms an mbarrier and issues ONE bulk async copy
+// (cp.async.bulk global -> shared, the 1-D TMA path; SASS: UBLKCP) for the bin's low words while all threads stage the
+// bin's sub-bin offsets as 16-bit segment-relative values.  Bins larger than the staging buffer are walked in several
+// passes cut at sub-bin boundaries.  After that every lookup and every compare of the hot loop is an LDS.
+// Work inside the bin is split into tiles of 32 first-level masks handed to WARPS through a shared counter; a warp
+// expands its tile's guide ranges into a private list and enumerates (guide, sub mask) items on its own, so the main
+// loop has no block-wide barrier.  Hits are staged per warp and flushed with one global atomic per flush.
+constexpr int kStThreads = 512;
+constexpr int kStWarps = kStThreads / 32;
+constexpr int kLW = 32;  // list entries per warp
+constexpr int kHW = 32;  // staged hits per warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct WarpHits {
+  uint64_t *buf;          // this warp's staging slots (shared)
+  unsigned int *count;    // this warp's counter (shared)
+};
+
+__device__ __forceinline__ void emit_hit(const ScanParams &p, const WarpHits &wh, uint64_t key) {
+  const unsigned int slot = atomicAdd(wh.count, 1u);
+  if (slot < kHW) {
+    wh.buf[slot] = key;
+  } else {
+    const unsigned long long g = atomicAdd(p.hit_count, 1ull);
+    if (g < p.hit_cap) p.hits[g] = key;
+  }
+}
+
+__device__ __forceinline__ void flush_warp_hits(const ScanParams &p, const WarpHits &wh, int lane) {
+  __syncwarp();
+  const unsigned int nh = min(*wh.count, (unsigned int)kHW);
+  if (nh == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(p.hit_count, (unsigned long long)nh);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if ((unsigned int)lane < nh && base + lane < p.hit_cap) p.hits[base + lane] = wh.buf[lane];
+  __syncwarp();
+  if (lane == 0) *wh.count = 0;
+  __syncwarp();
+}
+
+// One (guide entry, sub mask) item.  STAGED: look up and compare in shared memory; otherwise straight from global.
+template <bool STAGED>
+__device__ __forceinline__ void scan_item(const ScanParams &p, const WarpHits &wh, uint64_t entry, uint32_t sm, int r,
+                                          uint32_t sub_key_mask, uint32_t sub_base, uint32_t sb, uint32_t nsb_pass,
+                                          uint32_t t0a, const uint32_t *__restrict__ s_tlow, const uint16_t *__restrict__ s_sub,
+                                          unsigned long long &compares) {
+  const uint32_t glow = (uint32_t)entry;
+  const int rem = r - (int)(sm >> 16);
+  const uint32_t sub = ((glow >> p.sub_shift) & sub_key_mask) ^ (sm & 0xFFFFu);
+  const uint32_t rel = sub - sb;
+  if (rel >= nsb_pass) return;  // sub-bin handled by another pass of this bin
+  uint32_t t0, t1;
+  if (STAGED) {
+    t0 = s_sub[rel];
+    t1 = s_sub[rel + 1];
+  } else {
+    t0 = p.sub_off[sub_base + sub];
+    t1 = p.sub_off[sub_base + sub + 1];
+  }
+  compares += t1 - t0;
+  for (uint32_t t = t0; t < t1; ++t) {
+    const uint32_t tl = STAGED ? s_tlow[t] : p.tlow[t];
+    const uint32_t x = (tl ^ glow) & p.rem_mask;
+    if (__popc((x | (x >> 1)) & 0x55555555u) <= rem)
+      emit_hit(p, wh, (entry & 0xFFFFFFFF00000000ull) | (STAGED ? t0a + t : t));
+  }
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void scan_pass_tiles(const ScanParams &p, const WarpHits &wh, int *s_tile, uint64_t *my_list, int b,
+                                                uint32_t sub_key_mask, uint32_t sub_base, uint32_t sb, uint32_t nsb_pass,
+                                                uint32_t t0a, const uint32_t *s_tlow, const uint16_t *s_sub, int lane,
+                                                unsigned long long &compares) {
+  for (;;) {
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(s_tile, 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= p.n_tiles) break;
+    int d = 0;
+    while (tile >= p.tile_start[d + 1]) ++d;
+    const int j = p.m7off[d] + (tile - p.tile_start[d]) * 32 + lane;
+    uint32_t lo = 0, cnt = 0;
+    if (j < p.m7off[d + 1]) {
+      const uint32_t nb = (uint32_t)b ^ p.mask7[j];
+      lo = p.goff[nb];
+      cnt = p.goff[nb + 1] - lo;
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    const uint32_t offs = incl - cnt;
+    const int r = p.k - d;
+    const uint32_t N = (uint32_t)p.nsub[min(r, p.s)];
+    const float inv_n = 1.0f / (float)N;
+    for (uint32_t c = 0; c < total; c += kLW) {
+      const uint32_t q0 = max(offs, c), q1 = min(offs + cnt, c + (uint32_t)kLW);
+      for (uint32_t q = q0; q < q1; ++q) my_list[q - c] = p.gentry[lo + (q - offs)];
+      __syncwarp();
+      const uint32_t n = min((uint32_t)kLW, total - c);
+      if (N >= 32) {
+        for (uint32_t e = 0; e < n; ++e) {
+          const uint64_t entry = my_list[e];
+          for (uint32_t i = lane; i < N; i += 32)
+            scan_item<STAGED>(p, wh, entry, p.submask32[i], r, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, compares);
+        }
+      } else {
+        const uint32_t items = n * N;
+        for (uint32_t item = lane; item < items; item += 32) {
+          const uint32_t e = (uint32_t)(((float)item + 0.5f) * inv_n);
+          const uint32_t i = item - e * N;
+          scan_item<STAGED>(p, wh, my_list[e], p.submask32[i], r, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, compares);
+        }
+      }
+      __syncwarp();
+      if (*wh.count >= kHW / 2) flush_warp_hits(p, wh, lane);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kStThreads, 2) k_scan_staged(ScanParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_tile, s_bin;
+  __shared__ unsigned int s_hitn[kStWarps];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nsb = 1u << (2 * p.s);
+  const uint32_t sub_key_mask = nsb - 1u;
+  uint32_t *s_tlow = reinterpret_cast<uint32_t *>(smem);
+  uint16_t *s_sub = reinterpret_cast<uint16_t *>(smem + (size_t)p.cap * 4);
+  const size_t sub_bytes = ((size_t)(nsb + 1) * 2 + 15) & ~(size_t)15;
+  uint64_t *s_list = reinterpret_cast<uint64_t *>(smem + (size_t)p.cap * 4 + sub_bytes);
+  uint64_t *s_hit = s_list + kStWarps * kLW;
+  WarpHits wh{s_hit + warp * kHW, &s_hitn[warp]};
+  uint64_t *my_list = s_list + warp * kLW;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (lane == 0) s_hitn[warp] = 0;
+  __syncthreads();
+
+  uint32_t parity = 0;
+  unsigned long long compares = 0;
+  for (;;) {
+    if (tid == 0) s_bin = (int)atomicAdd(p.bin_cursor, 1u);
+    __syncthreads();
+    const int b = s_bin;
+    if (b >= kNumBins) break;
+    const uint32_t sub_base = (uint32_t)b << (2 * p.s);
+    uint32_t sb = 0;
+    const uint32_t bin_t1 = p.sub_off[sub_base + nsb];
+    while (sb < nsb) {
+      // ---- choose the pass [sb, sb_end): as many whole sub-bins as fit the staging buffer
+      const uint32_t seg_t0 = p.sub_off[sub_base + sb];
+      if (seg_t0 == bin_t1) break;  // nothing left in this bin
+      const uint32_t t0a = seg_t0 & ~3u;  // 16-byte aligned source for the bulk copy
+      uint32_t sb_end = nsb;
+      if (bin_t1 - t0a > (uint32_t)p.cap) {
+        uint32_t lo = sb, hi = nsb;  // largest e with sub_off[e] - t0a <= cap
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi + 1) >> 1;
+          if (p.sub_off[sub_base + mid] - t0a <= (uint32_t)p.cap) lo = mid; else hi = mid - 1;
+        }
+        sb_end = lo;
+      }
+      const bool staged = sb_end > sb;
+      if (!staged) sb_end = sb + 1;  // a single sub-bin larger than the buffer: compare it straight from global
+      const uint32_t seg_t1 = p.sub_off[sub_base + sb_end];
+      const uint32_t nsb_pass = sb_end - sb;
+      __syncthreads();  // every warp is done with the previous pass's buffers (and has read s_bin)
+      if (staged) {
+        if (tid == 0) {
+          const uint32_t bytes = (((seg_t1 - t0a) * 4u) + 15u) & ~15u;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old pass before the async write
+          mbar_expect_tx(&s_bar, bytes);
+          bulk_g2s(s_tlow, p.tlow + t0a, bytes, &s_bar);
+        }
+        for (uint32_t q = tid; q <= nsb_pass; q += kStThreads) s_sub[q] = (uint16_t)(p.sub_off[sub_base + sb + q] - t0a);
+      }
+      if (tid == 0) s_tile = 0;
+      __syncthreads();
+      if (staged) {
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
+        scan_pass_tiles<true>(p, wh, &s_tile, my_list, b, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, lane, compares);
+      } else {
+        scan_pass_tiles<false>(p, wh, &s_tile, my_list, b, sub_key_mask, sub_base, sb, nsb_pass, 0u, nullptr, nullptr, lane, compares);
+      }
+      sb = sb_end;
+    }
+    __syncthreads();
+  }
+  flush_warp_hits(p, wh, lane);
+  for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
+  if (lane == 0 && compares) atomicAdd(p.n_compares, compares);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -329,6 +570,25 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   sp.s = db.sub_bases; sp.k = max_mm;
   sp.sub_shift = 2 * (db.pack.scan_len - kPrefixBases - db.sub_bases);
   sp.rem_mask = (uint32_t)(db.pack.cmp_mask & ((1ull << sp.sub_shift) - 1ull));
+  // staged kernel: tiles of 32 first-level masks per distance class, staging capacity from the shared-memory budget
+  sp.submask32 = db.d_submask32;
+  sp.tile_start[0] = 0;
+  {
+    const int dmax = max_mm < kPrefixBases ? max_mm : kPrefixBases;
+    for (int d = 0; d <= kPrefixBases + 1; ++d) {
+      const int n_masks = d <= dmax ? db.m7off[d + 1] - db.m7off[d] : 0;
+      sp.tile_start[d + 1] = sp.tile_start[d] + (n_masks + 31) / 32;
+    }
+    sp.n_tiles = sp.tile_start[dmax + 1];
+  }
+  const size_t sub_bytes = ((((size_t)1 << (2 * db.sub_bases)) + 1) * 2 + 15) & ~(size_t)15;
+  const size_t fixed_bytes = sub_bytes + (size_t)kStWarps * (kLW + kHW) * 8;
+  const size_t smem_budget = 113 * 1024;  // two CTAs per SM
+  sp.cap = (int)(((smem_budget - fixed_bytes) / 4) & ~(size_t)3);
+  const size_t staged_smem = (size_t)sp.cap * 4 + fixed_bytes;
+  bool staged_mode = true;
+  if (const char *e = getenv("FF_SCAN_MODE")) staged_mode = strcmp(e, "direct") != 0;
+  if (staged_mode) FF_CUDA(cudaFuncSetAttribute(k_scan_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem));
   unsigned long long *d_cnt = ctx->counters.as<unsigned long long>();  // [0] hits [1] compares [2] bin cursor
   sp.hit_count = d_cnt; sp.n_compares = d_cnt + 1; sp.bin_cursor = reinterpret_cast<unsigned int *>(d_cnt + 2);
   unsigned long long h_cnt[3] = {0, 0, 0};
@@ -340,7 +600,8 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
     sp.hits = ctx->hit_keys.as<uint64_t>(); sp.hit_cap = ctx->hit_cap;
     FF_CUDA(cudaMemsetAsync(d_cnt, 0, 32, st));
     if (G > 0) {
-      k_scan<<<grid, kScanThreads, 0, st>>>(sp);
+      if (staged_mode) k_scan_staged<<<2 * ctx->sm_count, kStThreads, staged_smem, st>>>(sp);
+      else k_scan_direct<<<grid, kScanThreads, 0, st>>>(sp);
       launches++;
       scan_launches++;
     }
