@@ -20,6 +20,7 @@
 // Hits are emitted as (guide, target index) keys, radix-sorted, and cut per guide in database order.
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -74,7 +75,8 @@ struct ScanParams {
   // staged kernel only
   const uint32_t *submask32;  // sub masks sorted by distance: mask | distance << 16
   int cap;                    // targets per staged segment
-  int n_tiles;                // 32-mask tiles over all distance classes 0..min(k,7)
+  int n_tiles;                // 32-mask tiles over the light distance classes heavy_classes..min(k,7)
+  int heavy_classes;          // classes 0..heavy_classes-1 have >= 32 sub masks per guide
   int tile_start[kPrefixBases + 3];
 };
 
@@ -289,14 +291,45 @@ __device__ __forceinline__ void scan_item(const ScanParams &p, const WarpHits &w
 template <bool STAGED>
 __device__ __forceinline__ void scan_pass_tiles(const ScanParams &p, const WarpHits &wh, int *s_tile, uint64_t *my_list, int b,
                                                 uint32_t sub_key_mask, uint32_t sub_base, uint32_t sb, uint32_t nsb_pass,
-                                                uint32_t t0a, const uint32_t *s_tlow, const uint16_t *s_sub, int lane,
+                                                uint32_t t0a, const uint32_t *s_tlow, const uint16_t *s_sub, int lane, int warp,
                                                 unsigned long long &compares) {
+  // ---- phase A: "heavy" distance classes (>= 32 sub masks per guide).  Few first-level masks, a lot of work per
+  // guide: every warp walks all of these masks and takes every kStWarps-th guide entry (static round-robin), the
+  // lanes stride over the guide's sub masks.
+  uint32_t pos = 0;  // running entry ordinal, identical in every warp
+  for (int d = 0; d < p.heavy_classes; ++d) {
+    const int r = p.k - d;
+    const uint32_t N = (uint32_t)p.nsub[min(r, p.s)];
+    const int m_end = p.m7off[d + 1];
+    for (int jb = p.m7off[d]; jb < m_end; jb += 32) {
+      uint32_t lo = 0, cnt = 0;
+      if (jb + lane < m_end) {
+        const uint32_t nb = (uint32_t)b ^ p.mask7[jb + lane];
+        lo = p.goff[nb];
+        cnt = p.goff[nb + 1] - lo;
+      }
+      const int nl = min(32, m_end - jb);
+      for (int l = 0; l < nl; ++l) {
+        const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), cnt_l = __shfl_sync(0xffffffffu, cnt, l);
+        for (uint32_t e = ((uint32_t)warp - pos) & (kStWarps - 1); e < cnt_l; e += kStWarps) {
+          const uint64_t entry = p.gentry[lo_l + e];
+          for (uint32_t i = lane; i < N; i += 32)
+            scan_item<STAGED>(p, wh, entry, p.submask32[i], r, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, compares);
+          __syncwarp();
+          if (*wh.count >= kHW / 2) flush_warp_hits(p, wh, lane);
+        }
+        pos += cnt_l;
+      }
+    }
+  }
+  // ---- phase B: "light" classes (< 32 sub masks per guide, many first-level masks): tiles of 32 masks handed out
+  // through a shared counter; a warp expands its tile's guide ranges into a private list and flattens guide x mask.
   for (;;) {
     int tile = 0;
     if (lane == 0) tile = atomicAdd(s_tile, 1);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= p.n_tiles) break;
-    int d = 0;
+    int d = p.heavy_classes;
     while (tile >= p.tile_start[d + 1]) ++d;
     const int j = p.m7off[d] + (tile - p.tile_start[d]) * 32 + lane;
     uint32_t lo = 0, cnt = 0;
@@ -322,19 +355,11 @@ __device__ __forceinline__ void scan_pass_tiles(const ScanParams &p, const WarpH
       for (uint32_t q = q0; q < q1; ++q) my_list[q - c] = p.gentry[lo + (q - offs)];
       __syncwarp();
       const uint32_t n = min((uint32_t)kLW, total - c);
-      if (N >= 32) {
-        for (uint32_t e = 0; e < n; ++e) {
-          const uint64_t entry = my_list[e];
-          for (uint32_t i = lane; i < N; i += 32)
-            scan_item<STAGED>(p, wh, entry, p.submask32[i], r, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, compares);
-        }
-      } else {
-        const uint32_t items = n * N;
-        for (uint32_t item = lane; item < items; item += 32) {
-          const uint32_t e = (uint32_t)(((float)item + 0.5f) * inv_n);
-          const uint32_t i = item - e * N;
-          scan_item<STAGED>(p, wh, my_list[e], p.submask32[i], r, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, compares);
-        }
+      const uint32_t items = n * N;
+      for (uint32_t item = lane; item < items; item += 32) {
+        const uint32_t e = (uint32_t)(((float)item + 0.5f) * inv_n);
+        const uint32_t i = item - e * N;
+        scan_item<STAGED>(p, wh, my_list[e], p.submask32[i], r, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, compares);
       }
       __syncwarp();
       if (*wh.count >= kHW / 2) flush_warp_hits(p, wh, lane);
@@ -409,9 +434,9 @@ __global__ void __launch_bounds__(kStThreads, 2) k_scan_staged(ScanParams p) {
       if (staged) {
         mbar_wait(&s_bar, parity);
         parity ^= 1u;
-        scan_pass_tiles<true>(p, wh, &s_tile, my_list, b, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, lane, compares);
+        scan_pass_tiles<true>(p, wh, &s_tile, my_list, b, sub_key_mask, sub_base, sb, nsb_pass, t0a, s_tlow, s_sub, lane, warp, compares);
       } else {
-        scan_pass_tiles<false>(p, wh, &s_tile, my_list, b, sub_key_mask, sub_base, sb, nsb_pass, 0u, nullptr, nullptr, lane, compares);
+        scan_pass_tiles<false>(p, wh, &s_tile, my_list, b, sub_key_mask, sub_base, sb, nsb_pass, 0u, nullptr, nullptr, lane, warp, compares);
       }
       sb = sb_end;
     }
@@ -572,10 +597,13 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   sp.rem_mask = (uint32_t)(db.pack.cmp_mask & ((1ull << sp.sub_shift) - 1ull));
   // staged kernel: tiles of 32 first-level masks per distance class, staging capacity from the shared-memory budget
   sp.submask32 = db.d_submask32;
-  sp.tile_start[0] = 0;
   {
     const int dmax = max_mm < kPrefixBases ? max_mm : kPrefixBases;
-    for (int d = 0; d <= kPrefixBases + 1; ++d) {
+    int dh = 0;
+    while (dh <= dmax && db.nsub[std::min(max_mm - dh, db.sub_bases)] >= 32) ++dh;
+    sp.heavy_classes = dh;
+    for (int d = 0; d <= kPrefixBases + 2; ++d) sp.tile_start[d] = 0;
+    for (int d = dh; d <= kPrefixBases + 1; ++d) {
       const int n_masks = d <= dmax ? db.m7off[d + 1] - db.m7off[d] : 0;
       sp.tile_start[d + 1] = sp.tile_start[d] + (n_masks + 31) / 32;
     }
