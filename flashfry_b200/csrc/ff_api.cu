@@ -164,7 +164,7 @@ void ff_destroy(ff_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->db.release();
-  DevBuf *bufs[] = {&c->guides, &c->gkeys, &c->gkeys_sorted, &c->gentry, &c->gentry_sorted, &c->goff, &c->cub_tmp, &c->hit_keys,
+  DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys,
                     &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->row_ptr, &c->total_count, &c->overflowed,
                     &c->out_targets, &c->out_mm, &c->out_tidx, &c->pos_cnt, &c->pos_ptr, &c->out_positions, &c->cfd_per_ot,
                     &c->hsu_per_ot, &c->cfd_max, &c->cfd_spec, &c->hsu, &c->scratch_guides};
@@ -214,7 +214,7 @@ int ff_db_info(const ff_ctx *c, ff_db_info_t *o) {
   const Database &d = c->db;
   o->enzyme_index = d.pack.enzyme_index; o->bin_width = d.bin_width; o->scan_len = d.pack.scan_len; o->pam_len = d.pack.pam_len;
   o->five_prime_pam = d.pack.five_prime; o->cmp_mask = d.pack.cmp_mask; o->n_targets = d.n_targets; o->n_positions = d.n_positions;
-  o->n_contigs = (int)d.contigs.size(); o->sub_index_bases = d.sub_bases; o->device_bytes = d.device_bytes;
+  o->n_contigs = (int)d.contigs.size(); o->sub_index_bases = d.A.key_bases; o->device_bytes = d.device_bytes;
   return FF_OK;
 }
 

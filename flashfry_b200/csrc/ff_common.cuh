@@ -52,26 +52,30 @@ struct Pack {
 };
 int pack_from_index(int enzyme_index, Pack *out);  // StandardScanParameters.scala:61-70
 
-constexpr int kPrefixBases = 7;             // device-side first-level prefix (the reference's default bin width)
-constexpr int kNumBins = 1 << (2 * kPrefixBases);
-constexpr int kMaxSubBases = 7;
+// One half of the seed index: targets ordered by `key` (a run of consecutive protospacer bases), the complementary
+// part of the protospacer stored next to it.
+struct SeedIndex {
+  int key_bases = 0;            // w: bases in the key
+  uint32_t *d_off = nullptr;    // [4^w + 1] first entry of every key
+  uint32_t *d_other = nullptr;  // [n + pad] the other part of the protospacer, right-aligned
+  uint32_t *d_canon = nullptr;  // [n] database-order index of every entry; nullptr when the order IS database order
+  uint32_t *d_masks = nullptr;  // [4^w] XOR masks sorted by Hamming distance (in bases): mask | distance << 24
+  int cum[16] = {0};            // cum[h] = # masks at distance <= h (h = 0..w)
+  void release();
+};
 
 struct Database {
   bool resident = false;
   Pack pack;
-  int bin_width = 7;         // of the file header; the device index always uses kPrefixBases
+  int bin_width = 7;            // of the file header (the device index does not use the file's bins)
   uint64_t n_targets = 0, n_positions = 0;
-  int sub_bases = 0;         // s: depth of the sub-bin index below the 7-mer
+  int proto_bases = 0;          // P: compared bases (popcount(cmp_mask) / 2)
+  int proto_shift = 0;          // bit offset of the protospacer inside the target long
   uint64_t *d_targets = nullptr;   // [n_targets] target longs, database order
-  uint32_t *d_tlow = nullptr;      // [n_targets + pad] low words (everything below the 7-mer prefix)
-  uint32_t *d_sub_off = nullptr;   // [4^(7+s) + 1] first target of every (7+s)-mer
   uint64_t *d_pos_off = nullptr;   // [n_targets + 1] exclusive scan of counts (only with positions)
   uint64_t *d_positions = nullptr; // [n_positions]
-  uint16_t *d_mask7 = nullptr;     // 4^7 XOR masks sorted by Hamming distance (in bases)
-  uint16_t *d_submask = nullptr;   // 4^s XOR masks sorted by Hamming distance
-  uint32_t *d_submask32 = nullptr; // the same, packed as mask | distance << 16
-  int m7off[kPrefixBases + 2] = {0};   // m7off[d] .. m7off[d+1] = masks at distance exactly d
-  int nsub[kMaxSubBases + 2] = {0};    // nsub[r] = # sub masks at distance <= r
+  SeedIndex A;                  // keyed by the first a protospacer bases, other = the last P-a bases
+  SeedIndex B;                  // keyed by the last P-a bases, other = the first a bases
   uint64_t device_bytes = 0;
   std::vector<std::string> contigs;
   void release();
@@ -88,7 +92,7 @@ struct ff_ctx {
   ff::Database db;
 
   // ---- per-call workspaces (grow-only) ----
-  ff::DevBuf guides, gkeys, gkeys_sorted, gentry, gentry_sorted, goff, cub_tmp;
+  ff::DevBuf cub_tmp;
   ff::DevBuf hit_keys, hit_keys_sorted, counters;
   ff::DevBuf seg_start, n_keep, row_ptr, total_count, overflowed, out_targets, out_mm, out_tidx;
   ff::DevBuf pos_cnt, pos_ptr, out_positions;

@@ -7,11 +7,14 @@
 //   Utils.byteArrayToLong                   utils/Utils.scala:167-186 (native = little-endian longs)
 //   block decoders                          reference/binary/blocks/BlockManager.scala:266-351
 //
-// HBM layout (all in database order, which for 3'-PAM enzymes is the lexicographic order of the target string):
-//   targets  u64[N_t]            the reference's target longs (2-bit bases in bits 0..47, occurrence count in 48..63)
-//   tlow     u32[N_t]            their low words = every base below the 7-mer prefix (+PAM): all the scan kernel reads
-//   sub_off  u32[4^(7+s)+1]      first target of every (7+s)-mer prefix; s is chosen from N_t so that a sub-bin holds
-//                                a handful of targets (s=6 at human-genome size, s=3 for chr22)
+// HBM layout:
+//   targets  u64[N_t]            the reference's target longs in DATABASE ORDER (2-bit bases in bits 0..47, occurrence
+//                                count in 48..63) -- read only for emitted hits
+//   seed index A                 entries ordered by the first a protospacer bases (for 3'-PAM enzymes that IS database
+//                                order): off u32[4^a+1], other u32[N_t] = the last P-a bases
+//   seed index B                 entries ordered by the last b = P-a bases: off u32[4^b+1], other u32[N_t] = the first a
+//                                bases, canon u32[N_t] = database-order index of every entry
+//   mask tables                  all XOR masks over a (resp. b) bases sorted by Hamming distance, mask | distance << 24
 //   pos_off  u64[N_t+1], positions u64[N_p]   only touched for emitted hits when positions are requested
 #include <cub/cub.cuh>
 #include <zlib.h>
@@ -40,35 +43,53 @@ int pack_from_index(int idx, Pack *o) {
   }
 }
 
+void SeedIndex::release() {
+  cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks);
+  *this = SeedIndex();
+}
+
 void Database::release() {
-  cudaFree(d_targets); cudaFree(d_tlow); cudaFree(d_sub_off); cudaFree(d_pos_off); cudaFree(d_positions);
-  cudaFree(d_mask7); cudaFree(d_submask); cudaFree(d_submask32);
+  cudaFree(d_targets); cudaFree(d_pos_off); cudaFree(d_positions);
+  A.release(); B.release();
   *this = Database();
 }
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_low_words(const uint64_t *__restrict__ t, uint64_t n, uint32_t *__restrict__ lo) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i < n) lo[i] = (uint32_t)t[i];
-}
-
-// strictly increasing over the 48 sequence bits?  (what makes database order == index order for 3'-PAM enzymes)
-__global__ void k_check_sorted(const uint64_t *__restrict__ t, uint64_t n, unsigned int *__restrict__ bad) {
+// strictly increasing over the 48 sequence bits?  (what makes database order == index-A order for 3'-PAM enzymes)
+__global__ void k_check_sorted(const uint64_t *__restrict__ t, uint64_t n, int check_order, unsigned int *__restrict__ bad) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t m = 0xFFFFFFFFFFFFull;
-  if (i > 0 && (t[i - 1] & m) >= (t[i] & m)) atomicAdd(bad, 1u);
+  if (check_order && i > 0 && (t[i - 1] & m) >= (t[i] & m)) atomicAdd(bad, 1u);
   if ((t[i] >> 48) == 0 || (t[i] >> 63)) atomicAdd(bad + 1, 1u);
 }
 
-// sub_off[j] = first target whose (7+s)-mer prefix >= j.  One thread per target boundary.
-__global__ void k_sub_offsets(const uint64_t *__restrict__ t, uint64_t n, int shift, uint32_t n_keys, uint32_t *__restrict__ off) {
+// split every protospacer into its first a bases (keyA) and its last b bases (keyB)
+__global__ void k_split_proto(const uint64_t *__restrict__ t, uint64_t n, int proto_shift, int b_bits, uint64_t proto_mask,
+                              uint32_t *__restrict__ key_a, uint32_t *__restrict__ key_b, uint32_t *__restrict__ iota) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i > n) return;
-  const uint64_t m = 0xFFFFFFFFFFFFull;
-  const int64_t prev = i == 0 ? -1 : (int64_t)((t[i - 1] & m) >> shift);
-  const int64_t cur = i == n ? (int64_t)n_keys : (int64_t)((t[i] & m) >> shift);
-  for (int64_t j = prev + 1; j <= cur; ++j) off[j] = (uint32_t)i;
+  if (i >= n) return;
+  const uint64_t proto = (t[i] >> proto_shift) & proto_mask;
+  key_a[i] = (uint32_t)(proto >> b_bits);
+  key_b[i] = (uint32_t)(proto & ((1ull << b_bits) - 1ull));
+  if (iota) iota[i] = (uint32_t)i;
+}
+
+__global__ void k_gather_u32(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint64_t n, uint32_t *__restrict__ dst) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+// off[j] = first entry whose key >= j, for j in [0, n_keys]; one thread per key (binary search over the sorted keys)
+__global__ void k_key_offsets(const uint32_t *__restrict__ sorted_keys, uint64_t n, uint32_t n_keys, uint32_t *__restrict__ off) {
+  uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (j > n_keys) return;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (sorted_keys[mid] < j) lo = mid + 1; else hi = mid;
+  }
+  off[j] = (uint32_t)lo;
 }
 
 __global__ void k_counts(const uint64_t *__restrict__ t, uint64_t n, uint64_t *__restrict__ c) {
@@ -79,29 +100,57 @@ __global__ void k_counts(const uint64_t *__restrict__ t, uint64_t n, uint64_t *_
 
 static int base_distance(uint32_t m) { return __builtin_popcount((m | (m >> 1)) & 0x55555555u); }
 
-// XOR masks over `bases` bases, sorted by (distance, value); off[d] = first mask at distance d, off[bases+1] = 4^bases
-static void make_masks(int bases, std::vector<uint16_t> *out, int *off) {
+// all XOR masks over `bases` bases sorted by (distance, value), packed mask | distance << 24; cum[h] = # masks with distance <= h
+static void make_masks(int bases, std::vector<uint32_t> *out, int *cum) {
   const uint32_t n = 1u << (2 * bases);
-  out->clear();
-  for (int d = 0; d <= bases; ++d) {
-    off[d] = (int)out->size();
-    for (uint32_t m = 0; m < n; ++m)
-      if (base_distance(m) == d) out->push_back((uint16_t)m);
+  std::vector<uint32_t> count(bases + 2, 0);
+  for (uint32_t m = 0; m < n; ++m) count[base_distance(m) + 1]++;
+  for (int d = 0; d <= bases; ++d) count[d + 1] += count[d];
+  for (int h = 0; h <= bases; ++h) cum[h] = (int)count[h + 1];
+  for (int h = bases + 1; h < 16; ++h) cum[h] = (int)n;
+  out->assign(n, 0);
+  std::vector<uint32_t> cursor(count.begin(), count.end() - 1);
+  for (uint32_t m = 0; m < n; ++m) {
+    const int d = base_distance(m);
+    (*out)[cursor[d]++] = m | ((uint32_t)d << 24);
   }
-  off[bases + 1] = (int)out->size();
 }
 
-static int choose_sub_bases(const Pack &pack, uint64_t n_targets) {
-  if (const char *e = getenv("FF_SUB_BASES")) {
-    int v = atoi(e);
-    if (v >= 0 && v <= kMaxSubBases) return v;
+static unsigned int nblk(uint64_t n) { return (unsigned int)((n + 255) / 256); }
+
+// Build one half of the seed index from per-target keys.  identity: entries stay in database order (keys must already be sorted).
+static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, const uint32_t *d_key, const uint32_t *d_other_src,
+                            const uint32_t *d_iota, uint64_t n, bool identity) {
+  cudaStream_t st = ctx->stream;
+  ix->key_bases = key_bases;
+  const uint32_t n_keys = 1u << (2 * key_bases);
+  FF_CUDA(cudaMalloc(&ix->d_off, ((size_t)n_keys + 1) * 4));
+  FF_CUDA(cudaMalloc(&ix->d_other, (n + 64) * 4));
+  FF_CUDA(cudaMemsetAsync(ix->d_other, 0xFF, (n + 64) * 4, st));
+  const uint32_t *sorted_keys = d_key;
+  uint32_t *d_sorted = nullptr;
+  if (identity) {
+    if (n) FF_CUDA(cudaMemcpyAsync(ix->d_other, d_other_src, n * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    FF_CUDA(cudaMalloc(&d_sorted, (n + 1) * 4));
+    FF_CUDA(cudaMalloc(&ix->d_canon, (n + 1) * 4));
+    size_t tmp = 0;
+    FF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_key, d_sorted, d_iota, ix->d_canon, n, 0, 2 * key_bases, st));
+    FF_TRY(ctx->cub_tmp.reserve(tmp));
+    FF_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, d_key, d_sorted, d_iota, ix->d_canon, n, 0, 2 * key_bases, st));
+    if (n) k_gather_u32<<<nblk(n), 256, 0, st>>>(d_other_src, ix->d_canon, n, ix->d_other);
+    sorted_keys = d_sorted;
   }
-  // aim at <= ~4 targets per (7+s)-mer sub-bin
-  int s = 0;
-  double per = (double)n_targets / (double)kNumBins;
-  while (s < 6 && per > 4.0) { per /= 4.0; ++s; }
-  const int max_s = pack.scan_len - pack.pam_len - kPrefixBases - 1;  // leave at least one compared base below the sub key
-  return std::min(s, std::max(0, max_s));
+  k_key_offsets<<<nblk((uint64_t)n_keys + 1), 256, 0, st>>>(sorted_keys, n, n_keys, ix->d_off);
+  std::vector<uint32_t> masks;
+  make_masks(key_bases, &masks, ix->cum);
+  FF_CUDA(cudaMalloc(&ix->d_masks, masks.size() * 4));
+  FF_CUDA(cudaMemcpyAsync(ix->d_masks, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice, st));
+  FF_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_sorted);
+  FF_CUDA(cudaGetLastError());
+  ctx->db.device_bytes += ((size_t)n_keys + 1) * 4 + (n + 64) * 4 + (identity ? 0 : (n + 1) * 4) + masks.size() * 4;
+  return FF_OK;
 }
 
 int db_build_index(ff_ctx *ctx) {
@@ -109,11 +158,12 @@ int db_build_index(ff_ctx *ctx) {
   cudaStream_t st = ctx->stream;
   const uint64_t n = db.n_targets;
   if (n >= 0xFFFFFFF0ull) { set_error("database too large for 32-bit target indices"); return FF_EUNSUPPORTED; }
-  if (!db.pack.five_prime) {
+  const bool sorted_db = !db.pack.five_prime;  // 3'-PAM: database order == lexicographic order of the target string
+  {
     unsigned int *d_bad = nullptr, h_bad[2] = {0, 0};
     FF_CUDA(cudaMalloc(&d_bad, 8));
     FF_CUDA(cudaMemsetAsync(d_bad, 0, 8, st));
-    if (n > 0) k_check_sorted<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(db.d_targets, n, d_bad);
+    if (n > 0) k_check_sorted<<<nblk(n), 256, 0, st>>>(db.d_targets, n, sorted_db ? 1 : 0, d_bad);
     FF_CUDA(cudaMemcpyAsync(h_bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_bad);
@@ -122,22 +172,30 @@ int db_build_index(ff_ctx *ctx) {
       return FF_EFORMAT;
     }
   }
-  db.sub_bases = db.pack.five_prime ? 0 : choose_sub_bases(db.pack, n);
-  const int s = db.sub_bases;
-  const uint32_t n_keys = 1u << (2 * (kPrefixBases + s));
-  FF_CUDA(cudaMalloc(&db.d_tlow, (n + 16) * 4));
-  FF_CUDA(cudaMalloc(&db.d_sub_off, ((size_t)n_keys + 1) * 4));
-  if (n > 0) k_low_words<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(db.d_targets, n, db.d_tlow);
-  if (!db.pack.five_prime) {
-    const int shift = 2 * (db.pack.scan_len - kPrefixBases - s);
-    k_sub_offsets<<<(unsigned int)((n + 1 + 255) / 256), 256, 0, st>>>(db.d_targets, n, shift, n_keys, db.d_sub_off);
-  }
-  db.device_bytes = n * 8 + (n + 16) * 4 + ((size_t)n_keys + 1) * 4;
+  // the compared bases: a contiguous run of P bases at bit proto_shift (every pack of StandardScanParameters.scala)
+  db.proto_bases = __builtin_popcountll(db.pack.cmp_mask) / 2;
+  db.proto_shift = __builtin_ctzll(db.pack.cmp_mask);
+  const int P = db.proto_bases;
+  int a = (P + 2) / 2;  // 11 | 9 for the 20-mers, 10 | 9 for the 19-mers
+  if (const char *e = getenv("FF_SPLIT_A")) { const int v = atoi(e); if (v >= 4 && v <= 12 && P - v >= 4 && P - v <= 12) a = v; }
+  const int b = P - a;
+  db.device_bytes = n * 8;
+
+  uint32_t *d_ka = nullptr, *d_kb = nullptr, *d_iota = nullptr;
+  FF_CUDA(cudaMalloc(&d_ka, (n + 1) * 4));
+  FF_CUDA(cudaMalloc(&d_kb, (n + 1) * 4));
+  FF_CUDA(cudaMalloc(&d_iota, (n + 1) * 4));
+  if (n) k_split_proto<<<nblk(n), 256, 0, st>>>(db.d_targets, n, db.proto_shift, 2 * b, (1ull << (2 * P)) - 1ull, d_ka, d_kb, d_iota);
+  int rc = build_seed_index(ctx, &db.A, a, d_ka, d_kb, d_iota, n, /*identity=*/sorted_db);
+  if (rc == FF_OK) rc = build_seed_index(ctx, &db.B, b, d_kb, d_ka, d_iota, n, /*identity=*/false);
+  cudaFree(d_ka); cudaFree(d_kb); cudaFree(d_iota);
+  FF_TRY(rc);
+
   if (db.d_positions) {
     FF_CUDA(cudaMalloc(&db.d_pos_off, (n + 1) * 8));
     uint64_t *d_c = nullptr;
     FF_CUDA(cudaMalloc(&d_c, (n + 1) * 8));
-    k_counts<<<(unsigned int)((n + 1 + 255) / 256), 256, 0, st>>>(db.d_targets, n, d_c);
+    k_counts<<<nblk(n + 1), 256, 0, st>>>(db.d_targets, n, d_c);
     size_t tmp = 0;
     FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_c, db.d_pos_off, n + 1, st));
     FF_TRY(ctx->cub_tmp.reserve(tmp));
@@ -152,23 +210,6 @@ int db_build_index(ff_ctx *ctx) {
     }
     db.device_bytes += (n + 1) * 8 + db.n_positions * 8;
   }
-  // mask tables
-  std::vector<uint16_t> m7, ms;
-  int off7[kPrefixBases + 2], offs[kMaxSubBases + 2];
-  make_masks(kPrefixBases, &m7, off7);
-  for (int i = 0; i < kPrefixBases + 2; ++i) db.m7off[i] = off7[i];
-  make_masks(s, &ms, offs);
-  for (int r = 0; r <= kMaxSubBases; ++r) db.nsub[r] = offs[std::min(r, s) + 1];
-  db.nsub[kMaxSubBases + 1] = offs[s + 1];
-  FF_CUDA(cudaMalloc(&db.d_mask7, m7.size() * 2));
-  FF_CUDA(cudaMalloc(&db.d_submask, std::max<size_t>(ms.size(), 1) * 2));
-  FF_CUDA(cudaMemcpyAsync(db.d_mask7, m7.data(), m7.size() * 2, cudaMemcpyHostToDevice, st));
-  FF_CUDA(cudaMemcpyAsync(db.d_submask, ms.data(), ms.size() * 2, cudaMemcpyHostToDevice, st));
-  std::vector<uint32_t> ms32(ms.size());
-  for (size_t i = 0; i < ms.size(); ++i) ms32[i] = (uint32_t)ms[i] | ((uint32_t)base_distance(ms[i]) << 16);
-  FF_CUDA(cudaMalloc(&db.d_submask32, std::max<size_t>(ms32.size(), 1) * 4));
-  FF_CUDA(cudaMemcpyAsync(db.d_submask32, ms32.data(), ms32.size() * 4, cudaMemcpyHostToDevice, st));
-  FF_CUDA(cudaStreamSynchronize(st));
   FF_CUDA(cudaGetLastError());
   db.resident = true;
   return FF_OK;
@@ -465,7 +506,7 @@ int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed) {
   k_synth_counts<<<(unsigned int)((n_unique + 255) / 256), 256, 0, st>>>(n_unique, seed, family_every, d_a);
   FF_CUDA(cudaStreamSynchronize(st));
   FF_CUDA(cudaGetLastError());
-  db.pack = pack; db.bin_width = kPrefixBases; db.n_targets = n_unique; db.n_positions = 0;
+  db.pack = pack; db.bin_width = 7; db.n_targets = n_unique; db.n_positions = 0;
   db.d_targets = d_a;
   int rc = db_build_index(ctx);
   if (rc != FF_OK) db.release();
