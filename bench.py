@@ -12,8 +12,9 @@ A "step" = one discover call over one batch of guides per GPU; with N GPUs every
 
 `value`  : whole-job guides/s with guides already in HBM and results left in HBM (CUDA events, max over ranks).
 `e2e`    : the same metric through the C ABI with HOST buffers (ff_discover: H2D of the guides, D2H of the hit lists).
-`roofline`: the dominant kernel (k_scan) against the measured HBM copy bandwidth; see DESIGN.md section 4 for why the
-            100k-guide configuration is integer-pipe bound and what `roofline.streaming` (a 256-guide pass) shows.
+`roofline`: the dominant kernel (k_seed_scan) against the measured HBM copy bandwidth.  Algorithmic bytes per launch =
+            for every (guide, seed) the two 4-byte index entries + 4 bytes per index entry streamed from the seed's
+            bucket + 8 bytes per guide + 8 bytes per candidate hit written.
 """
 import argparse
 import json
@@ -234,26 +235,14 @@ def run_native(args):
         peak, peak_src = measured_peak()
         scan_avg_ms = float(np.mean(scan_ms))
         achieved = scan_bytes / (scan_avg_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        roof = {"bound": "hbm", "kernel": "k_seed_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "alg_bytes_per_launch": scan_bytes, "kernel_ms": scan_avg_ms,
                 "kernel_share_of_step": scan_avg_ms / ms_per_step, "traffic": None,
-                "note": "100k guides per pass is integer-pipe bound (DESIGN.md s4); see compare_rate and streaming"}
+                "entries_streamed_per_launch": compares, "entries_per_guide": compares / max(G, 1)}
         tr = ncu_traffic()
         if tr and tr.get("guides") == G and tr.get("targets") == n_t:
             roof["traffic"] = tr.get("dram_bytes_per_launch")
-        roof["compare_rate"] = {"guide_target_compares_per_launch": compares, "per_s": compares / (scan_avg_ms / 1e3)}
-        # the HBM-streaming regime of the same kernel: one pass over the whole index for a 256-guide batch
-        small = d_guides[:256].contiguous()
-        for _ in range(3):
-            ctx.discover_device(small.data_ptr(), 256, args.k, args.max_ot, 0)
-        sm = []
-        for _ in range(10):
-            ctx.discover_device(small.data_ptr(), 256, args.k, args.max_ot, 0)
-            t = ctx.timings()
-            sm.append((t.scan_ms, t.scan_bytes_read))
-        s_ms = float(np.median([a for a, _ in sm]))
-        roof["streaming"] = {"guides": 256, "kernel_ms": s_ms, "alg_bytes": int(sm[0][1]),
-                             "achieved": sm[0][1] / (s_ms / 1e3) / 1e9, "frac": sm[0][1] / (s_ms / 1e3) / 1e9 / peak}
+            roof["traffic_source"] = tr.get("source")
         out = {"metric": "guides/sec at <=4 mismatches vs hg38-sized index", "value": value, "unit": "guides/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": value / 53.7, "dtype": "u64", "data": "synthetic",
@@ -262,7 +251,8 @@ def run_native(args):
                           "guides_per_gpu": G, "targets": n_t, "max_mismatch": args.k, "maximum_off_targets": args.max_ot,
                           "parallelism": "guide-sharded x%d, one index replica per GPU" % world,
                           "l2": "index (%.1f GB) is larger than L2, re-streamed every step" % (info.device_bytes / 1e9),
-                          "sub_index_bases": int(info.sub_index_bases), "db_build_s": db_s},
+                          "seed_split": "first %d | last %d protospacer bases" % (int(info.sub_index_bases), 20 - int(info.sub_index_bases)),
+                          "db_build_s": db_s},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
                "hits_per_step": n_hits, "candidate_hits_per_step": cand, "scan_launches_last_step": scan_launches,
                "baseline_note": "vs_baseline = value / 53.7 guides/s (published single-core JVM, 100k guides, hg38, k<=4; BASELINE.md)"}

@@ -103,18 +103,21 @@ __device__ __forceinline__ int base_dist32(uint32_t x) {  // # non-zero 2-bit di
 }
 
 // Compare one 128-bit chunk (4 entries starting at the 4-aligned index `base`) of a bucket [lo, hi).
-// PASS_B: accept only d1 > hA (pairs with d1 <= hA belong to pass A).
+// PASS_B: accept only d1 > hA (pairs with d1 <= hA belong to pass A).  The common case (no entry within budget) is
+// four XOR/fold/POPC and ONE branch; range checks and the emit sit behind it.
 template <bool PASS_B>
 __device__ __forceinline__ void verify_chunk(const ScanParams &p, const WarpHits &wh, const uint32_t *canon, uint4 v, uint32_t base,
                                              uint32_t lo, uint32_t hi, uint32_t probe, int budget, uint64_t guide_key) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const int d0 = base_dist32(v.x ^ probe), d1 = base_dist32(v.y ^ probe), d2 = base_dist32(v.z ^ probe), d3 = base_dist32(v.w ^ probe);
+  if (min(min(d0, d1), min(d2, d3)) <= budget) {
+    const int dd[4] = {d0, d1, d2, d3};
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t idx = base + c;
-    const int dd = base_dist32(w[c] ^ probe);
-    bool ok = dd <= budget && idx >= lo && idx < hi;
-    if (PASS_B) ok = ok && dd > p.hA;
-    if (ok) emit_hit(p, wh, guide_key | (canon ? canon[idx] : idx));
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t idx = base + c;
+      bool ok = dd[c] <= budget && idx >= lo && idx < hi;
+      if (PASS_B) ok = ok && dd[c] > p.hA;
+      if (ok) emit_hit(p, wh, guide_key | (canon ? canon[idx] : idx));
+    }
   }
 }
 
@@ -165,7 +168,10 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_seed_scan(ScanParams p) {
+#ifndef FF_SCAN_MIN_BLOCKS
+#define FF_SCAN_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_seed_scan(ScanParams p) {
   __shared__ uint64_t s_hits[kScanWarps * kHW];
   __shared__ unsigned int s_hitn[kScanWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
