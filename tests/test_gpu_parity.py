@@ -247,3 +247,113 @@ def test_synthetic_database_properties(ff, oracle):
         got = ctx.discover(guides, 4, 2000)
         helpers.assert_hits_equal(got, ref)
         assert ref.overflowed.sum() > 0
+
+
+CLI = os.path.join(os.path.dirname(GOLDEN), "..", "flashfry_b200", "flashfry_b200_cli")
+
+
+def test_cli_discover_and_score_reproduce_the_pinned_files(oracle, chr22_db_path, tmp_path):
+    """The drop-in CLI end to end on the quick-start data: `discover` output is byte-identical to the md5-pinned
+    EMX1.output (integration_test.sh:81); `score` reproduces every CFD / Hsu2013 / minot / dangerous column of the
+    md5-pinned EMX1.output.scored (:84) and the per-off-target CFD annotations of the --includeOTs flavour."""
+    import subprocess
+    fasta = os.path.join(GOLDEN, "EMX1_GAGTCCGAGCAGAAGAAGAAGGG.fasta")
+    out = str(tmp_path / "EMX1.output")
+    r = subprocess.run([CLI, "discover", "--database", chr22_db_path, "--fasta", fasta, "--output", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert oracle.md5_file(out) == "895e282bf486c359667e2c3e0e0e0260"
+    outp = str(tmp_path / "EMX1.output.with_positions")
+    r = subprocess.run([CLI, "discover", "-database", chr22_db_path, "-fasta", fasta, "-output", outp, "-positionOutput"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(outp).read() == open(os.path.join(GOLDEN, "EMX1.output.with_positions")).read()
+
+    scored = str(tmp_path / "EMX1.output.scored")
+    r = subprocess.run([CLI, "score", "--input", out, "--output", scored, "--scoringMetrics", "doench2016cfd,DanGerous,hsu2013,minot",
+                        "--database", chr22_db_path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+    def table(path):
+        lines = open(path).read().rstrip("\n").split("\n")
+        hdr = lines[0].split("\t")
+        return hdr, [dict(zip(hdr, ln.split("\t"))) for ln in lines[1:]]
+    ghdr, grows = table(os.path.join(GOLDEN, "EMX1.output.scored"))
+    hdr, rows = table(scored)
+    assert [c for c in ghdr if c != "Doench2014OnTarget"] == hdr  # same columns, same order, minus the out-of-scope metric
+    assert len(rows) == len(grows) == 3
+    for a, b in zip(rows, grows):
+        for c in hdr:
+            assert a[c] == b[c], c
+    with_ots = str(tmp_path / "EMX1.output.scored_with_ots")
+    r = subprocess.run([CLI, "score", "--input", out, "--output", with_ots, "--scoringMetrics", "doench2016cfd,dangerous,hsu2013,minot",
+                        "--database", chr22_db_path, "--includeOTs"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    _, wrows = table(with_ots)
+    _, gwrows = table(os.path.join(GOLDEN, "EMX1.output.scored_with_ots"))
+    for a, b in zip(wrows, gwrows):
+        assert a["offTargets"] == b["offTargets"] and a["otCount"] == b["otCount"]
+    # an out-of-scope metric is an error, not a silent skip
+    r = subprocess.run([CLI, "score", "--input", out, "--output", scored, "--scoringMetrics", "doench2014ontarget", "--database", chr22_db_path],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "outside the GPU hot path" in r.stderr
+
+
+def test_cpf1_five_prime_pam(ff, oracle, tmp_path):
+    """Cpf1 (TTTN 5' PAM, 24-base scan): database order is bin-major, not lexicographic, and blocks are always linear
+    (DatabaseWriter.scala:84-85); hits must still come back in database order."""
+    contigs = helpers.random_genome(77, 300_000, repeat_unit=70, n_repeats=150)
+    fa = str(tmp_path / "cpf1.fa")
+    helpers.write_fasta(fa, contigs)
+    dbp = str(tmp_path / "cpf1_db")
+    stats = oracle.build_database(fa, dbp, "cpf1")
+    db = oracle.read_database(dbp)
+    assert stats["indexed_bins"] == 0 and stats["targets"] > 3000
+    targets = db.soa()[0]
+    rng = np.random.default_rng(9)
+    planted = []
+    for _ in range(150):
+        t = int(targets[int(rng.integers(0, len(targets)))]) & 0xFFFFFFFFFFFF
+        for _ in range(int(rng.integers(0, 5))):
+            t ^= int(rng.integers(1, 4)) << (2 * int(rng.integers(0, 20)))
+        planted.append(t | (1 << 48))
+    guides = np.asarray(planted, np.uint64)
+    with ff.Context(0) as ctx:
+        ctx.load_database(dbp)
+        assert ctx.info().five_prime_pam == 1 and ctx.info().scan_len == 24
+        for k in (0, 2, 4):
+            ref = oracle.discover_blocks(db, guides, k, 2000)
+            got = ctx.discover(guides, k, 2000, positions=True)
+            helpers.assert_hits_equal(got, ref, check_positions=True)
+        assert int(ref.row_ptr[-1]) > 150
+        with pytest.raises(ff.FlashFryError) as e:   # CFD / Hsu2013 are Cas9-23 only -> host prints "NA"
+            ctx.score(guides[:1], [0, 0], [])
+        assert e.value.code == -7
+
+
+def test_large_k_and_many_guides_property(ff, oracle):
+    """Size-independent properties on a larger synthetic index: every reported hit really is within k mismatches, rows are
+    in strictly increasing database order, totals equal the summed counts, and the k=3 hit set is the subset of the
+    k=5 hit set with mm <= 3 (before the overflow cut bites)."""
+    with ff.Context(0) as ctx:
+        ctx.synth_database(3, 5_000_000, 77)
+        t = ctx.copy_targets()
+        pack = oracle.PACK_BY_INDEX[3]
+        guides = np.concatenate([helpers.random_guides(oracle, pack, 55, 3000), helpers.planted_guides(pack, t, 56, 1000)])
+        h5 = ctx.discover(guides, 5, 1_000_000)
+        h3 = ctx.discover(guides, 3, 1_000_000)
+        seq = t & np.uint64(0xFFFFFFFFFFFF)
+        mask = np.uint64(0x3FFFFFFFFFC0)
+        for h, k in ((h5, 5), (h3, 3)):
+            g_of_hit = np.repeat(np.arange(len(guides)), np.diff(h.row_ptr))
+            x = (h.targets ^ guides[g_of_hit]) & mask
+            y = (x | (x >> np.uint64(1))) & np.uint64(0x555555555555)
+            mm = np.asarray([bin(int(v)).count("1") for v in y[:20000]])
+            assert (mm == h.mismatches[:20000]).all() and int(h.mismatches.max()) <= k
+            idx = np.searchsorted(seq, h.targets & np.uint64(0xFFFFFFFFFFFF))
+            assert (t[idx] == h.targets).all()
+            same_row = g_of_hit[1:] == g_of_hit[:-1]
+            assert (np.diff(idx)[same_row] > 0).all()
+            tot = np.add.reduceat((h.targets >> np.uint64(48)).astype(np.int64), h.row_ptr[:-1][np.diff(h.row_ptr) > 0])
+            assert (tot == h.total_count[np.diff(h.row_ptr) > 0]).all()
+        keep = h5.mismatches <= 3
+        assert (h5.targets[keep] == h3.targets).all()
