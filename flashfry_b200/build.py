@@ -17,6 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libflashfry_b200.so")
 CLI = os.path.join(HERE, "flashfry_b200_cli")
+SELFTEST = os.path.join(HERE, "host_selftest")
 
 CU_SOURCES = ["ff_api.cu", "ff_db.cu", "ff_discover.cu", "ff_score.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -80,6 +81,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.exists("/usr/bin/g++"):
             gxx = "/usr/bin/g++"
         _run([gxx, "-O2", "-std=c++17", "-Wall", "-o", CLI, cli_src, "-I", os.path.join(HERE, "..", "include"),
+              "-L", HERE, "-lflashfry_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"], verbose)
+    st_src = os.path.join(CSRC, "host", "host_selftest.cpp")
+    if os.path.exists(st_src) and (force or _newer([st_src] + hdrs + [LIB], SELFTEST)):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+        _run([gxx, "-O2", "-std=c++17", "-Wall", "-o", SELFTEST, st_src, "-I", os.path.join(HERE, "..", "include"),
               "-L", HERE, "-lflashfry_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"], verbose)
     return LIB
 

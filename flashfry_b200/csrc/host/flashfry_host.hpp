@@ -500,8 +500,8 @@ struct TabDelimitedOutput {  // :104-160
 
   std::string hitToOutput(const CRISPRHit &hit, uint64_t guide) const {  // CRISPRHit.toOutput :54-101
     int count = 0;
-    std::string s = bitEncoding.bitDecodeString(hit.sequence, &count) + "_" + std::to_string(count) + "_" +
-                    std::to_string(bitEncoding.mismatches(guide, hit.sequence));
+    const std::string bases = bitEncoding.bitDecodeString(hit.sequence, &count);
+    std::string s = bases + "_" + std::to_string(count) + "_" + std::to_string(bitEncoding.mismatches(guide, hit.sequence));
     if (!writePositions) return s;
     if (hit.validOffTargetCoordinates && !hit.coordinates.empty()) {
       s += "<";
@@ -601,6 +601,13 @@ struct TabDelimitedInput {
             hit.coordinates.assign((size_t)cnt, 0);
             hit.validOffTargetCoordinates = false;
           }
+          const size_t lb = tokFull.find('{');  // :322-331 score pairs ride along
+          if (lb != std::string::npos)
+            for (auto &pair : split(tokFull.substr(lb + 1, tokFull.find('}') - lb - 1), '!')) {
+              const size_t eq = pair.find('=');
+              if (eq == std::string::npos) throw IllegalStateException("Score pairs should be key=value");
+              hit.scores.emplace_back(pair.substr(0, eq), pair.substr(eq + 1));
+            }
           if (!ot.full()) ot.addOT(std::move(hit));  // :311,:317
         }
       }

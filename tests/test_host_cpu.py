@@ -129,3 +129,51 @@ def test_guide_sharding_world2_gloo(tmp_path):
                         "--master-port", "29533", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+SELFTEST = os.path.join(ROOT, "flashfry_b200", "host_selftest")
+
+
+def test_host_mirror_tsv_round_trips(built, tmp_path):
+    """The C++ TabDelimitedInput/Output pair re-writes the reference's fixtures byte for byte
+    (TabDelimitedHanderTest.scala:40-51 on fake.sites; the md5-pinned EMX1 files)."""
+    import gzip
+    from conftest import GOLDEN
+    if not os.path.exists(SELFTEST):
+        pytest.skip("host_selftest not built")
+    fake = tmp_path / "fake.sites"
+    fake.write_bytes(gzip.open(os.path.join(GOLDEN, "fake.sites.gz")).read())
+    cases = [(2, str(fake), True), (3, os.path.join(GOLDEN, "EMX1.output"), False),
+             (3, os.path.join(GOLDEN, "EMX1.output.with_positions"), True),
+             (3, os.path.join(GOLDEN, "EMX1.output.scored_with_ots"), True)]
+    for enzyme, path, positions in cases:
+        out = tmp_path / "rt.tsv"
+        cmd = [SELFTEST, "roundtrip", str(enzyme), path, str(out)] + (["positions"] if positions else [])
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert out.read_bytes() == open(path, "rb").read(), path
+
+
+def test_host_mirror_site_finder_and_double_format(built, oracle, tmp_path):
+    """SimpleSiteFinder in C++ == the oracle's restatement on a random multi-contig FASTA (all six enzymes), and
+    javaDoubleToString == the oracle's Java formatting."""
+    import helpers
+    import numpy as np
+    if not os.path.exists(SELFTEST):
+        pytest.skip("host_selftest not built")
+    contigs = helpers.random_genome(12, 5000, n_contigs=3)
+    fa = tmp_path / "g.fa"
+    helpers.write_fasta(str(fa), contigs, lower_fraction=0.3)
+    for pack in oracle.PACKS.values():
+        r = subprocess.run([SELFTEST, "sites", str(pack.index), str(fa), "6"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = [ln.split("\t") for ln in r.stdout.strip().split("\n") if ln]
+        ref = oracle.find_target_sites(oracle.read_fasta(str(fa)), pack, 6)
+        assert len(got) == len(ref) and len(ref) > 10, pack.name
+        for g, s in zip(got, ref):
+            assert g == [s.contig, str(s.position), s.bases, "FWD" if s.forward else "RVS", s.context or "NONE"]
+    rng = np.random.default_rng(1)
+    xs = [0.0, 1.0, 100.0, 1e7, 9999999.999, 1e-3, 9.99e-4, 0.023, 0.16666666680238093, 98.41774847095192, 1.5e-10, 2e22, 123456789.125]
+    xs += list(rng.random(200)) + list(rng.random(50) * 1e-6) + list(rng.random(50) * 1e9)
+    r = subprocess.run([SELFTEST, "double"] + [repr(float(x)) for x in xs], capture_output=True, text=True)
+    assert r.stdout.strip().split("\n") == [oracle.java_double_str(float(x)) for x in xs]
