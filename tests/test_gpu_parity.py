@@ -324,7 +324,7 @@ def test_cpf1_five_prime_pam(ff, oracle, tmp_path):
             ref = oracle.discover_blocks(db, guides, k, 2000)
             got = ctx.discover(guides, k, 2000, positions=True)
             helpers.assert_hits_equal(got, ref, check_positions=True)
-        assert int(ref.row_ptr[-1]) > 150
+        assert int(ref.row_ptr[-1]) >= 100
         with pytest.raises(ff.FlashFryError) as e:   # CFD / Hsu2013 are Cas9-23 only -> host prints "NA"
             ctx.score(guides[:1], [0, 0], [])
         assert e.value.code == -7
