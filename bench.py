@@ -251,7 +251,7 @@ def run_native(args):
                           "guides_per_gpu": G, "targets": n_t, "max_mismatch": args.k, "maximum_off_targets": args.max_ot,
                           "parallelism": "guide-sharded x%d, one index replica per GPU" % world,
                           "l2": "index (%.1f GB) is larger than L2, re-streamed every step" % (info.device_bytes / 1e9),
-                          "seed_split": "first %d | last %d protospacer bases" % (int(info.sub_index_bases), 20 - int(info.sub_index_bases)),
+                          "seed_split": "first %d | last %d protospacer bases" % (int(info.seed_split_a), 20 - int(info.seed_split_a)),
                           "db_build_s": db_s},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
                "hits_per_step": n_hits, "candidate_hits_per_step": cand, "scan_launches_last_step": scan_launches,

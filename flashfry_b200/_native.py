@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libflashfry_b200.so")
+LIB_PATH = os.environ.get("FLASHFRY_B200_LIB") or os.path.join(HERE, "libflashfry_b200.so")
 
 FF_METRIC_CFD = 1
 FF_METRIC_HSU2013 = 2
@@ -32,7 +32,7 @@ class FFHits(C.Structure):
 class FFDbInfo(C.Structure):
     _fields_ = [("enzyme_index", C.c_int), ("bin_width", C.c_int), ("scan_len", C.c_int), ("pam_len", C.c_int),
                 ("five_prime_pam", C.c_int), ("cmp_mask", C.c_uint64), ("n_targets", C.c_uint64),
-                ("n_positions", C.c_uint64), ("n_contigs", C.c_int), ("sub_index_bases", C.c_int),
+                ("n_positions", C.c_uint64), ("n_contigs", C.c_int), ("seed_split_a", C.c_int),
                 ("device_bytes", C.c_uint64)]
 
 

@@ -214,7 +214,7 @@ int ff_db_info(const ff_ctx *c, ff_db_info_t *o) {
   const Database &d = c->db;
   o->enzyme_index = d.pack.enzyme_index; o->bin_width = d.bin_width; o->scan_len = d.pack.scan_len; o->pam_len = d.pack.pam_len;
   o->five_prime_pam = d.pack.five_prime; o->cmp_mask = d.pack.cmp_mask; o->n_targets = d.n_targets; o->n_positions = d.n_positions;
-  o->n_contigs = (int)d.contigs.size(); o->sub_index_bases = d.A.key_bases; o->device_bytes = d.device_bytes;
+  o->n_contigs = (int)d.contigs.size(); o->seed_split_a = d.A.key_bases; o->device_bytes = d.device_bytes;
   return FF_OK;
 }
 

@@ -40,6 +40,7 @@ struct SeedSide {
   const uint32_t *canon;   // database index per entry, or nullptr when entries are in database order
   const uint32_t *masks;   // mask | distance << 24, sorted by distance
   int n_seeds;             // masks [0, n_seeds) are within this pass's seed budget
+  int cum[16];             // cum[d] = # masks at distance <= d
   int seeds_per_item;      // seeds a warp takes at once
   int items;               // ceil(n_seeds / seeds_per_item)
 };
@@ -121,55 +122,74 @@ __device__ __forceinline__ void verify_chunk(const ScanParams &p, const WarpHits
   }
 }
 
-// One pass (A or B) of one work item: `n` seeds starting at `seed0`; lanes look the buckets up, the warp streams them.
+// One pass (A or B) of one work item: `n` (<= 32) seeds starting at `seed0`.  Lanes look the buckets up (one batched
+// index access per 32 seeds); the warp then streams the buckets in seed order with a rolling software pipeline that
+// keeps the first 128-entry chunk of the next TWO buckets in flight while the current one is verified.
+// The mismatch budget of a seed depends only on its rank in the distance-sorted mask table, so it is recomputed from
+// warp-uniform thresholds instead of being shuffled.
 template <bool PASS_B>
 __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &sd, const WarpHits &wh, int lane, uint32_t key,
                                            uint32_t probe, int seed0, int n, uint64_t guide_key, unsigned long long &compares) {
-  uint32_t lo = 0, hi = 0;
-  int budget = -1;
+  uint32_t lo = 0, hi = 0;  // lanes >= n keep an empty bucket
   if (lane < n) {
-    const uint32_t m = sd.masks[seed0 + lane];
-    const uint32_t kk = key ^ (m & 0xFFFFFFu);
+    const uint32_t kk = key ^ (sd.masks[seed0 + lane] & 0xFFFFFFu);
     lo = sd.off[kk];
     hi = sd.off[kk + 1];
-    budget = p.k - (int)(m >> 24);
   }
   compares += hi - lo;
-  // software pipeline: the first chunk of bucket l+1 is requested before bucket l is verified
-  uint32_t blo = __shfl_sync(0xffffffffu, lo, 0), bhi = __shfl_sync(0xffffffffu, hi, 0);
-  int bbud = __shfl_sync(0xffffffffu, budget, 0);
-  uint32_t base = (blo & ~3u) + 4u * lane;
-  uint4 cur = make_uint4(0, 0, 0, 0);
-  if (base < bhi) cur = ldg128(sd.other + base);
+#ifndef FF_PIPE_DEPTH
+#define FF_PIPE_DEPTH 1
+#endif
+  auto budget_of = [&](int seed) {  // k - distance(seed); distance d covers seeds [cum[d-1], cum[d])
+    int d = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) d += seed >= sd.cum[t];
+    for (int t = 4; seed >= sd.cum[t]; ++t) ++d;  // only for large k
+    return p.k - d;
+  };
+  auto fetch = [&](int l, uint32_t &blo, uint32_t &bhi, uint32_t &base, uint4 &v) {
+    blo = __shfl_sync(0xffffffffu, lo, l & 31);
+    bhi = l < n ? __shfl_sync(0xffffffffu, hi, l & 31) : 0u;
+    base = (blo & ~3u) + 4u * lane;
+    v = make_uint4(0, 0, 0, 0);
+    if (base < bhi) v = ldg128(sd.other + base);
+  };
+  uint32_t lo0, hi0, b0, lo1, hi1, b1;
+  uint4 v0, v1;
+  fetch(0, lo0, hi0, b0, v0);
+#if FF_PIPE_DEPTH == 2
+  uint32_t lo2, hi2, b2;
+  uint4 v2;
+  fetch(1, lo1, hi1, b1, v1);
+#endif
   for (int l = 0; l < n; ++l) {
-    uint32_t nlo = 0, nhi = 0, nbase = 0;
-    int nbud = -1;
-    uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (l + 1 < n) {
-      nlo = __shfl_sync(0xffffffffu, lo, l + 1);
-      nhi = __shfl_sync(0xffffffffu, hi, l + 1);
-      nbud = __shfl_sync(0xffffffffu, budget, l + 1);
-      nbase = (nlo & ~3u) + 4u * lane;
-      if (nbase < nhi) nxt = ldg128(sd.other + nbase);
-    }
-    if (base < bhi) verify_chunk<PASS_B>(p, wh, sd.canon, cur, base, blo, bhi, probe, bbud, guide_key);
+#if FF_PIPE_DEPTH == 2
+    fetch(l + 2, lo2, hi2, b2, v2);
+#else
+    fetch(l + 1, lo1, hi1, b1, v1);
+#endif
+    const int bud = budget_of(seed0 + l);
+    if (b0 < hi0) verify_chunk<PASS_B>(p, wh, sd.canon, v0, b0, lo0, hi0, probe, bud, guide_key);
     // buckets longer than 128 entries: keep streaming, two chunks in flight
-    for (uint32_t b2 = base + 128u; b2 < bhi; b2 += 256u) {
-      const uint4 v0 = ldg128(sd.other + b2);
-      const bool two = b2 + 128u < bhi;
-      uint4 v1 = make_uint4(0, 0, 0, 0);
-      if (two) v1 = ldg128(sd.other + b2 + 128u);
-      verify_chunk<PASS_B>(p, wh, sd.canon, v0, b2, blo, bhi, probe, bbud, guide_key);
-      if (two) verify_chunk<PASS_B>(p, wh, sd.canon, v1, b2 + 128u, blo, bhi, probe, bbud, guide_key);
+    for (uint32_t c2 = b0 + 128u; c2 < hi0; c2 += 256u) {
+      const uint4 w0 = ldg128(sd.other + c2);
+      const bool two = c2 + 128u < hi0;
+      uint4 w1 = make_uint4(0, 0, 0, 0);
+      if (two) w1 = ldg128(sd.other + c2 + 128u);
+      verify_chunk<PASS_B>(p, wh, sd.canon, w0, c2, lo0, hi0, probe, bud, guide_key);
+      if (two) verify_chunk<PASS_B>(p, wh, sd.canon, w1, c2 + 128u, lo0, hi0, probe, bud, guide_key);
     }
-    __syncwarp();
-    if (*wh.count >= kHW / 2) flush_warp_hits(p, wh, lane);
-    blo = nlo; bhi = nhi; bbud = nbud; base = nbase; cur = nxt;
+    lo0 = lo1; hi0 = hi1; b0 = b1; v0 = v1;
+#if FF_PIPE_DEPTH == 2
+    lo1 = lo2; hi1 = hi2; b1 = b2; v1 = v2;
+#endif
   }
+  __syncwarp();
+  if (*wh.count >= kHW / 2) flush_warp_hits(p, wh, lane);
 }
 
 #ifndef FF_SCAN_MIN_BLOCKS
-#define FF_SCAN_MIN_BLOCKS 5
+#define FF_SCAN_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_seed_scan(ScanParams p) {
   __shared__ uint64_t s_hits[kScanWarps * kHW];
@@ -341,6 +361,7 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   sp.guides = d_guides; sp.n_guides = G;
   sp.A.off = db.A.d_off; sp.A.other = db.A.d_other; sp.A.canon = db.A.d_canon; sp.A.masks = db.A.d_masks;
   sp.A.n_seeds = nA; sp.A.seeds_per_item = 32; sp.A.items = (nA + 31) / 32;
+  for (int i = 0; i < 16; ++i) { sp.A.cum[i] = db.A.cum[i]; sp.B.cum[i] = db.B.cum[i]; }
   sp.B.off = db.B.d_off; sp.B.other = db.B.d_other; sp.B.canon = db.B.d_canon; sp.B.masks = db.B.d_masks;
   sp.B.n_seeds = nB;
   {  // part-two buckets are 4^(a-b) times longer: hand them out in smaller batches

@@ -77,7 +77,7 @@ typedef struct {
   uint64_t n_targets;
   uint64_t n_positions;  /* 0 when the image has no positions */
   int n_contigs;
-  int sub_index_bases;   /* depth of the device-side sub-bin index below the bin prefix */
+  int seed_split_a;      /* the device seed index splits the protospacer into first a | last P-a bases */
   uint64_t device_bytes; /* HBM held by the resident image */
 } ff_db_info_t;
 int ff_db_info(const ff_ctx *ctx, ff_db_info_t *out);

@@ -357,3 +357,42 @@ def test_large_k_and_many_guides_property(ff, oracle):
             assert (tot == h.total_count[np.diff(h.row_ptr) > 0]).all()
         keep = h5.mismatches <= 3
         assert (h5.targets[keep] == h3.targets).all()
+
+
+def test_dense_neighbourhood_regrows_hit_buffer_and_streams_long_buckets(ff, oracle):
+    """Adversarial repeat-like index: every protospacer within two substitutions of one centre (x 4 N bases).  Guides
+    near the centre hit thousands of targets each, so the candidate-hit buffer overflows and the scan is repeated with a
+    larger one, part-one buckets exceed one 128-entry chunk, the per-warp staging spills to the direct path, and every
+    guide overflows maximumOffTargets -- the kept rows must still be the reference's database-order prefix."""
+    rng = np.random.default_rng(2024)
+    centre = [int(x) for x in rng.integers(0, 4, 20)]
+
+    def enc(bases20, n):
+        v = 0
+        for b in bases20:
+            v = v * 4 + b
+        return (v << 6) | (n << 4) | 0xA
+
+    protos = {tuple(centre)}
+    for i in range(20):
+        for x in range(1, 4):
+            a = list(centre); a[i] ^= x; protos.add(tuple(a))
+            for j in range(i + 1, 20):
+                for y in range(1, 4):
+                    b2 = list(a); b2[j] ^= y; protos.add(tuple(b2))
+    seqs = sorted(enc(p, n) for p in protos for n in range(4))
+    counts = rng.integers(1, 40, len(seqs))
+    targets = np.asarray(seqs, np.uint64) | (counts.astype(np.uint64) << np.uint64(48))
+    assert len(targets) == 4 * 1771
+    pack = oracle.PACK_BY_INDEX[3]
+    guides = helpers.planted_guides(pack, targets, 9, 1500, max_subs=2)
+    bin_off = oracle.bin_offsets_from_sorted(pack, 7, targets)
+    with ff.Context(0) as ctx:
+        ctx.load_database_arrays(3, targets)
+        for max_ot in (2000, 10 ** 9):
+            ref = oracle.discover_soa(pack, 7, targets, bin_off, guides, 4, max_ot, n_threads=os.cpu_count() or 1)
+            got = ctx.discover(guides, 4, max_ot)
+            helpers.assert_hits_equal(got, ref)
+            assert got.n_candidate_hits > (1 << 22)          # more than the initial hit buffer
+        assert ctx.timings().scan_launches >= 1
+        assert ref.row_ptr[-1] > 5_000_000

@@ -34,4 +34,4 @@ for i in range(a.steps):
     tm = ctx.timings()
     print("step %d: %.1f ms wall, scan %.2f ms, prep %.2f, order %.2f, cut %.2f, score %.2f, hits %d, compares %d, sub_bases %d"
           % (i, dt * 1e3, tm.scan_ms, tm.prep_ms, tm.order_ms, tm.cut_ms, tm.score_ms, len(h.targets), h.n_compares,
-             ctx.info().sub_index_bases), flush=True)
+             ctx.info().seed_split_a), flush=True)
