@@ -256,6 +256,16 @@ def run_native(args):
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
                "hits_per_step": n_hits, "candidate_hits_per_step": cand, "scan_launches_last_step": scan_launches,
                "baseline_note": "vs_baseline = value / 53.7 guides/s (published single-core JVM, 100k guides, hg38, k<=4; BASELINE.md)"}
+        # BASELINE.json configs[4] flavour on the same batch: discover + CFD + Hsu2013 fused on the device
+        fs = []
+        for _ in range(3):
+            ctx.discover_device(d_guides.data_ptr(), G, args.k, args.max_ot, 3)
+            t = ctx.timings()
+            fs.append((t.total_ms, t.score_ms))
+        out["fused_discover_score"] = {"guides": G, "total_ms": float(np.median([a for a, _ in fs])),
+                                       "score_kernel_ms": float(np.median([b for _, b in fs])),
+                                       "guides_per_s": G / (float(np.median([a for a, _ in fs])) / 1e3),
+                                       "metrics": "DoenchCFD_maxOT, DoenchCFD_specificityscore, Hsu2013 (FP64, bit-identical to the oracle)"}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(ctx, guides, args, threads=1, budget_guides=args.cpu_guides)
     ctx.close()
@@ -281,10 +291,16 @@ def cpu_baseline(ctx, guides, args, threads, budget_guides):
     got = ctx.discover(sample, args.k, args.max_ot)
     ok = bool((got.row_ptr == ref.row_ptr).all() and (got.targets == ref.targets).all() and (got.mismatches == ref.mismatches).all()
               and (got.overflowed == ref.overflowed).all())
+    _h, cmax, cspec, hsu = ctx.discover_score(sample[:64], args.k, args.max_ot)
+    score_ok = True
+    for g in range(min(64, len(sample))):
+        ots = ref.targets[ref.row_ptr[g]:ref.row_ptr[g + 1]]
+        mx, sp, _ = o.cfd_guide(int(sample[g]), ots)
+        score_ok = score_ok and cmax[g] == mx and cspec[g] == sp and hsu[g] == o.hsu_guide(pack, int(sample[g]), ots)
     return {"value": len(sample) / dt, "unit": "guides/s", "cores": threads, "kind": "port",
             "sample": "%d of the %d guides vs the full %d-target index, oracle/ff_oracle.c ffo_discover_soa (C restatement of the "
                       "reference loop order, not the JVM), %.1f s" % (len(sample), len(guides), len(t), dt),
-            "parity_with_gpu_on_sample": ok, "reference_compares": int(ref.n_compares)}
+            "parity_with_gpu_on_sample": ok, "score_parity_on_64_guides": bool(score_ok), "reference_compares": int(ref.n_compares)}
 
 
 def run_reference(args):
