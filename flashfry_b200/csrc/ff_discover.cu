@@ -65,29 +65,33 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kHW = 32;  // staged hits per warp
 
-struct WarpHits {
-  uint64_t *buf;        // this warp's staging slots (shared)
-  unsigned int *count;  // this warp's counter (shared)
+struct WarpHits {  // everything the (rare) emit path needs, passed by value so the out-of-line path takes no pointer to the params
+  uint64_t *buf;                 // this warp's staging slots (shared)
+  unsigned int *count;           // this warp's counter (shared)
+  uint64_t *hits;                // global candidate-hit buffer
+  unsigned long long *hit_count;
+  unsigned long long hit_cap;
+  int hA;
 };
 
-__device__ __forceinline__ void emit_hit(const ScanParams &p, const WarpHits &wh, uint64_t key) {
+__device__ __forceinline__ void emit_hit(const WarpHits &wh, uint64_t key) {
   const unsigned int slot = atomicAdd(wh.count, 1u);
   if (slot < kHW) {
     wh.buf[slot] = key;
   } else {  // staging full (a guide sitting in a repeat family): straight to global
-    const unsigned long long g = atomicAdd(p.hit_count, 1ull);
-    if (g < p.hit_cap) p.hits[g] = key;
+    const unsigned long long g = atomicAdd(wh.hit_count, 1ull);
+    if (g < wh.hit_cap) wh.hits[g] = key;
   }
 }
 
-__device__ __forceinline__ void flush_warp_hits(const ScanParams &p, const WarpHits &wh, int lane) {
+__device__ __forceinline__ void flush_warp_hits(const WarpHits &wh, int lane) {
   __syncwarp();
   const unsigned int nh = min(*wh.count, (unsigned int)kHW);
   if (nh == 0) return;
   unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(p.hit_count, (unsigned long long)nh);
+  if (lane == 0) base = atomicAdd(wh.hit_count, (unsigned long long)nh);
   base = __shfl_sync(0xffffffffu, base, 0);
-  if ((unsigned int)lane < nh && base + lane < p.hit_cap) p.hits[base + lane] = wh.buf[lane];
+  if ((unsigned int)lane < nh && base + lane < wh.hit_cap) wh.hits[base + lane] = wh.buf[lane];
   __syncwarp();
   if (lane == 0) *wh.count = 0;
   __syncwarp();
@@ -103,89 +107,84 @@ __device__ __forceinline__ int base_dist32(uint32_t x) {  // # non-zero 2-bit di
   return __popc((x | (x >> 1)) & 0x55555555u);
 }
 
-// Compare one 128-bit chunk (4 entries starting at the 4-aligned index `base`) of a bucket [lo, hi).
-// PASS_B: accept only d1 > hA (pairs with d1 <= hA belong to pass A).  The common case (no entry within budget) is
-// four XOR/fold/POPC and ONE branch; range checks and the emit sit behind it.
+// Compare one 128-bit chunk (4 entries starting at the 4-aligned index `base`) of a bucket [lo, hi): four
+// XOR / fold / POPC and ONE branch in the common case.  The rare path (some entry within budget) is a compact rolled
+// loop so that the hot loop stays small in the instruction cache: it applies the bucket-range check (the 16-byte
+// aligned chunk may straddle the neighbouring buckets) and, in pass B, the d1 > hA rule, then emits.
 template <bool PASS_B>
 __device__ __forceinline__ void verify_chunk(const ScanParams &p, const WarpHits &wh, const uint32_t *canon, uint4 v, uint32_t base,
                                              uint32_t lo, uint32_t hi, uint32_t probe, int budget, uint64_t guide_key) {
   const int d0 = base_dist32(v.x ^ probe), d1 = base_dist32(v.y ^ probe), d2 = base_dist32(v.z ^ probe), d3 = base_dist32(v.w ^ probe);
   if (min(min(d0, d1), min(d2, d3)) <= budget) {
-    const int dd[4] = {d0, d1, d2, d3};
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
+      const int dc = c == 0 ? d0 : c == 1 ? d1 : c == 2 ? d2 : d3;
       const uint32_t idx = base + c;
-      bool ok = dd[c] <= budget && idx >= lo && idx < hi;
-      if (PASS_B) ok = ok && dd[c] > p.hA;
-      if (ok) emit_hit(p, wh, guide_key | (canon ? canon[idx] : idx));
+      bool ok = dc <= budget && idx >= lo && idx < hi;
+      if (PASS_B) ok = ok && dc > wh.hA;
+      if (ok) emit_hit(wh, guide_key | (canon ? canon[idx] : idx));
     }
   }
 }
 
+#ifndef FF_GROUP
+#define FF_GROUP 4
+#endif
+
 // One pass (A or B) of one work item: `n` (<= 32) seeds starting at `seed0`.  Lanes look the buckets up (one batched
-// index access per 32 seeds); the warp then streams the buckets in seed order with a rolling software pipeline that
-// keeps the first 128-entry chunk of the next TWO buckets in flight while the current one is verified.
-// The mismatch budget of a seed depends only on its rank in the distance-sorted mask table, so it is recomputed from
-// warp-uniform thresholds instead of being shuffled.
+// index access per 32 seeds); the warp then streams the buckets FF_GROUP at a time: the first 128-entry chunk of every
+// bucket of the group is requested back to back before any of them is verified, so each lane keeps FF_GROUP 128-bit
+// loads in flight (tools/gather_bw.cu: random 288-byte runs reach 2.4 TB/s with one load in flight per warp, 4.3 TB/s
+// with four).
 template <bool PASS_B>
 __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &sd, const WarpHits &wh, int lane, uint32_t key,
                                            uint32_t probe, int seed0, int n, uint64_t guide_key, unsigned long long &compares) {
   uint32_t lo = 0, hi = 0;  // lanes >= n keep an empty bucket
+  int budget = -1;
   if (lane < n) {
-    const uint32_t kk = key ^ (sd.masks[seed0 + lane] & 0xFFFFFFu);
+    const uint32_t m = sd.masks[seed0 + lane];
+    const uint32_t kk = key ^ (m & 0xFFFFFFu);
     lo = sd.off[kk];
     hi = sd.off[kk + 1];
+    budget = p.k - (int)(m >> 24);
   }
   compares += hi - lo;
-#ifndef FF_PIPE_DEPTH
-#define FF_PIPE_DEPTH 1
-#endif
-  auto budget_of = [&](int seed) {  // k - distance(seed); distance d covers seeds [cum[d-1], cum[d])
-    int d = 0;
+  static_assert(32 % FF_GROUP == 0, "a group must not wrap around the warp");
+  const uint32_t lane4 = 4u * lane;
+  for (int l0 = 0; l0 < n; l0 += FF_GROUP) {
+    uint32_t blo[FF_GROUP], bhi[FF_GROUP];
+    uint4 v[FF_GROUP];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) d += seed >= sd.cum[t];
-    for (int t = 4; seed >= sd.cum[t]; ++t) ++d;  // only for large k
-    return p.k - d;
-  };
-  auto fetch = [&](int l, uint32_t &blo, uint32_t &bhi, uint32_t &base, uint4 &v) {
-    blo = __shfl_sync(0xffffffffu, lo, l & 31);
-    bhi = l < n ? __shfl_sync(0xffffffffu, hi, l & 31) : 0u;
-    base = (blo & ~3u) + 4u * lane;
-    v = make_uint4(0, 0, 0, 0);
-    if (base < bhi) v = ldg128(sd.other + base);
-  };
-  uint32_t lo0, hi0, b0, lo1, hi1, b1;
-  uint4 v0, v1;
-  fetch(0, lo0, hi0, b0, v0);
-#if FF_PIPE_DEPTH == 2
-  uint32_t lo2, hi2, b2;
-  uint4 v2;
-  fetch(1, lo1, hi1, b1, v1);
-#endif
-  for (int l = 0; l < n; ++l) {
-#if FF_PIPE_DEPTH == 2
-    fetch(l + 2, lo2, hi2, b2, v2);
-#else
-    fetch(l + 1, lo1, hi1, b1, v1);
-#endif
-    const int bud = budget_of(seed0 + l);
-    if (b0 < hi0) verify_chunk<PASS_B>(p, wh, sd.canon, v0, b0, lo0, hi0, probe, bud, guide_key);
-    // buckets longer than 128 entries: keep streaming, two chunks in flight
-    for (uint32_t c2 = b0 + 128u; c2 < hi0; c2 += 256u) {
-      const uint4 w0 = ldg128(sd.other + c2);
-      const bool two = c2 + 128u < hi0;
-      uint4 w1 = make_uint4(0, 0, 0, 0);
-      if (two) w1 = ldg128(sd.other + c2 + 128u);
-      verify_chunk<PASS_B>(p, wh, sd.canon, w0, c2, lo0, hi0, probe, bud, guide_key);
-      if (two) verify_chunk<PASS_B>(p, wh, sd.canon, w1, c2 + 128u, lo0, hi0, probe, bud, guide_key);
+    for (int j = 0; j < FF_GROUP; ++j) {  // lanes beyond n hold empty buckets, so l0 + j (< 32) needs no bound check
+      blo[j] = __shfl_sync(0xffffffffu, lo, l0 + j);
+      bhi[j] = __shfl_sync(0xffffffffu, hi, l0 + j);
+      v[j] = make_uint4(0, 0, 0, 0);
+      if ((blo[j] & ~3u) + lane4 < bhi[j]) v[j] = ldg128(sd.other + (blo[j] & ~3u) + lane4);
     }
-    lo0 = lo1; hi0 = hi1; b0 = b1; v0 = v1;
-#if FF_PIPE_DEPTH == 2
-    lo1 = lo2; hi1 = hi2; b1 = b2; v1 = v2;
-#endif
+#pragma unroll
+    for (int j = 0; j < FF_GROUP; ++j) {
+      const int bud = __shfl_sync(0xffffffffu, budget, l0 + j);
+      const uint32_t base = (blo[j] & ~3u) + lane4;
+      if (base < bhi[j]) verify_chunk<PASS_B>(p, wh, sd.canon, v[j], base, blo[j], bhi[j], probe, bud, guide_key);
+    }
+    // buckets longer than 128 entries (pass B, repeat-rich part-one keys): stream the rest, two chunks in flight
+#pragma unroll 1
+    for (int j = 0; j < FF_GROUP; ++j) {
+      const uint32_t jlo = __shfl_sync(0xffffffffu, lo, l0 + j), jhi = __shfl_sync(0xffffffffu, hi, l0 + j);
+      if (jhi - (jlo & ~3u) <= 128u) continue;  // warp-uniform
+      const int bud = __shfl_sync(0xffffffffu, budget, l0 + j);
+      for (uint32_t c2 = (jlo & ~3u) + lane4 + 128u; c2 < jhi; c2 += 256u) {
+        const uint4 w0 = ldg128(sd.other + c2);
+        const bool two = c2 + 128u < jhi;
+        uint4 w1 = make_uint4(0, 0, 0, 0);
+        if (two) w1 = ldg128(sd.other + c2 + 128u);
+        verify_chunk<PASS_B>(p, wh, sd.canon, w0, c2, jlo, jhi, probe, bud, guide_key);
+        if (two) verify_chunk<PASS_B>(p, wh, sd.canon, w1, c2 + 128u, jlo, jhi, probe, bud, guide_key);
+      }
+    }
   }
   __syncwarp();
-  if (*wh.count >= kHW / 2) flush_warp_hits(p, wh, lane);
+  if (*wh.count >= kHW / 2) flush_warp_hits(wh, lane);
 }
 
 #ifndef FF_SCAN_MIN_BLOCKS
@@ -195,7 +194,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_seed_scan(
   __shared__ uint64_t s_hits[kScanWarps * kHW];
   __shared__ unsigned int s_hitn[kScanWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp]};
+  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, p.hA};
   if (lane == 0) s_hitn[warp] = 0;
   __syncwarp();
   unsigned long long compares = 0;
@@ -218,7 +217,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_seed_scan(
       scan_seeds<true>(p, p.B, wh, lane, key_b, key_a, seed0, min(p.B.seeds_per_item, p.B.n_seeds - seed0), guide_key, compares);
     }
   }
-  flush_warp_hits(p, wh, lane);
+  flush_warp_hits(wh, lane);
   for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
   if (lane == 0 && compares) atomicAdd(p.n_compares, compares);
 }
