@@ -24,6 +24,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -375,7 +376,16 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   // ---- scan (repeated once with a larger buffer if the hit buffer overflowed)
   if (ctx->hit_cap == 0) ctx->hit_cap = 1u << 22;
   {
-    size_t want = (size_t)G * 192;  // ~116 expected hits per random guide at k=4 on a human-sized index
+    // expected candidates per random guide = N x P(a random P-mer is within k) (116 at k = 4 on a human-sized index);
+    // start with 1.4x that (+ slack), never more than 2^28 keys up front -- the scan is repeated if it was not enough
+    double prob = 0.0, term = 1.0;  // term = C(P, i) 3^i
+    for (int i = 0; i <= k_eff; ++i) {
+      prob += term;
+      term = term * 3.0 * (double)(db.proto_bases - i) / (double)(i + 1);
+    }
+    prob /= std::pow(4.0, (double)db.proto_bases);
+    const double per_guide = (double)db.n_targets * prob * 1.4 + 64.0;
+    size_t want = (size_t)std::min((double)G * per_guide, 268435456.0);
     if (want > ctx->hit_cap) ctx->hit_cap = want;
   }
   unsigned long long *d_cnt = ctx->counters.as<unsigned long long>();  // [0] hits [1] compares
