@@ -41,7 +41,6 @@ struct SeedSide {
   const uint32_t *canon;   // database index per entry, or nullptr when entries are in database order
   const uint32_t *masks;   // mask | distance << 24, sorted by distance
   int n_seeds;             // masks [0, n_seeds) are within this pass's seed budget
-  int cum[16];             // cum[d] = # masks at distance <= d
   int seeds_per_item;      // seeds a warp takes at once
   int items;               // ceil(n_seeds / seeds_per_item)
 };
@@ -174,13 +173,19 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
       const uint32_t jlo = __shfl_sync(0xffffffffu, lo, l0 + j), jhi = __shfl_sync(0xffffffffu, hi, l0 + j);
       if (jhi - (jlo & ~3u) <= 128u) continue;  // warp-uniform
       const int bud = __shfl_sync(0xffffffffu, budget, l0 + j);
-      for (uint32_t c2 = (jlo & ~3u) + lane4 + 128u; c2 < jhi; c2 += 256u) {
-        const uint4 w0 = ldg128(sd.other + c2);
-        const bool two = c2 + 128u < jhi;
-        uint4 w1 = make_uint4(0, 0, 0, 0);
-        if (two) w1 = ldg128(sd.other + c2 + 128u);
-        verify_chunk<PASS_B>(p, wh, sd.canon, w0, c2, jlo, jhi, probe, bud, guide_key);
-        if (two) verify_chunk<PASS_B>(p, wh, sd.canon, w1, c2 + 128u, jlo, jhi, probe, bud, guide_key);
+#ifndef FF_TAIL
+#define FF_TAIL 4
+#endif
+      for (uint32_t c2 = (jlo & ~3u) + lane4 + 128u; c2 < jhi; c2 += 128u * FF_TAIL) {
+        uint4 w[FF_TAIL];
+#pragma unroll
+        for (int c = 0; c < FF_TAIL; ++c) {
+          w[c] = make_uint4(0, 0, 0, 0);
+          if (c2 + 128u * c < jhi) w[c] = ldg128(sd.other + c2 + 128u * c);
+        }
+#pragma unroll
+        for (int c = 0; c < FF_TAIL; ++c)
+          if (c2 + 128u * c < jhi) verify_chunk<PASS_B>(p, wh, sd.canon, w[c], c2 + 128u * c, jlo, jhi, probe, bud, guide_key);
       }
     }
   }
@@ -361,12 +366,12 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   sp.guides = d_guides; sp.n_guides = G;
   sp.A.off = db.A.d_off; sp.A.other = db.A.d_other; sp.A.canon = db.A.d_canon; sp.A.masks = db.A.d_masks;
   sp.A.n_seeds = nA; sp.A.seeds_per_item = 32; sp.A.items = (nA + 31) / 32;
-  for (int i = 0; i < 16; ++i) { sp.A.cum[i] = db.A.cum[i]; sp.B.cum[i] = db.B.cum[i]; }
   sp.B.off = db.B.d_off; sp.B.other = db.B.d_other; sp.B.canon = db.B.d_canon; sp.B.masks = db.B.d_masks;
   sp.B.n_seeds = nB;
   {  // part-two buckets are 4^(a-b) times longer: hand them out in smaller batches
     const double bucket_b = (double)db.n_targets / (double)(1ull << (2 * db.B.key_bases));
     int spi = bucket_b > 2048 ? 1 : bucket_b > 512 ? 4 : bucket_b > 128 ? 8 : 32;
+    if (const char *e = getenv("FF_B_SPI")) spi = std::max(1, atoi(e));
     sp.B.seeds_per_item = spi; sp.B.items = (nB + spi - 1) / spi;
   }
   sp.items_per_guide = sp.A.items + sp.B.items;
