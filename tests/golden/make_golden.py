@@ -108,6 +108,27 @@ def unit_vectors():
         {"pack": "CPF1", "guide": sp("TTTT CGAGC AGAAG AAGAA GGGAC"), "bin": "CAAGCAG", "mm": 1},
         {"pack": "CPF1", "guide": sp("TTTT CGAGC AGAAG AAGAA GGGAC"), "bin": "AGAGCAA", "mm": 2},
     ]
+    # SimpleSiteFinderTest known answers (src/test/scala/reference/SimpleSiteFinderTest.scala:14-175):
+    # input string, pack, flank -> expected site bases (rc = reverse complement of the slice) / context presence
+    out["site_finder_cases"] = [
+        {"pack": "SPCAS9NGG", "flank": 0, "seq": sp("ATTTA AAAAA CCCCC AAAAA GGG"), "sites": [["fwd", 0, 23]], "context_defined": [True]},
+        {"pack": "SPCAS9NGG", "flank": 8, "seq": sp("ATA ATATA ATTTA AAAAA TTTTT AAAAA AGG AATTA AAT"), "sites": [["fwd", 8, 31]], "context_is_whole": True},
+        {"pack": "SPCAS9NGG", "flank": 0, "seq": sp("CCTTA AAAAA CCCCC AAAAA AAA"), "sites": [["rc", 0, 23]]},
+        {"pack": "SPCAS9NGG", "flank": 0, "seq": sp("A ATTTA AAAAA CCCCC AAAAA GGG"), "sites": [["fwd", 0, 23], ["fwd", 1, 24]]},
+        {"pack": "SPCAS9NAG", "flank": 0, "seq": sp("ATTTA AAAAA CCCCC AAAAA GAG"), "sites": [["fwd", 0, 23]]},
+        {"pack": "SPCAS9NAG", "flank": 0, "seq": sp("CTTTA AAAAA CCCCC AAAAA AAA"), "sites": [["rc", 0, 23]]},
+        {"pack": "SPCAS9", "flank": 0, "seq": sp("A ATTTA AAAAA CCCCC AAAAA AGG"), "sites": [["fwd", 0, 23], ["fwd", 1, 24]]},
+        {"pack": "SPCAS9NGG", "flank": 0, "seq": sp("AAATA AAAAA CCCCC AAAAA GGG"), "sites": [["fwd", 0, 23]]},
+        {"pack": "CPF1", "flank": 0, "seq": sp("TTTTA ATTTA AAAAA CCCCC AATTT"), "sites": [["fwd", 0, 24], ["fwd", 1, 25]]},
+        {"pack": "CPF1", "flank": 0, "seq": sp("TAATA ATTTA AAAAA CCCCC AAAAA"), "sites": [["rc", 0, 24], ["rc", 1, 25]]},
+        {"pack": "SPCAS9NGG", "flank": 1, "seq": sp("ATTTA AAAAA CCCCC AAAAA GGG"), "sites": [["fwd", 0, 23]], "context_defined": [False]},
+    ]
+    st = open(os.path.join(REF, "src/test/scala/reference/SimpleSiteFinderTest.scala")).read().replace(" ", "")
+    for c in out["site_finder_cases"]:
+        assert c["seq"] in st, c
+    # BitPositionTest.scala:25-94
+    out["bit_position_cases"] = [{"contigs": ["chr1", "chr2"], "contig": "chr2", "start": 1000, "len": 23, "fwd": True},
+                                 {"contigs": ["chr1", "chr2"], "contig": "chr2", "start": 102200, "len": 23, "fwd": False}]
     # sanity: the hand-entered BitEncodingTest cases must literally occur in the reference test source
     bt = open(os.path.join(REF, "src/test/scala/bitcoding/BitEncodingTest.scala")).read().replace(" ", "")
     for c in out["mismatch_cases"]:

@@ -396,3 +396,42 @@ def test_dense_neighbourhood_regrows_hit_buffer_and_streams_long_buckets(ff, ora
             assert got.n_candidate_hits > (1 << 22)          # more than the initial hit buffer
         assert ctx.timings().scan_launches >= 1
         assert ref.row_ptr[-1] > 5_000_000
+
+
+def test_randomised_small_configurations(ff, oracle):
+    """Fuzz: random spCas9-family indexes of 1..20 000 targets (clustered so that hits exist), random guides, k in 0..7
+    (and one k larger than the protospacer), random maximumOffTargets; every result must equal the oracle's."""
+    rng = np.random.default_rng(20261017)
+    for trial in range(40):
+        enzyme = int(rng.choice([2, 3, 3, 4, 5, 6]))
+        pack = oracle.PACK_BY_INDEX[enzyme]
+        proto = pack.scan_len - pack.pam_len
+        n = int(rng.choice([1, 2, 17, 300, 5000, 20000]))
+        centres = rng.integers(0, 1 << (2 * proto), max(1, n // 50), dtype=np.uint64)
+        base = centres[rng.integers(0, len(centres), n)]
+        for _ in range(3):  # up to three random substitutions around a centre
+            pos = rng.integers(0, proto, n).astype(np.uint64)
+            sub = rng.integers(0, 4, n).astype(np.uint64)
+            base = base ^ (sub << (np.uint64(2) * pos))
+        nbase = rng.integers(0, 4, n).astype(np.uint64)
+        pam2 = {2: [0xA, 0x2], 3: [0xA], 4: [0x2], 5: [0xA, 0x2], 6: [0xA]}[enzyme]
+        seq = (base << np.uint64(6)) | (nbase << np.uint64(4)) | np.asarray(rng.choice(pam2, n), np.uint64)
+        seq = np.unique(seq)
+        counts = np.where(rng.random(len(seq)) < 0.8, 1, rng.integers(1, 3000, len(seq))).astype(np.uint64)
+        targets = seq | (counts << np.uint64(48))
+        g = int(rng.choice([1, 3, 40, 400]))
+        gp = centres[rng.integers(0, len(centres), g)]
+        for _ in range(int(rng.integers(0, 4))):
+            gp = gp ^ (rng.integers(0, 4, g).astype(np.uint64) << (np.uint64(2) * rng.integers(0, proto, g).astype(np.uint64)))
+        guides = (gp << np.uint64(6)) | np.uint64(0x2A) | (np.uint64(1) << np.uint64(48))
+        k = int(rng.choice([0, 1, 2, 3, 4, 4, 5, 6, 7, 25]))
+        max_ot = int(rng.choice([1, 10, 2000, 2000, 10 ** 6]))
+        bin_off = oracle.bin_offsets_from_sorted(pack, 7, targets)
+        ref = oracle.discover_soa(pack, 7, targets, bin_off, guides, k, max_ot, n_threads=4)
+        with ff.Context(0) as ctx:
+            ctx.load_database_arrays(enzyme, targets)
+            got = ctx.discover(guides, k, max_ot)
+        try:
+            helpers.assert_hits_equal(got, ref)
+        except AssertionError as e:
+            raise AssertionError("trial %d enzyme %d n %d g %d k %d maxOT %d: %s" % (trial, enzyme, len(targets), g, k, max_ot, e))

@@ -177,3 +177,26 @@ def test_host_mirror_site_finder_and_double_format(built, oracle, tmp_path):
     xs += list(rng.random(200)) + list(rng.random(50) * 1e-6) + list(rng.random(50) * 1e9)
     r = subprocess.run([SELFTEST, "double"] + [repr(float(x)) for x in xs], capture_output=True, text=True)
     assert r.stdout.strip().split("\n") == [oracle.java_double_str(float(x)) for x in xs]
+
+
+def test_host_mirror_site_finder_reference_vectors(built, tmp_path):
+    """SimpleSiteFinderTest.scala known answers through the C++ SimpleSiteFinder."""
+    import json
+    from conftest import GOLDEN
+    if not os.path.exists(SELFTEST):
+        pytest.skip("host_selftest not built")
+    vec = json.load(open(os.path.join(GOLDEN, "reference_unit_vectors.json")))
+    idx = {"CPF1": 1, "SPCAS9": 2, "SPCAS9NGG": 3, "SPCAS9NAG": 4, "SPCAS919": 5, "SPCAS9NGG19": 6}
+    comp = str.maketrans("ACGT", "TGCA")
+    for c in vec["site_finder_cases"]:
+        fa = tmp_path / "c.fa"
+        fa.write_text(">testContig\n" + c["seq"] + "\n")
+        r = subprocess.run([SELFTEST, "sites", str(idx[c["pack"]]), str(fa), str(c["flank"])], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = [ln.split("\t") for ln in r.stdout.strip().split("\n") if ln]
+        assert len(got) == len(c["sites"]), c
+        for g, (kind, a, b) in zip(got, c["sites"]):
+            want = c["seq"][a:b] if kind == "fwd" else c["seq"][a:b].translate(comp)[::-1]
+            assert g[2] == want and int(g[1]) == a and g[3] == ("FWD" if kind == "fwd" else "RVS")
+        if "context_defined" in c:
+            assert [g[4] != "NONE" for g in got] == c["context_defined"]

@@ -213,3 +213,28 @@ def test_discover_chr22_emx1_reproduces_pinned_tsv(oracle, chr22_db_path, tmp_pa
     t, bo, _po, _pp = db.soa()
     soa = oracle.discover_soa(db.pack, 7, t, bo, [g.encoding for g in guides], 4, 2000, n_threads=2)
     assert (soa.row_ptr == hits.row_ptr).all() and (soa.targets == hits.targets).all()
+
+
+def test_site_finder_known_answers(oracle, vec):
+    # SimpleSiteFinderTest.scala:14-175
+    for c in vec["site_finder_cases"]:
+        pack = oracle.pack_by_name(c["pack"])
+        sites = oracle.find_target_sites([("testContig", c["seq"])], pack, c["flank"])
+        assert len(sites) == len(c["sites"]), c
+        for s, (kind, a, b) in zip(sites, c["sites"]):
+            want = c["seq"][a:b] if kind == "fwd" else oracle.revcomp(c["seq"][a:b])
+            assert s.bases == want and s.position == a and s.forward == (kind == "fwd")
+        if "context_defined" in c:
+            assert [s.context is not None for s in sites] == c["context_defined"]
+        if c.get("context_is_whole"):
+            assert sites[0].context == c["seq"]
+
+
+def test_bit_position_known_answers(oracle, vec):
+    # BitPositionTest.scala:25-61 (round trip) and :63-94 (overlap is host-side annotation code, out of scope)
+    for c in vec["bit_position_cases"]:
+        cid = c["contigs"].index(c["contig"]) + 1
+        enc = oracle.pos_encode(cid, c["start"], c["len"], c["fwd"])
+        assert oracle.pos_decode(enc) == (cid, c["start"], c["len"], c["fwd"])
+    assert oracle.pos_encode(2, 1000, 23, True) == (2 << 32) | 1000 | (23 << 52)
+    assert oracle.pos_encode(1, 5, 23, False) >> 60 == 1
