@@ -116,13 +116,17 @@ __device__ __forceinline__ void verify_chunk(const ScanParams &p, const WarpHits
                                              uint32_t lo, uint32_t hi, uint32_t probe, int budget, uint64_t guide_key) {
   const int d0 = base_dist32(v.x ^ probe), d1 = base_dist32(v.y ^ probe), d2 = base_dist32(v.z ^ probe), d3 = base_dist32(v.w ^ probe);
   if (min(min(d0, d1), min(d2, d3)) <= budget) {
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      const int dc = c == 0 ? d0 : c == 1 ? d1 : c == 2 ? d2 : d3;
-      const uint32_t idx = base + c;
-      bool ok = dc <= budget && idx >= lo && idx < hi;
-      if (PASS_B) ok = ok && dc > wh.hA;
-      if (ok) emit_hit(wh, guide_key | (canon ? canon[idx] : idx));
+    // rare path: which of the four entries are inside the bucket and within budget (and, in pass B, have d1 > hA)
+    const int lo_d = PASS_B ? wh.hA : -1;
+    unsigned int ok = 0;
+    ok |= (d0 <= budget && d0 > lo_d && base + 0 >= lo && base + 0 < hi) ? 1u : 0u;
+    ok |= (d1 <= budget && d1 > lo_d && base + 1 >= lo && base + 1 < hi) ? 2u : 0u;
+    ok |= (d2 <= budget && d2 > lo_d && base + 2 >= lo && base + 2 < hi) ? 4u : 0u;
+    ok |= (d3 <= budget && d3 > lo_d && base + 3 >= lo && base + 3 < hi) ? 8u : 0u;
+    while (ok) {
+      const uint32_t idx = base + (uint32_t)(__ffs((int)ok) - 1);
+      ok &= ok - 1u;
+      emit_hit(wh, guide_key | (canon ? canon[idx] : idx));
     }
   }
 }
@@ -151,6 +155,9 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
   compares += hi - lo;
   static_assert(32 % FF_GROUP == 0, "a group must not wrap around the warp");
   const uint32_t lane4 = 4u * lane;
+  // does any bucket of this batch need more than its first 128-entry chunk?  (never, for part-one buckets of a
+  // human-sized index; always, for part-two buckets)
+  const bool any_long = __any_sync(0xffffffffu, hi - (lo & ~3u) > 128u);
   for (int l0 = 0; l0 < n; l0 += FF_GROUP) {
     uint32_t blo[FF_GROUP], bhi[FF_GROUP];
     uint4 v[FF_GROUP];
@@ -158,7 +165,7 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
     for (int j = 0; j < FF_GROUP; ++j) {  // lanes beyond n hold empty buckets, so l0 + j (< 32) needs no bound check
       blo[j] = __shfl_sync(0xffffffffu, lo, l0 + j);
       bhi[j] = __shfl_sync(0xffffffffu, hi, l0 + j);
-      v[j] = make_uint4(0, 0, 0, 0);
+      v[j] = make_uint4(0, 0, 0, 0);  // (leaving idle lanes' registers undefined makes ptxas spill: measured 7.2 -> 10.2 ms)
       if ((blo[j] & ~3u) + lane4 < bhi[j]) v[j] = ldg128(sd.other + (blo[j] & ~3u) + lane4);
     }
 #pragma unroll
@@ -167,7 +174,8 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
       const uint32_t base = (blo[j] & ~3u) + lane4;
       if (base < bhi[j]) verify_chunk<PASS_B>(p, wh, sd.canon, v[j], base, blo[j], bhi[j], probe, bud, guide_key);
     }
-    // buckets longer than 128 entries (pass B, repeat-rich part-one keys): stream the rest, two chunks in flight
+    if (!any_long) continue;
+    // buckets longer than 128 entries (pass B, repeat-rich part-one keys): stream the rest, FF_TAIL chunks in flight
 #pragma unroll 1
     for (int j = 0; j < FF_GROUP; ++j) {
       const uint32_t jlo = __shfl_sync(0xffffffffu, lo, l0 + j), jhi = __shfl_sync(0xffffffffu, hi, l0 + j);
