@@ -157,7 +157,7 @@ int db_build_index(ff_ctx *ctx) {
   Database &db = ctx->db;
   cudaStream_t st = ctx->stream;
   const uint64_t n = db.n_targets;
-  if (n >= 0xFFFFFFF0ull) { set_error("database too large for 32-bit target indices"); return FF_EUNSUPPORTED; }
+  if (n >= 0xFFFF0000ull) { set_error("database too large for 32-bit target indices"); return FF_EUNSUPPORTED; }
   const bool sorted_db = !db.pack.five_prime;  // 3'-PAM: database order == lexicographic order of the target string
   {
     unsigned int *d_bad = nullptr, h_bad[2] = {0, 0};
@@ -412,7 +412,7 @@ int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
     return false;  // "Invalid bin type" BlockManager.scala:85-87
   };
   for_bins([&](size_t b, unsigned w) {
-    const uint64_t *body; size_t nl;
+    const uint64_t *body = nullptr; size_t nl = 0;
     if (!block_body(b, &body, &nl)) { bad[w] = 1; return; }
     uint64_t nt = 0, np = 0, v;
     for (size_t i = 0; i < nl;) {
@@ -432,7 +432,7 @@ int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
   std::vector<uint64_t> targets(n_targets + 1), positions(n_positions + 1);
   // pass 2: fill
   for_bins([&](size_t b, unsigned) {
-    const uint64_t *body; size_t nl;
+    const uint64_t *body = nullptr; size_t nl = 0;
     block_body(b, &body, &nl);
     uint64_t ti = bin_t[b], pi = bin_p[b], v;
     for (size_t i = 0; i < nl;) {
