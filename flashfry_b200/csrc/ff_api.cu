@@ -1,6 +1,8 @@
 // C ABI of libflashfry_b200 (include/flashfry_b200.h): context, error plumbing, host <-> device staging.
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -71,55 +73,129 @@ static void owner_put(HitsOwner *o) {
   delete o;
 }
 
-static int copy_out(ff_ctx *ctx, const DeviceResult &r, ff_hits **out) {
-  HitsOwner *o = owner_get();
-  if (!o) { set_error("out of host memory"); return FF_ENOMEM; }
-  const int64_t G = r.n_guides, H = r.n_hits, P = r.n_positions;
-  int rc = FF_OK;
-  auto fail = [&](int code) { owner_put(o); return code; };
-  if ((rc = o->row_ptr.reserve((G + 1) * 8)) || (rc = o->targets.reserve((H + 1) * 8)) || (rc = o->mm.reserve(H + 1)) ||
-      (rc = o->total.reserve((G + 1) * 4)) || (rc = o->ovf.reserve(G + 1)))
-    return fail(rc);
-  cudaStream_t st = ctx->stream;
-  cudaError_t e = cudaMemcpyAsync(o->row_ptr.p, r.d_row_ptr, (G + 1) * 8, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->targets.p, r.d_targets, H * 8, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->mm.p, r.d_mismatches, H, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && G > 0) e = cudaMemcpyAsync(o->total.p, r.d_total_count, G * 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && G > 0) e = cudaMemcpyAsync(o->ovf.p, r.d_overflowed, G, cudaMemcpyDeviceToHost, st);
-  const bool with_pos = r.d_pos_ptr != nullptr;
-  if (e == cudaSuccess && with_pos) {
-    if ((rc = o->pos_ptr.reserve((H + 1) * 8)) || (rc = o->positions.reserve((P + 1) * 8))) return fail(rc);
-    e = cudaMemcpyAsync(o->pos_ptr.p, r.d_pos_ptr, (H + 1) * 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && P > 0) e = cudaMemcpyAsync(o->positions.p, r.d_positions, P * 8, cudaMemcpyDeviceToHost, st);
-  }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return fail(cuda_fail(e, "D2H of discover results", __FILE__, __LINE__));
-  ff_hits &h = o->pub;
-  h.n_guides = G; h.n_hits = H;
-  h.row_ptr = o->row_ptr.as<int64_t>(); h.targets = o->targets.as<uint64_t>(); h.mismatches = o->mm.as<uint8_t>();
-  h.pos_ptr = with_pos ? o->pos_ptr.as<int64_t>() : nullptr;
-  h.positions = with_pos ? o->positions.as<uint64_t>() : nullptr;
-  h.total_count = o->total.as<int32_t>(); h.overflowed = o->ovf.as<uint8_t>();
-  h.n_compares = r.n_compares; h.n_candidate_hits = r.n_candidate_hits;
-  h.opaque = o;
-  *out = &h;
+// Grow a pinned host buffer while copies into it may still be in flight on the copy stream.
+static int grow_pinned(ff_ctx *ctx, HostBuf &hb, size_t used_bytes, size_t want_bytes) {
+  if (want_bytes <= hb.cap && hb.p) return FF_OK;
+  FF_CUDA(cudaStreamSynchronize(ctx->copy_stream));  // nothing may be writing into the old block while it moves
+  HostBuf bigger;
+  FF_TRY(bigger.reserve(want_bytes + want_bytes / 2));
+  if (hb.p && used_bytes) memcpy(bigger.p, hb.p, used_bytes);
+  hb.release();
+  hb = bigger;
   return FF_OK;
 }
 
-static int run_scores(ff_ctx *ctx, const uint64_t *d_guides, const DeviceResult &r, uint32_t metrics) {
+static int score_slot(ff_ctx *ctx, const uint64_t *d_guides, const DeviceResult &r, uint32_t metrics, int slot) {
   if (!metrics) return FF_OK;
+  ff_ctx::OutSlot &os = ctx->out[slot & 1];
   const int64_t Gp = r.n_guides > 0 ? r.n_guides : 1;
-  FF_TRY(ctx->cfd_max.reserve(Gp * 8));
-  FF_TRY(ctx->cfd_spec.reserve(Gp * 8));
-  FF_TRY(ctx->hsu.reserve(Gp * 8));
+  FF_TRY(os.cfd_max.reserve(Gp * 8));
+  FF_TRY(os.cfd_spec.reserve(Gp * 8));
+  FF_TRY(os.hsu.reserve(Gp * 8));
   cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
   FF_CUDA(cudaEventRecord(e0, ctx->stream));
-  FF_TRY(score_on_device(ctx, d_guides, r.n_guides, r.d_row_ptr, r.d_targets, r.n_hits, metrics, ctx->cfd_max.as<double>(),
-                         ctx->cfd_spec.as<double>(), ctx->hsu.as<double>(), nullptr));
+  FF_TRY(score_on_device(ctx, d_guides, r.n_guides, r.d_row_ptr, r.d_targets, r.n_hits, metrics, os.cfd_max.as<double>(),
+                         os.cfd_spec.as<double>(), os.hsu.as<double>(), nullptr));
   FF_CUDA(cudaEventRecord(e1, ctx->stream));
   FF_CUDA(cudaStreamSynchronize(ctx->stream));
   FF_CUDA(cudaEventElapsedTime(&ctx->last.score_ms, e0, e1));
   ctx->last.total_ms += ctx->last.score_ms;
+  return FF_OK;
+}
+
+static void add_timings(ff_timings *acc, const ff_timings &t) {
+  acc->prep_ms += t.prep_ms; acc->scan_ms += t.scan_ms; acc->order_ms += t.order_ms; acc->cut_ms += t.cut_ms;
+  acc->score_ms += t.score_ms; acc->total_ms += t.total_ms; acc->scan_launches += t.scan_launches;
+  acc->kernel_launches += t.kernel_launches; acc->scan_bytes_read += t.scan_bytes_read;
+}
+
+// The host-facing discover: guides come from host memory, results go back to pinned host memory.  Large guide sets are
+// cut into a few sub-batches; the D2H of sub-batch i runs on the copy stream while sub-batch i+1 is being scanned.
+static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions,
+                         uint32_t metrics, ff_hits **out, double *cfd_max, double *cfd_spec, double *hsu) {
+  if (!c || !out || (n_guides > 0 && !guides)) { set_error("null argument"); return FF_EINVAL; }
+  *out = nullptr;
+  FF_CUDA(cudaSetDevice(c->device));
+  if (!c->db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
+  if (n_guides < 0 || max_mm < 0 || max_ot < 0) { set_error("bad discover argument"); return FF_EINVAL; }
+  FF_TRY(c->scratch_guides.reserve((n_guides > 0 ? n_guides : 1) * 8));
+  if (n_guides > 0) FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, n_guides * 8, cudaMemcpyHostToDevice, c->stream));
+  const uint64_t *d_guides = c->scratch_guides.as<uint64_t>();
+
+  int64_t min_batch = 16384;
+  if (const char *e = getenv("FF_SUBBATCH_MIN")) min_batch = std::max<long long>(1, atoll(e));
+  int nb = want_positions ? 1 : (int)std::min<int64_t>(4, std::max<int64_t>(1, n_guides / min_batch));
+
+  HitsOwner *o = owner_get();
+  if (!o) { set_error("out of host memory"); return FF_ENOMEM; }
+  int rc = FF_OK;
+  auto fail = [&](int code) { cudaStreamSynchronize(c->copy_stream); owner_put(o); return code; };
+  const int64_t G = n_guides;
+  if ((rc = o->row_ptr.reserve((G + 1) * 8)) || (rc = o->total.reserve((G + 1) * 4)) || (rc = o->ovf.reserve(G + 1))) return fail(rc);
+  ff_timings acc = {};
+  uint64_t n_compares = 0, n_cand = 0;
+  int64_t hit_off = 0, pos_total = 0;
+  bool with_pos = false;
+  std::vector<int64_t> batch_hit_off(nb + 1, 0), batch_g0(nb + 1, 0);
+  cudaStream_t cs = c->copy_stream;
+  for (int b = 0; b < nb; ++b) {
+    const int64_t g0 = G * b / nb, g1 = G * (b + 1) / nb, gn = g1 - g0;
+    const int slot = b & 1;
+    batch_g0[b] = g0;
+    if (b >= 2) { cudaError_t e = cudaEventSynchronize(c->slot_copied[slot]); if (e != cudaSuccess) return fail(cuda_fail(e, "event sync", __FILE__, __LINE__)); }
+    DeviceResult r;
+    if ((rc = discover_on_device(c, d_guides + g0, gn, max_mm, max_ot, want_positions != 0, slot, &r)) != FF_OK) return fail(rc);
+    add_timings(&acc, c->last);
+    if (metrics) {
+      if ((rc = score_slot(c, d_guides + g0, r, metrics, slot)) != FF_OK) return fail(rc);
+      acc.score_ms += c->last.score_ms; acc.total_ms += c->last.score_ms; acc.kernel_launches += 1;
+    }
+    n_compares += r.n_compares; n_cand += r.n_candidate_hits;
+    const int64_t H = r.n_hits;
+    if ((rc = grow_pinned(c, o->targets, (size_t)hit_off * 8, (size_t)(hit_off + H + 1) * 8)) ||
+        (rc = grow_pinned(c, o->mm, (size_t)hit_off, (size_t)(hit_off + H + 1))))
+      return fail(rc);
+    // the compute stream is idle here (discover_on_device synchronises), so the slot's contents are final
+    cudaError_t e = cudaMemcpyAsync(o->row_ptr.as<int64_t>() + g0, r.d_row_ptr, (gn + 1) * 8, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->targets.as<uint64_t>() + hit_off, r.d_targets, H * 8, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->mm.as<uint8_t>() + hit_off, r.d_mismatches, H, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && gn > 0) e = cudaMemcpyAsync(o->total.as<int32_t>() + g0, r.d_total_count, gn * 4, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && gn > 0) e = cudaMemcpyAsync(o->ovf.as<uint8_t>() + g0, r.d_overflowed, gn, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && metrics && gn > 0) {
+      ff_ctx::OutSlot &os = c->out[slot];
+      if (cfd_max && (metrics & FF_METRIC_CFD)) e = cudaMemcpyAsync(cfd_max + g0, os.cfd_max.p, gn * 8, cudaMemcpyDeviceToHost, cs);
+      if (e == cudaSuccess && cfd_spec && (metrics & FF_METRIC_CFD)) e = cudaMemcpyAsync(cfd_spec + g0, os.cfd_spec.p, gn * 8, cudaMemcpyDeviceToHost, cs);
+      if (e == cudaSuccess && hsu && (metrics & FF_METRIC_HSU2013)) e = cudaMemcpyAsync(hsu + g0, os.hsu.p, gn * 8, cudaMemcpyDeviceToHost, cs);
+    }
+    if (e == cudaSuccess && r.d_pos_ptr) {  // positions: single batch only
+      with_pos = true;
+      pos_total = r.n_positions;
+      if ((rc = o->pos_ptr.reserve((H + 1) * 8)) || (rc = o->positions.reserve((pos_total + 1) * 8))) return fail(rc);
+      e = cudaMemcpyAsync(o->pos_ptr.p, r.d_pos_ptr, (H + 1) * 8, cudaMemcpyDeviceToHost, cs);
+      if (e == cudaSuccess && pos_total > 0) e = cudaMemcpyAsync(o->positions.p, r.d_positions, pos_total * 8, cudaMemcpyDeviceToHost, cs);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(c->slot_copied[slot], cs);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "D2H of discover results", __FILE__, __LINE__));
+    batch_hit_off[b] = hit_off;
+    hit_off += H;
+  }
+  batch_hit_off[nb] = hit_off; batch_g0[nb] = G;
+  { cudaError_t e = cudaStreamSynchronize(cs); if (e != cudaSuccess) return fail(cuda_fail(e, "D2H of discover results", __FILE__, __LINE__)); }
+  // sub-batch row pointers are local: shift them by the batch's first hit
+  int64_t *rp = o->row_ptr.as<int64_t>();
+  for (int b = 1; b < nb; ++b)
+    for (int64_t g = batch_g0[b]; g < batch_g0[b + 1]; ++g) rp[g] += batch_hit_off[b];
+  rp[G] = hit_off;
+  c->last = acc;
+  ff_hits &h = o->pub;
+  h.n_guides = G; h.n_hits = hit_off;
+  h.row_ptr = rp; h.targets = o->targets.as<uint64_t>(); h.mismatches = o->mm.as<uint8_t>();
+  h.pos_ptr = with_pos ? o->pos_ptr.as<int64_t>() : nullptr;
+  h.positions = with_pos ? o->positions.as<uint64_t>() : nullptr;
+  h.total_count = o->total.as<int32_t>(); h.overflowed = o->ovf.as<uint8_t>();
+  h.n_compares = n_compares; h.n_candidate_hits = n_cand;
+  h.opaque = o;
+  *out = &h;
   return FF_OK;
 }
 
@@ -151,6 +227,12 @@ int ff_create(ff_ctx **out, int device_id) {
   e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
   c->stream = c->own_stream;
+  e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+  for (auto &ev : c->slot_copied) {
+    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+  }
   for (auto &ev : c->ev) {
     e = cudaEventCreate(&ev);
     if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
@@ -164,11 +246,16 @@ void ff_destroy(ff_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->db.release();
-  DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys,
-                    &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->row_ptr, &c->total_count, &c->overflowed,
-                    &c->out_targets, &c->out_mm, &c->out_tidx, &c->pos_cnt, &c->pos_ptr, &c->out_positions, &c->cfd_per_ot,
-                    &c->hsu_per_ot, &c->cfd_max, &c->cfd_spec, &c->hsu, &c->scratch_guides};
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys, &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->out_tidx, &c->pos_cnt,
+                    &c->pos_ptr, &c->out_positions, &c->cfd_per_ot, &c->hsu_per_ot, &c->scratch_guides};
   for (DevBuf *b : bufs) b->release();
+  for (auto &os : c->out) {
+    DevBuf *ob[] = {&os.row_ptr, &os.total_count, &os.overflowed, &os.out_targets, &os.out_mm, &os.cfd_max, &os.cfd_spec, &os.hsu};
+    for (DevBuf *b : ob) b->release();
+  }
+  for (auto &ev : c->slot_copied) if (ev) cudaEventDestroy(ev);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -232,26 +319,6 @@ int ff_db_copy_targets(ff_ctx *c, uint64_t first, uint64_t n, uint64_t *out) {
   return FF_OK;
 }
 
-static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions,
-                         uint32_t metrics, ff_hits **out, double *cfd_max, double *cfd_spec, double *hsu) {
-  if (!c || !out || (n_guides > 0 && !guides)) { set_error("null argument"); return FF_EINVAL; }
-  *out = nullptr;
-  FF_CUDA(cudaSetDevice(c->device));
-  FF_TRY(c->scratch_guides.reserve((n_guides > 0 ? n_guides : 1) * 8));
-  if (n_guides > 0) FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, n_guides * 8, cudaMemcpyHostToDevice, c->stream));
-  DeviceResult r;
-  FF_TRY(discover_on_device(c, c->scratch_guides.as<uint64_t>(), n_guides, max_mm, max_ot, want_positions != 0, &r));
-  if (metrics) {
-    FF_TRY(run_scores(c, c->scratch_guides.as<uint64_t>(), r, metrics));
-    if (n_guides > 0) {
-      if (cfd_max && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_max, c->cfd_max.p, n_guides * 8, cudaMemcpyDeviceToHost, c->stream));
-      if (cfd_spec && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_spec, c->cfd_spec.p, n_guides * 8, cudaMemcpyDeviceToHost, c->stream));
-      if (hsu && (metrics & FF_METRIC_HSU2013)) FF_CUDA(cudaMemcpyAsync(hsu, c->hsu.p, n_guides * 8, cudaMemcpyDeviceToHost, c->stream));
-    }
-  }
-  return copy_out(c, r, out);
-}
-
 int ff_discover(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions, ff_hits **out) {
   return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, 0, out, nullptr, nullptr, nullptr);
 }
@@ -275,20 +342,21 @@ int ff_score(ff_ctx *c, const uint64_t *guides, const ff_hits *hits, uint32_t me
   const int64_t H = hits->row_ptr[G];
   cudaStream_t st = c->stream;
   FF_TRY(c->scratch_guides.reserve(G * 8));
-  FF_TRY(c->row_ptr.reserve((G + 1) * 8));
-  FF_TRY(c->out_targets.reserve((H + 1) * 8));
-  FF_TRY(c->cfd_max.reserve(G * 8));
-  FF_TRY(c->cfd_spec.reserve(G * 8));
-  FF_TRY(c->hsu.reserve(G * 8));
+  ff_ctx::OutSlot &os = c->out[0];
+  FF_TRY(os.row_ptr.reserve((G + 1) * 8));
+  FF_TRY(os.out_targets.reserve((H + 1) * 8));
+  FF_TRY(os.cfd_max.reserve(G * 8));
+  FF_TRY(os.cfd_spec.reserve(G * 8));
+  FF_TRY(os.hsu.reserve(G * 8));
   FF_TRY(c->cfd_per_ot.reserve((H + 1) * 8));
   FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, G * 8, cudaMemcpyHostToDevice, st));
-  FF_CUDA(cudaMemcpyAsync(c->row_ptr.p, hits->row_ptr, (G + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (H > 0) FF_CUDA(cudaMemcpyAsync(c->out_targets.p, hits->targets, H * 8, cudaMemcpyHostToDevice, st));
-  FF_TRY(score_on_device(c, c->scratch_guides.as<uint64_t>(), G, c->row_ptr.as<int64_t>(), c->out_targets.as<uint64_t>(), H, metrics,
-                         c->cfd_max.as<double>(), c->cfd_spec.as<double>(), c->hsu.as<double>(), c->cfd_per_ot.as<double>()));
-  if (cfd_max && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_max, c->cfd_max.p, G * 8, cudaMemcpyDeviceToHost, st));
-  if (cfd_spec && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_spec, c->cfd_spec.p, G * 8, cudaMemcpyDeviceToHost, st));
-  if (hsu && (metrics & FF_METRIC_HSU2013)) FF_CUDA(cudaMemcpyAsync(hsu, c->hsu.p, G * 8, cudaMemcpyDeviceToHost, st));
+  FF_CUDA(cudaMemcpyAsync(os.row_ptr.p, hits->row_ptr, (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (H > 0) FF_CUDA(cudaMemcpyAsync(os.out_targets.p, hits->targets, H * 8, cudaMemcpyHostToDevice, st));
+  FF_TRY(score_on_device(c, c->scratch_guides.as<uint64_t>(), G, os.row_ptr.as<int64_t>(), os.out_targets.as<uint64_t>(), H, metrics,
+                         os.cfd_max.as<double>(), os.cfd_spec.as<double>(), os.hsu.as<double>(), c->cfd_per_ot.as<double>()));
+  if (cfd_max && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_max, os.cfd_max.p, G * 8, cudaMemcpyDeviceToHost, st));
+  if (cfd_spec && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_spec, os.cfd_spec.p, G * 8, cudaMemcpyDeviceToHost, st));
+  if (hsu && (metrics & FF_METRIC_HSU2013)) FF_CUDA(cudaMemcpyAsync(hsu, os.hsu.p, G * 8, cudaMemcpyDeviceToHost, st));
   if (per_ot_cfd && (metrics & FF_METRIC_CFD) && H > 0) FF_CUDA(cudaMemcpyAsync(per_ot_cfd, c->cfd_per_ot.p, H * 8, cudaMemcpyDeviceToHost, st));
   FF_CUDA(cudaStreamSynchronize(st));
   FF_CUDA(cudaGetLastError());
@@ -300,14 +368,14 @@ int ff_discover_device(ff_ctx *c, const uint64_t *d_guides, int64_t n_guides, in
   if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
   FF_CUDA(cudaSetDevice(c->device));
   DeviceResult r;
-  FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, &r));
-  FF_TRY(run_scores(c, d_guides, r, metrics));
+  FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, 0, &r));
+  FF_TRY(score_slot(c, d_guides, r, metrics, 0));
   out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
   out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
   out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
-  out->d_cfd_max = (metrics & FF_METRIC_CFD) ? c->cfd_max.as<double>() : nullptr;
-  out->d_cfd_specificity = (metrics & FF_METRIC_CFD) ? c->cfd_spec.as<double>() : nullptr;
-  out->d_hsu2013 = (metrics & FF_METRIC_HSU2013) ? c->hsu.as<double>() : nullptr;
+  out->d_cfd_max = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_max.as<double>() : nullptr;
+  out->d_cfd_specificity = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_spec.as<double>() : nullptr;
+  out->d_hsu2013 = (metrics & FF_METRIC_HSU2013) ? c->out[0].hsu.as<double>() : nullptr;
   return FF_OK;
 }
 

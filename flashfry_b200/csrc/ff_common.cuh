@@ -94,10 +94,16 @@ struct ff_ctx {
   // ---- per-call workspaces (grow-only) ----
   ff::DevBuf cub_tmp;
   ff::DevBuf hit_keys, hit_keys_sorted, counters;
-  ff::DevBuf seg_start, n_keep, row_ptr, total_count, overflowed, out_targets, out_mm, out_tidx;
+  ff::DevBuf seg_start, n_keep, out_tidx;
   ff::DevBuf pos_cnt, pos_ptr, out_positions;
-  ff::DevBuf cfd_per_ot, hsu_per_ot, cfd_max, cfd_spec, hsu;
+  ff::DevBuf cfd_per_ot, hsu_per_ot;
   ff::DevBuf scratch_guides;  // H2D staging target for ff_discover
+  // results of a discover call; two sets so that the D2H of one guide sub-batch overlaps the scan of the next
+  struct OutSlot {
+    ff::DevBuf row_ptr, total_count, overflowed, out_targets, out_mm, cfd_max, cfd_spec, hsu;
+  } out[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t slot_copied[2] = {nullptr, nullptr};  // D2H of the slot's previous contents has finished
   size_t hit_cap = 0;
 
   cudaEvent_t ev[8] = {nullptr};

@@ -345,8 +345,9 @@ static void plan_passes(const Database &db, int k, int *hA_out, int *nA, int *nB
 }
 
 int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
-                       bool want_positions, DeviceResult *res) {
+                       bool want_positions, int slot, DeviceResult *res) {
   Database &db = ctx->db;
+  ff_ctx::OutSlot &os = ctx->out[slot & 1];
   if (!db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
   if (n_guides < 0 || max_mm < 0 || max_ot < 0 || (n_guides > 0 && !d_guides)) { set_error("bad discover argument"); return FF_EINVAL; }
   if (n_guides >= (1ll << 31)) { set_error("too many guides in one call"); return FF_EINVAL; }
@@ -359,9 +360,9 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   FF_TRY(ctx->counters.reserve(64));
   FF_TRY(ctx->seg_start.reserve((Gp + 1) * 8));
   FF_TRY(ctx->n_keep.reserve((Gp + 1) * 8));
-  FF_TRY(ctx->row_ptr.reserve((Gp + 1) * 8));
-  FF_TRY(ctx->total_count.reserve(Gp * 4));
-  FF_TRY(ctx->overflowed.reserve(Gp));
+  FF_TRY(os.row_ptr.reserve((Gp + 1) * 8));
+  FF_TRY(os.total_count.reserve(Gp * 4));
+  FF_TRY(os.overflowed.reserve(Gp));
 
   FF_CUDA(cudaEventRecord(ctx->ev[0], st));
   FF_CUDA(cudaEventRecord(ctx->ev[1], st));  // (no separate guide preparation in the seed-and-verify design)
@@ -446,24 +447,24 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   launches++;
   if (G > 0) {
     k_overflow_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), db.d_targets, G, max_ot,
-                                                           ctx->n_keep.as<int64_t>(), ctx->total_count.as<int32_t>(), ctx->overflowed.as<uint8_t>());
+                                                           ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>());
     launches++;
   }
   FF_CUDA(cudaMemsetAsync(ctx->n_keep.as<int64_t>() + G, 0, 8, st));
-  FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->n_keep.as<int64_t>(), ctx->row_ptr.as<int64_t>(), G + 1, st));
+  FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
   FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
-  FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), ctx->row_ptr.as<int64_t>(), G + 1, st));
+  FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
   launches += 2;
   int64_t n_hits = 0;
-  FF_CUDA(cudaMemcpyAsync(&n_hits, ctx->row_ptr.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, st));
+  FF_CUDA(cudaMemcpyAsync(&n_hits, os.row_ptr.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, st));
   FF_CUDA(cudaStreamSynchronize(st));
   const int64_t Hp = n_hits > 0 ? n_hits : 1;
-  FF_TRY(ctx->out_targets.reserve(Hp * 8));
-  FF_TRY(ctx->out_mm.reserve(Hp));
+  FF_TRY(os.out_targets.reserve(Hp * 8));
+  FF_TRY(os.out_mm.reserve(Hp));
   FF_TRY(ctx->out_tidx.reserve(Hp * 4));
   if (G > 0 && n_hits > 0) {
-    k_gather<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), ctx->row_ptr.as<int64_t>(), db.d_targets, d_guides,
-                                                     db.pack.cmp_mask, G, ctx->out_targets.as<uint64_t>(), ctx->out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>());
+    k_gather<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), db.d_targets, d_guides,
+                                                     db.pack.cmp_mask, G, os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>());
     launches++;
   }
   int64_t n_pos = 0;
@@ -473,7 +474,7 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
     FF_TRY(ctx->pos_ptr.reserve((Hp + 1) * 8));
     FF_CUDA(cudaMemsetAsync(ctx->pos_cnt.p, 0, (Hp + 1) * 8, st));
     if (n_hits > 0) {
-      k_pos_counts<<<blocks_for(n_hits, 256), 256, 0, st>>>(ctx->out_targets.as<uint64_t>(), n_hits, ctx->pos_cnt.as<int64_t>());
+      k_pos_counts<<<blocks_for(n_hits, 256), 256, 0, st>>>(os.out_targets.as<uint64_t>(), n_hits, ctx->pos_cnt.as<int64_t>());
       launches++;
     }
     FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->pos_cnt.as<int64_t>(), ctx->pos_ptr.as<int64_t>(), n_hits + 1, st));
@@ -510,9 +511,9 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
 
   res->n_guides = G; res->n_hits = n_hits; res->n_positions = n_pos;
   res->n_candidate_hits = (uint64_t)n_cand; res->n_compares = h_cnt[1];
-  res->d_row_ptr = ctx->row_ptr.as<int64_t>(); res->d_targets = ctx->out_targets.as<uint64_t>();
-  res->d_mismatches = ctx->out_mm.as<uint8_t>(); res->d_total_count = ctx->total_count.as<int32_t>();
-  res->d_overflowed = ctx->overflowed.as<uint8_t>();
+  res->d_row_ptr = os.row_ptr.as<int64_t>(); res->d_targets = os.out_targets.as<uint64_t>();
+  res->d_mismatches = os.out_mm.as<uint8_t>(); res->d_total_count = os.total_count.as<int32_t>();
+  res->d_overflowed = os.overflowed.as<uint8_t>();
   return FF_OK;
 }
 

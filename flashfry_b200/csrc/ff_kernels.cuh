@@ -32,7 +32,7 @@ struct DeviceResult {
 
 // ff_discover.cu
 int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
-                       bool want_positions, DeviceResult *res);
+                       bool want_positions, int slot, DeviceResult *res);
 
 // ff_score.cu : CFD + Hsu2013 over a CSR hit list resident in HBM.  Any output may be null.
 int score_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, const int64_t *d_row_ptr,

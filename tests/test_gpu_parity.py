@@ -435,3 +435,26 @@ def test_randomised_small_configurations(ff, oracle):
             helpers.assert_hits_equal(got, ref)
         except AssertionError as e:
             raise AssertionError("trial %d enzyme %d n %d g %d k %d maxOT %d: %s" % (trial, enzyme, len(targets), g, k, max_ot, e))
+
+
+def test_pipelined_sub_batches_equal_single_batch(ff, oracle, small_db, monkeypatch):
+    """ff_discover cuts large guide sets into sub-batches whose D2H overlaps the next scan; the stitched CSR (row
+    pointers, per-guide totals, fused scores) must equal the single-batch result and the oracle's."""
+    _, db, _ = small_db
+    targets = db.soa()[0]
+    guides = np.concatenate([helpers.planted_guides(db.pack, targets, 41, 333, max_subs=3), helpers.random_guides(oracle, db.pack, 42, 70)])
+    ref = oracle.discover_blocks(db, guides, 4, 2000)
+    with ff.Context(0) as ctx:
+        ctx.load_database(small_db[0])
+        monkeypatch.setenv("FF_SUBBATCH_MIN", "1000000")
+        one, c1, s1, h1 = ctx.discover_score(guides, 4, 2000)
+        for min_batch in ("100", "50", "7"):
+            monkeypatch.setenv("FF_SUBBATCH_MIN", min_batch)
+            many, c4, s4, h4 = ctx.discover_score(guides, 4, 2000)
+            helpers.assert_hits_equal(many, ref)
+            helpers.assert_hits_equal(many, one)
+            assert (c1 == c4).all() and (s1 == s4).all() and (h1 == h4).all()
+            plain = ctx.discover(guides, 4, 2000)
+            helpers.assert_hits_equal(plain, ref)
+        withpos = ctx.discover(guides, 4, 2000, positions=True)   # positions force a single batch
+        helpers.assert_hits_equal(withpos, ref, check_positions=True)
