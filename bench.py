@@ -77,9 +77,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def mark(self):
+        """perf_counter timestamp, to delimit the timed region in stop()."""
+        return time.perf_counter()
+
+    def stop(self, t_from=None, t_to=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -90,7 +94,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_from is not None and not (t_from <= ts <= t_to + 0.06):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -174,12 +180,13 @@ def run_native(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~0.2 s to deliver its first sample: start it before the warm-up
     for _ in range(args.warmup):
         r = step()
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_region0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, launches, cand, compares, scan_bytes = [], 0, 0, 0, 0
     sync_all()
@@ -193,7 +200,6 @@ def run_native(args):
     e1.record(stream)
     sync_all()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tmax = torch.tensor([ms], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -223,6 +229,7 @@ def run_native(args):
         nh = e2e_step()
     sync_all()
     e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop(t_region0, sampler.mark()) if rank == 0 else None  # samples taken inside the two timed regions
     if world > 1:
         tmax = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -240,8 +247,9 @@ def run_native(args):
                 "kernel_share_of_step": scan_avg_ms / ms_per_step, "traffic": None,
                 "entries_streamed_per_launch": compares, "entries_per_guide": compares / max(G, 1)}
         tr = ncu_traffic()
-        if tr and tr.get("guides") == G and tr.get("targets") == n_t:
-            roof["traffic"] = tr.get("dram_bytes_per_launch")
+        if tr and tr.get("targets") == n_t and tr.get("max_mismatch") == args.k:
+            # ncu measured one launch over guides_in_profiled_launch guides; traffic is linear in the guide count
+            roof["traffic"] = tr.get("dram_bytes_per_guide") * G
             roof["traffic_source"] = tr.get("source")
         out = {"metric": "guides/sec at <=4 mismatches vs hg38-sized index", "value": value, "unit": "guides/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -351,7 +359,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--targets", type=int, default=300_000_000)
