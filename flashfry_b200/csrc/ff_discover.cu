@@ -55,6 +55,7 @@ struct ScanParams {
   uint64_t proto_mask;
   int k;                   // max mismatches
   int hA;                  // pass A finds pairs with d1 <= hA, pass B the pairs with d1 > hA
+  int tbits;               // bits of a database index: a hit key is guide << tbits | index (fewest radix-sort passes)
   uint64_t *hits;
   unsigned long long *hit_count;
   unsigned long long hit_cap;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_seed_scan(
     const uint64_t proto = (guide >> p.proto_shift) & p.proto_mask;
     const uint32_t key_a = (uint32_t)(proto >> p.b_bits);
     const uint32_t key_b = (uint32_t)(proto & ((1ull << p.b_bits) - 1ull));
-    const uint64_t guide_key = (uint64_t)g << 32;
+    const uint64_t guide_key = (uint64_t)g << p.tbits;
     if (bi < p.A.items) {
       const int seed0 = bi * p.A.seeds_per_item;
       scan_seeds<false>(p, p.A, wh, lane, key_a, key_b, seed0, min(p.A.seeds_per_item, p.A.n_seeds - seed0), guide_key, compares);
@@ -239,10 +240,10 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_seed_scan(
 // ------------------------------------------------------------------------------------------------------------
 // ordering + overflow cut
 // seg_start[g] = first sorted key whose guide index >= g   (g in [0, n_guides])
-__global__ void k_segments(const uint64_t *__restrict__ keys, int64_t n_hits, int64_t n_guides, int64_t *__restrict__ seg_start) {
+__global__ void k_segments(const uint64_t *__restrict__ keys, int64_t n_hits, int64_t n_guides, int tbits, int64_t *__restrict__ seg_start) {
   int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (g > n_guides) return;
-  const uint64_t want = (uint64_t)g << 32;
+  const uint64_t want = (uint64_t)g << tbits;
   int64_t lo = 0, hi = n_hits;
   while (lo < hi) {
     int64_t mid = (lo + hi) >> 1;
@@ -254,7 +255,7 @@ __global__ void k_segments(const uint64_t *__restrict__ keys, int64_t n_hits, in
 // One warp per guide: walk its hits in database order and keep the shortest prefix whose summed occurrence count
 // reaches max_ot (ResultsAggregator.scala:61-69 / CRISPRSiteOT.scala:39-46: append while currentTotal < overflow).
 __global__ void k_overflow_cut(const uint64_t *__restrict__ keys, const int64_t *__restrict__ seg_start,
-                               const uint64_t *__restrict__ targets, int64_t n_guides, int max_ot,
+                               const uint64_t *__restrict__ targets, int64_t n_guides, int max_ot, int tbits,
                                int64_t *__restrict__ n_keep, int32_t *__restrict__ total_count,
                                uint8_t *__restrict__ overflowed) {
   const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -266,7 +267,7 @@ __global__ void k_overflow_cut(const uint64_t *__restrict__ keys, const int64_t 
   for (int64_t base = s0; base < s1 && running < max_ot; base += 32) {
     const int64_t i = base + lane;
     long long c = 0;
-    if (i < s1) c = (long long)(targets[(uint32_t)keys[i]] >> 48);
+    if (i < s1) c = (long long)(targets[keys[i] & ((1ull << tbits) - 1ull)] >> 48);
     long long incl = c;
     for (int o = 1; o < 32; o <<= 1) {
       long long v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -290,7 +291,7 @@ __global__ void k_overflow_cut(const uint64_t *__restrict__ keys, const int64_t 
 // One warp per guide: copy the kept prefix out (target long, mismatch count, target index).
 __global__ void k_gather(const uint64_t *__restrict__ keys, const int64_t *__restrict__ seg_start,
                          const int64_t *__restrict__ row_ptr, const uint64_t *__restrict__ targets,
-                         const uint64_t *__restrict__ guides, uint64_t cmp_mask, int64_t n_guides,
+                         const uint64_t *__restrict__ guides, uint64_t cmp_mask, int64_t n_guides, int tbits,
                          uint64_t *__restrict__ out_targets, uint8_t *__restrict__ out_mm, uint32_t *__restrict__ out_tidx) {
   const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -299,7 +300,7 @@ __global__ void k_gather(const uint64_t *__restrict__ keys, const int64_t *__res
   const int64_t r0 = row_ptr[g], r1 = row_ptr[g + 1];
   const uint64_t guide = guides[g];
   for (int64_t i = lane; i < r1 - r0; i += 32) {
-    const uint32_t t = (uint32_t)keys[s0 + i];
+    const uint32_t t = (uint32_t)(keys[s0 + i] & ((1ull << tbits) - 1ull));
     const uint64_t tl = targets[t];
     out_targets[r0 + i] = tl;
     out_mm[r0 + i] = (uint8_t)mismatches64(guide, tl, cmp_mask);
@@ -386,6 +387,9 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   sp.items_per_guide = sp.A.items + sp.B.items;
   sp.proto_shift = db.proto_shift; sp.b_bits = 2 * db.B.key_bases; sp.proto_mask = (1ull << (2 * db.proto_bases)) - 1ull;
   sp.k = k_eff; sp.hA = hA;
+  int tbits = 1;
+  while ((1ull << tbits) < db.n_targets + 1) tbits++;
+  sp.tbits = tbits;
 
   // ---- scan (repeated once with a larger buffer if the hit buffer overflowed)
   if (ctx->hit_cap == 0) ctx->hit_cap = 1u << 22;
@@ -434,19 +438,19 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   while ((1ll << gbits) < Gp) gbits++;
   const uint64_t *sorted = ctx->hit_keys.as<uint64_t>();
   if (n_cand > 0) {
-    FF_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, ctx->hit_keys.as<uint64_t>(), ctx->hit_keys_sorted.as<uint64_t>(), n_cand, 0, 32 + gbits, st));
+    FF_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, ctx->hit_keys.as<uint64_t>(), ctx->hit_keys_sorted.as<uint64_t>(), n_cand, 0, tbits + gbits, st));
     FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
-    FF_CUDA(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp_bytes, ctx->hit_keys.as<uint64_t>(), ctx->hit_keys_sorted.as<uint64_t>(), n_cand, 0, 32 + gbits, st));
+    FF_CUDA(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp_bytes, ctx->hit_keys.as<uint64_t>(), ctx->hit_keys_sorted.as<uint64_t>(), n_cand, 0, tbits + gbits, st));
     sorted = ctx->hit_keys_sorted.as<uint64_t>();
-    launches += 2 + (32 + gbits + 7) / 8;
+    launches += 2 + (tbits + gbits + 7) / 8;
   }
   FF_CUDA(cudaEventRecord(ctx->ev[3], st));
 
   // ---- overflow cut in database order
-  k_segments<<<blocks_for(G + 1, 256), 256, 0, st>>>(sorted, n_cand, G, ctx->seg_start.as<int64_t>());
+  k_segments<<<blocks_for(G + 1, 256), 256, 0, st>>>(sorted, n_cand, G, tbits, ctx->seg_start.as<int64_t>());
   launches++;
   if (G > 0) {
-    k_overflow_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), db.d_targets, G, max_ot,
+    k_overflow_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), db.d_targets, G, max_ot, tbits,
                                                            ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>());
     launches++;
   }
@@ -464,7 +468,7 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   FF_TRY(ctx->out_tidx.reserve(Hp * 4));
   if (G > 0 && n_hits > 0) {
     k_gather<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), db.d_targets, d_guides,
-                                                     db.pack.cmp_mask, G, os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>());
+                                                     db.pack.cmp_mask, G, tbits, os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>());
     launches++;
   }
   int64_t n_pos = 0;
