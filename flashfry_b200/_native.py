@@ -52,7 +52,7 @@ class FFTimings(C.Structure):
 # every symbol include/flashfry_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_load_database",
            "ff_load_database_arrays", "ff_synth_database", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
-           "ff_discover", "ff_hits_free", "ff_score", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
+           "ff_discover", "ff_hits_free", "ff_score", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
 
 _lib = None
 
@@ -83,6 +83,8 @@ def lib():
     L.ff_hits_free.argtypes = [C.POINTER(FFHits)]
     L.ff_hits_free.restype = None
     L.ff_score.argtypes = [vp, u64p, C.POINTER(FFHits), C.c_uint32, dp, dp, dp, dp]
+    i32p = C.POINTER(C.c_int32)
+    L.ff_hit_aggregates.argtypes = [vp, C.c_int, u64p, C.POINTER(FFHits), i32p, i32p, i32p, i32p]
     L.ff_discover_score.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                     C.POINTER(C.POINTER(FFHits)), dp, dp, dp]
     L.ff_discover_device.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.POINTER(FFDeviceResult)]

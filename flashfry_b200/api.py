@@ -151,6 +151,22 @@ class Context:
                                  dp(hsu), dp(per)))
         return cmax[:len(g)], cspec[:len(g)], hsu[:len(g)], per[:len(t)]
 
+    def hit_aggregates(self, enzyme_index: int, guides, row_ptr, targets):
+        """ff_hit_aggregates -> (closest, closest_count, hist[n][5], in_genome) int32 arrays."""
+        g = _u64(guides)
+        rp = np.ascontiguousarray(np.asarray(row_ptr, dtype=np.int64))
+        t = _u64(targets)
+        h = N.FFHits()
+        h.n_guides, h.n_hits = len(g), len(t)
+        h.row_ptr = rp.ctypes.data_as(C.POINTER(C.c_int64))
+        h.targets = t.ctypes.data_as(C.POINTER(C.c_uint64))
+        n = max(len(g), 1)
+        closest, cnt, hist, ing = (np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros((n, 5), np.int32), np.zeros(n, np.int32))
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        N.check(N.lib().ff_hit_aggregates(self._h, enzyme_index, g.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(h), ip(closest), ip(cnt),
+                                          ip(hist), ip(ing)))
+        return closest[:len(g)], cnt[:len(g)], hist[:len(g)], ing[:len(g)]
+
     def discover_device(self, d_guides_ptr: int, n_guides: int, max_mismatch: int = 4, maximum_off_targets: int = 2000,
                         metrics: int = 0) -> N.FFDeviceResult:
         r = N.FFDeviceResult()

@@ -363,6 +363,39 @@ int ff_score(ff_ctx *c, const uint64_t *guides, const ff_hits *hits, uint32_t me
   return FF_OK;
 }
 
+int ff_hit_aggregates(ff_ctx *c, int enzyme_index, const uint64_t *guides, const ff_hits *hits, int32_t *closest,
+                      int32_t *closest_count, int32_t *hist, int32_t *in_genome) {
+  if (!c || !hits || (!guides && hits->n_guides > 0)) { set_error("null argument"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  Pack pack;
+  FF_TRY(pack_from_index(enzyme_index, &pack));
+  const int64_t G = hits->n_guides;
+  if (G <= 0) return FF_OK;
+  const int64_t H = hits->row_ptr[G];
+  cudaStream_t st = c->stream;
+  ff_ctx::OutSlot &os = c->out[0];
+  FF_TRY(c->scratch_guides.reserve(G * 8));
+  FF_TRY(os.row_ptr.reserve((G + 1) * 8));
+  FF_TRY(os.out_targets.reserve((H + 1) * 8));
+  FF_TRY(os.total_count.reserve(G * 8 * 4));  // 8 int32 per guide
+  FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, G * 8, cudaMemcpyHostToDevice, st));
+  FF_CUDA(cudaMemcpyAsync(os.row_ptr.p, hits->row_ptr, (G + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (H > 0) FF_CUDA(cudaMemcpyAsync(os.out_targets.p, hits->targets, H * 8, cudaMemcpyHostToDevice, st));
+  FF_TRY(hit_aggregates_on_device(c, c->scratch_guides.as<uint64_t>(), G, os.row_ptr.as<int64_t>(), os.out_targets.as<uint64_t>(),
+                                  pack.cmp_mask, os.total_count.as<int32_t>()));
+  std::vector<int32_t> tmp((size_t)G * 8);
+  FF_CUDA(cudaMemcpyAsync(tmp.data(), os.total_count.p, (size_t)G * 8 * 4, cudaMemcpyDeviceToHost, st));
+  FF_CUDA(cudaStreamSynchronize(st));
+  for (int64_t g = 0; g < G; ++g) {
+    const int32_t *o = tmp.data() + g * 8;
+    if (closest) closest[g] = o[0];
+    if (closest_count) closest_count[g] = o[1];
+    if (hist) for (int m = 0; m < 5; ++m) hist[g * 5 + m] = o[2 + m];
+    if (in_genome) in_genome[g] = o[7];
+  }
+  return FF_OK;
+}
+
 int ff_discover_device(ff_ctx *c, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot, uint32_t metrics,
                        ff_device_result *out) {
   if (!c || !out) { set_error("null argument"); return FF_EINVAL; }

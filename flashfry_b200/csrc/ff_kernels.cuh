@@ -39,6 +39,9 @@ int score_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, con
                     const uint64_t *d_targets, int64_t n_hits, uint32_t metrics, double *d_cfd_max,
                     double *d_cfd_spec, double *d_hsu, double *d_per_ot_cfd);
 
+int hit_aggregates_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, const int64_t *d_row_ptr, const uint64_t *d_targets,
+                             uint64_t cmp_mask, int32_t *d_out);
+
 // ff_db.cu
 int db_from_host_arrays(ff_ctx *ctx, const Pack &pack, int bin_width, const uint64_t *targets, uint64_t n_targets,
                         const uint64_t *positions, uint64_t n_positions, const std::vector<std::string> &contigs);

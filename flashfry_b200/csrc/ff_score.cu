@@ -113,6 +113,52 @@ k_score(const uint64_t *__restrict__ guides, int64_t n_guides, const int64_t *__
   }
 }
 
+// scoring/ClosestHit.scala:43-76 and scoring/DangerousSequences.scala:61-65 as order-independent integer reductions:
+// one warp per guide, lanes stride its hits.  out: [0] closest (INT32_MAX = none), [1] occurrences at that distance,
+// [2..6] occurrence histogram for 0..4 mismatches, [7] occurrences with zero mismatches.
+__global__ void k_hit_aggregates(const uint64_t *__restrict__ guides, int64_t n_guides, const int64_t *__restrict__ row_ptr,
+                                 const uint64_t *__restrict__ targets, uint64_t cmp_mask, int32_t *__restrict__ out) {
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_guides) return;
+  const uint64_t guide = guides[g];
+  const int64_t r0 = row_ptr[g], r1 = row_ptr[g + 1];
+  int closest = 0x7fffffff;
+  int hist[5] = {0, 0, 0, 0, 0};
+  for (int64_t h = r0 + lane; h < r1; h += 32) {
+    const uint64_t t = targets[h];
+    const int mm = mismatches64(guide, t, cmp_mask), c = (int)(int16_t)(t >> 48);
+    if (mm <= 4) hist[mm] += c;
+    if (mm > 0 && mm < closest) closest = mm;
+  }
+  for (int o = 16; o > 0; o >>= 1) closest = min(closest, __shfl_xor_sync(0xffffffffu, closest, o));
+  int at_closest = 0;  // second walk: occurrences at the winning distance (distances above 4 are not in the histogram)
+  for (int64_t h = r0 + lane; h < r1; h += 32) {
+    const uint64_t t = targets[h];
+    if (mismatches64(guide, t, cmp_mask) == closest) at_closest += (int)(int16_t)(t >> 48);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    at_closest += __shfl_xor_sync(0xffffffffu, at_closest, o);
+#pragma unroll
+    for (int m = 0; m < 5; ++m) hist[m] += __shfl_xor_sync(0xffffffffu, hist[m], o);
+  }
+  if (lane == 0) {
+    int32_t *o = out + g * 8;
+    o[0] = closest; o[1] = closest == 0x7fffffff ? 0 : at_closest;
+    for (int m = 0; m < 5; ++m) o[2 + m] = hist[m];
+    o[7] = hist[0];
+  }
+}
+
+int hit_aggregates_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, const int64_t *d_row_ptr, const uint64_t *d_targets,
+                             uint64_t cmp_mask, int32_t *d_out) {
+  if (n_guides <= 0) return FF_OK;
+  const int64_t threads = n_guides * 32;
+  k_hit_aggregates<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_guides, n_guides, d_row_ptr, d_targets, cmp_mask, d_out);
+  FF_CUDA(cudaGetLastError());
+  return FF_OK;
+}
+
 int score_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, const int64_t *d_row_ptr,
                     const uint64_t *d_targets, int64_t n_hits, uint32_t metrics, double *d_cfd_max,
                     double *d_cfd_spec, double *d_hsu, double *d_per_ot_cfd) {

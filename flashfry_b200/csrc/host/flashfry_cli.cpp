@@ -110,8 +110,8 @@ int runScore(int argc, char **argv) {
     std::unique_ptr<ScoreModel> m;
     if (name == "hsu2013") m.reset(new GpuScoreModel(nc, FF_METRIC_HSU2013));
     else if (name == "doench2016cfd") m.reset(new GpuScoreModel(nc, FF_METRIC_CFD));
-    else if (name == "minot") m.reset(new ClosestHit());
-    else if (name == "dangerous") { auto *d = new DangerousSequences(); d->cleanOutput = a.flag("numericOutput"); m.reset(d); }
+    else if (name == "minot") { auto *ch = new ClosestHit(); ch->nc = &nc; m.reset(ch); }
+    else if (name == "dangerous") { auto *d = new DangerousSequences(); d->nc = &nc; d->cleanOutput = a.flag("numericOutput"); m.reset(d); }
     else if (name == "doench2014ontarget" || name == "moreno2015" || name == "bedannotator" || name == "reciprocalofftargets" ||
              name == "rank" || name == "jostandsantos" || name == "folding")
       throw std::invalid_argument("scoring metric '" + nameRaw + "' is outside the GPU hot path of this build (SURVEY.md section 8); use FlashFry itself for it");

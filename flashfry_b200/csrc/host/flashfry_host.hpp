@@ -429,12 +429,46 @@ struct GpuScoreModel : ScoreModel {
   }
 };
 
-// scoring/ClosestHit.scala:43-76 ("minot") -- integer aggregate over the same hit list, host side
+// ff_hit_aggregates over all guides at once: closest / count / 0..4 histogram / in-genome occurrences
+struct HitAggregates {
+  std::vector<int32_t> closest, count, hist, inGenome;
+  HitAggregates(NativeContext &nc, const ParameterPack &pack, const std::vector<CRISPRSiteOT> &guides) {
+    std::vector<uint64_t> enc, targets;
+    std::vector<int64_t> rowPtr{0};
+    for (auto &g : guides) {
+      enc.push_back(g.longEncoding);
+      for (auto &ot : g.offTargets) targets.push_back(ot.sequence);
+      rowPtr.push_back((int64_t)targets.size());
+    }
+    ff_hits h{};
+    h.n_guides = (int64_t)guides.size(); h.n_hits = (int64_t)targets.size();
+    h.row_ptr = rowPtr.data(); h.targets = targets.data();
+    const size_t n = guides.size() + 1;
+    closest.assign(n, 0); count.assign(n, 0); hist.assign(n * 5, 0); inGenome.assign(n, 0);
+    ffCheck(ff_hit_aggregates(nc.ctx, pack.index, enc.data(), &h, closest.data(), count.data(), hist.data(), inGenome.data()));
+  }
+};
+
+// scoring/ClosestHit.scala:43-76 ("minot") -- integer aggregate over the same hit list; on the GPU when a native context
+// is supplied (ff_hit_aggregates), otherwise the same reduction on the host
 struct ClosestHit : ScoreModel {
+  NativeContext *nc = nullptr;
   std::string scoreName() const override { return "closest"; }
   std::vector<std::string> headerColumns() const override { return {"basesDiffToClosestHit", "closestHitCount", "0-1-2-3-4_mismatch"}; }
   bool validOverEnzyme(const ParameterPack &) const override { return true; }
-  void scoreGuides(std::vector<CRISPRSiteOT> &guides, const BitEncoding &bitEnc, const ParameterPack &) override {
+  void scoreGuides(std::vector<CRISPRSiteOT> &guides, const BitEncoding &bitEnc, const ParameterPack &pack) override {
+    if (nc) {
+      HitAggregates agg(*nc, pack, guides);
+      for (size_t i = 0; i < guides.size(); ++i) {
+        std::string hs;
+        for (int m = 0; m < 5; ++m) hs += (m ? "," : "") + std::to_string(agg.hist[i * 5 + m]);
+        const bool none = agg.closest[i] == INT32_MAX;
+        guides[i].namedAnnotations["basesDiffToClosestHit"] = {none ? "UNK" : std::to_string(agg.closest[i])};
+        guides[i].namedAnnotations["closestHitCount"] = {none ? "0" : std::to_string(agg.count[i])};
+        guides[i].namedAnnotations["0-1-2-3-4_mismatch"] = {hs};
+      }
+      return;
+    }
     for (auto &g : guides) {
       int closest = INT32_MAX, count = 0, hist[5] = {0, 0, 0, 0, 0};
       for (auto &ot : g.offTargets) {
@@ -454,11 +488,15 @@ struct ClosestHit : ScoreModel {
 
 // scoring/DangerousSequences.scala:49-68
 struct DangerousSequences : ScoreModel {
+  NativeContext *nc = nullptr;
   bool cleanOutput = false;
   std::string scoreName() const override { return "dangerous"; }
   std::vector<std::string> headerColumns() const override { return {"dangerous_GC", "dangerous_polyT", "dangerous_in_genome"}; }
   bool validOverEnzyme(const ParameterPack &) const override { return true; }
   void scoreGuides(std::vector<CRISPRSiteOT> &guides, const BitEncoding &bitEnc, const ParameterPack &pack) override {
+    std::unique_ptr<HitAggregates> agg;
+    if (nc) agg.reset(new HitAggregates(*nc, pack, guides));
+    size_t gi = 0;
     for (auto &g : guides) {
       std::string p0 = cleanOutput ? "0" : "NONE", p1 = p0, p2 = p0;
       const double gc = gcContent(g.target.bases);
@@ -467,8 +505,11 @@ struct DangerousSequences : ScoreModel {
       auto r = pack.guideRange();
       if (g.target.bases.substr(r.first, r.second - r.first).find("TTTT") != std::string::npos) p1 = cleanOutput ? "1" : "PolyT";
       int inGenome = 0;
-      for (auto &ot : g.offTargets)
-        if (bitEnc.mismatches(ot.sequence, g.longEncoding) == 0) inGenome += bitEnc.getCount(ot.sequence);
+      if (agg) inGenome = agg->inGenome[gi];
+      else
+        for (auto &ot : g.offTargets)
+          if (bitEnc.mismatches(ot.sequence, g.longEncoding) == 0) inGenome += bitEnc.getCount(ot.sequence);
+      ++gi;
       if (inGenome > 0) p2 = cleanOutput ? std::to_string(inGenome) : "IN_GENOME=" + std::to_string(inGenome);
       g.namedAnnotations["dangerous_GC"] = {p0};
       g.namedAnnotations["dangerous_polyT"] = {p1};

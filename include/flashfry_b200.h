@@ -121,6 +121,13 @@ void ff_hits_free(ff_hits *hits);
 int ff_score(ff_ctx *ctx, const uint64_t *guides, const ff_hits *hits, uint32_t metrics, double *cfd_max,
              double *cfd_specificity, double *hsu2013, double *per_ot_cfd);
 
+/* Integer aggregates over the same hit lists: scoring/ClosestHit.scala:43-76 ("minot": smallest non-zero mismatch
+ * count, the summed occurrence count at that distance, the 0..4-mismatch occurrence histogram) and the in-genome count
+ * of scoring/DangerousSequences.scala:61-65 (occurrences with zero mismatches).  Outputs are [n_guides]
+ * (hist: [n_guides][5]); closest is INT32_MAX where the reference prints "UNK".  Any output may be NULL. */
+int ff_hit_aggregates(ff_ctx *ctx, int enzyme_index, const uint64_t *guides, const ff_hits *hits, int32_t *closest,
+                      int32_t *closest_count, int32_t *hist, int32_t *in_genome);
+
 /* Fused discover + score: the hit list is scored while still in HBM, then both come back in one D2H. */
 int ff_discover_score(ff_ctx *ctx, const uint64_t *guides, int64_t n_guides, int max_mismatch, int max_off_targets,
                       int want_positions, uint32_t metrics, ff_hits **out, double *cfd_max,

@@ -458,3 +458,46 @@ def test_pipelined_sub_batches_equal_single_batch(ff, oracle, small_db, monkeypa
             helpers.assert_hits_equal(plain, ref)
         withpos = ctx.discover(guides, 4, 2000, positions=True)   # positions force a single batch
         helpers.assert_hits_equal(withpos, ref, check_positions=True)
+
+
+def test_hit_aggregates_minot_and_in_genome(ff, oracle):
+    """ff_hit_aggregates (scoring/ClosestHit.scala:43-76 + the in-genome count of DangerousSequences.scala:61-65) against the
+    oracle on fake.sites, plus the ClosestHitTest.scala:23-59 known answers ("1","70","0,70,20,0,10" ...)."""
+    pack = oracle.pack_by_name("SPCAS9")
+    guides = oracle.read_discover_tsv(os.path.join(GOLDEN, "fake.sites.gz"), pack, filter_overflow=False)
+    enc = np.asarray([g.encoding for g in guides], np.uint64)
+    row_ptr, targets = [0], []
+    for g in guides:
+        targets += g.targets
+        row_ptr.append(len(targets))
+    seq = "GACTTGCATCCGAAGCCGGTGGG"
+
+    def mutate(n, count, salt):
+        s = list(seq)
+        for j in range(n):
+            pos = (3 * j + salt) % 20
+            s[pos] = "ACGT"[("ACGT".index(s[pos]) + 1 + salt % 3) % 4]
+        return oracle.encode("".join(s), count)
+    cases = [([(1, 1)], ("1", "1", "0,1,0,0,0")), ([(1, 40)], ("1", "40", "0,40,0,0,0")),
+             ([(1, 40), (1, 30), (2, 20), (4, 10)], ("1", "70", "0,70,20,0,10")), ([], ("UNK", "0", "0,0,0,0,0")),
+             ([(0, 7), (6, 3)], ("6", "3", "7,0,0,0,0"))]
+    extra_g, extra_rp, extra_t = [], [0], []
+    for ots, _ in cases:
+        extra_g.append(oracle.encode(seq))
+        extra_t += [mutate(n, c, i) for i, (n, c) in enumerate(ots)]
+        extra_rp.append(len(extra_t))
+    with ff.Context(0) as ctx:
+        closest, cnt, hist, ing = ctx.hit_aggregates(pack.index, enc, row_ptr, targets)
+        c2, n2, h2, i2 = ctx.hit_aggregates(pack.index, extra_g, extra_rp, extra_t)
+    t = np.asarray(targets, np.uint64)
+    for i, g in enumerate(guides):
+        ots = t[row_ptr[i]:row_ptr[i + 1]]
+        want = oracle.minot(pack, g.encoding, ots)
+        got = ("UNK" if closest[i] == 2 ** 31 - 1 else str(closest[i]), str(cnt[i]), ",".join(str(x) for x in hist[i]))
+        assert got == want
+        dang = oracle.dangerous(pack, g.site.bases, g.encoding, ots)[2]
+        assert dang == ("IN_GENOME=%d" % ing[i] if ing[i] > 0 else "NONE")
+    for i, (_ots, want) in enumerate(cases):
+        got = ("UNK" if c2[i] == 2 ** 31 - 1 else str(c2[i]), str(n2[i]), ",".join(str(x) for x in h2[i]))
+        assert got == want, (i, got, want)
+    assert i2[4] == 7
