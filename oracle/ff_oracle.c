@@ -240,7 +240,7 @@ static ffo_hits *collect(run_t *r, int64_t n_guides, const uint64_t *db, int wit
 void ffo_hits_free(ffo_hits *h) {
   if (!h) return;
   free(h->row_ptr); free(h->targets); free(h->mismatches); free(h->pos_ptr); free(h->positions);
-  free(h->total_count); free(h->overflowed); free(h);
+  free(h->total_count); free(h->overflowed); free(h->bulge); free(h);
 }
 
 static void init_sub_bins(run_t *r, int bin_width) {
@@ -499,4 +499,82 @@ double ffo_hsu_guide(const ffo_pack *p, uint64_t guide, const uint64_t *ots, int
   for (int64_t i = 0; i < n; i++)
     if (mismatches_raw(p->cmp_mask, guide, ots[i], STRING_MASK) != 0) sum += ffo_hsu_offtarget(guide, ots[i]); /* :90 */
   return (100.0 / (100.0 + sum)) * 100.0;
+}
+
+/* ================================================================================================ */
+/* EXTENSION: 1-bp bulge mode.  Not in the reference (PARITY UNPINNED); semantics defined in ff_oracle.h.
+ * Deliberately written base by base (no bit tricks) so that it shares nothing with the CUDA implementation. */
+void ffo_bulge_align(uint64_t guide, uint64_t target, int flags, int *mm_out, int *type_out, int *pos_out) {
+  int g[20], t[20];
+  for (int j = 0; j < 20; j++) { g[j] = base_at(guide, 23, j); t[j] = base_at(target, 23, j); }
+  int best = 0, btype = 0, bpos = 0;
+  for (int j = 0; j < 20; j++) best += g[j] != t[j];
+  if (flags & FFO_BULGE_RNA)
+    for (int q = 1; q <= 18; q++) {
+      int mm = 0;
+      for (int j = 1; j < 20; j++) mm += t[j] != (j <= q ? g[j - 1] : g[j]);
+      if (mm < best) { best = mm; btype = 1; bpos = q; }
+    }
+  if (flags & FFO_BULGE_DNA)
+    for (int q = 1; q <= 18; q++) {
+      int mm = 0;
+      for (int j = 0; j < 20; j++) if (j != q) mm += t[j] != (j < q ? g[j + 1] : g[j]);
+      if (mm < best) { best = mm; btype = 2; bpos = q; }
+    }
+  *mm_out = best; *type_out = btype; *pos_out = bpos;
+}
+
+int ffo_discover_bulge(const ffo_pack *p, const uint64_t *targets, int64_t n_targets, const uint64_t *guides,
+                       int64_t n_guides, int max_mismatch, int max_off_targets, int flags, int n_threads,
+                       ffo_hits **out) {
+  if (p->scan_len != 23 || p->five_prime) return -1;
+  ffo_hits *h = (ffo_hits *)calloc(1, sizeof(ffo_hits));
+  h->n_guides = n_guides;
+  h->row_ptr = (int64_t *)calloc((size_t)n_guides + 1, 8);
+  h->total_count = (int32_t *)calloc((size_t)n_guides + 1, 4);
+  h->overflowed = (uint8_t *)calloc((size_t)n_guides + 1, 1);
+  /* per guide: hit lists gathered independently (guides never interact), then concatenated */
+  int64_t **idx = (int64_t **)calloc((size_t)n_guides + 1, sizeof(int64_t *));
+  uint8_t **info = (uint8_t **)calloc((size_t)n_guides + 1, sizeof(uint8_t *));
+  int64_t *cnt = (int64_t *)calloc((size_t)n_guides + 1, 8);
+  (void)n_threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+  for (int64_t g = 0; g < n_guides; g++) {
+    int64_t cap = 64, n = 0;
+    int64_t *ix = (int64_t *)malloc((size_t)cap * 8);
+    uint8_t *inf = (uint8_t *)malloc((size_t)cap * 2);
+    int32_t total = 0;
+    for (int64_t i = 0; i < n_targets && total < max_off_targets; i++) { /* append while currentTotal < overflow */
+      int mm, type, pos;
+      ffo_bulge_align(guides[g], targets[i], flags, &mm, &type, &pos);
+      if (mm > max_mismatch) continue;
+      if (n == cap) { cap *= 2; ix = (int64_t *)realloc(ix, (size_t)cap * 8); inf = (uint8_t *)realloc(inf, (size_t)cap * 2); }
+      ix[n] = i; inf[2 * n] = (uint8_t)mm; inf[2 * n + 1] = (uint8_t)(type ? ((type == 1 ? 0x40 : 0x80) | pos) : 0);
+      n++;
+      total += (int)(int16_t)(targets[i] >> 48);
+    }
+    idx[g] = ix; info[g] = inf; cnt[g] = n;
+    h->total_count[g] = total;
+    h->overflowed[g] = total >= max_off_targets;
+  }
+  int64_t nh = 0;
+  for (int64_t g = 0; g < n_guides; g++) { h->row_ptr[g] = nh; nh += cnt[g]; }
+  h->row_ptr[n_guides] = nh;
+  h->targets = (uint64_t *)malloc((size_t)(nh + 1) * 8);
+  h->mismatches = (uint8_t *)malloc((size_t)nh + 1);
+  h->bulge = (uint8_t *)malloc((size_t)nh + 1);
+  for (int64_t g = 0, k = 0; g < n_guides; g++) {
+    for (int64_t i = 0; i < cnt[g]; i++, k++) {
+      h->targets[k] = targets[idx[g][i]];
+      h->mismatches[k] = info[g][2 * i];
+      h->bulge[k] = info[g][2 * i + 1];
+    }
+    free(idx[g]); free(info[g]);
+  }
+  free(idx); free(info); free(cnt);
+  h->n_targets_scanned = (uint64_t)n_targets;
+  *out = h;
+  return 0;
 }

@@ -59,6 +59,7 @@ typedef struct {
   uint64_t n_targets_scanned;
   int saturated;           /* OrderedBinTraversalFactory.saturated -> linear traversal taken */
   int bins_visited;
+  uint8_t *bulge;          /* only from ffo_discover_bulge (extension, see below): 0 = no bulge, 0x40|q RNA, 0x80|q DNA */
 } ffo_hits;
 
 void ffo_hits_free(ffo_hits *h);
@@ -96,6 +97,32 @@ void ffo_cfd_guide(uint64_t guide, const uint64_t *ots, int64_t n, double *max_o
 double ffo_hsu_offtarget(uint64_t guide, uint64_t off_target);
 /* CrisprMitEduOffTarget.scala:60,85-105 score_crispr */
 double ffo_hsu_guide(const ffo_pack *p, uint64_t guide, const uint64_t *ots, int64_t n);
+
+/* ---------------------------------------------------------------------------------------------------
+ * EXTENSION -- 1-bp bulge mode (BASELINE.json configs[3]).  The reference has NO gap / bulge /
+ * edit-distance mode: these functions restate nothing, they DEFINE the semantics the CUDA path is
+ * tested against.  PARITY UNPINNED (there is no reference behaviour to pin to); never part of a parity claim.
+ *
+ * Definition (20-base protospacer packs with a 3' PAM only; g = guide protospacer, t = target protospacer, base 0
+ * is PAM-distal, both PAM-anchored; q in 1..18):
+ *   no bulge      : mm = #{ j in 0..19 : g[j] != t[j] }                               (= BitEncoding.mismatches)
+ *   RNA bulge at q: guide base q is looped out; the other 19 guide bases pair with the 19 genomic bases next to the
+ *                   PAM:  mm = hamming( g[0..q) + g(q..19] , t[1..19] );  t[0] lies outside the alignment
+ *   DNA bulge at q: genomic base q is looped out; the other 19 stored genomic bases pair with g[1..19]:
+ *                   mm = hamming( g[1..19] , t[0..q) + t(q..19] );  g[0] would pair with the genomic base upstream of
+ *                   the stored 23-mer, which a FlashFry database does not hold, so it is not scored
+ * A target is a hit when the best alignment allowed by `flags` (bit0 RNA, bit1 DNA; the no-bulge alignment always)
+ * has mm <= max_mismatch; best = smallest (mm, type [none < RNA < DNA], q).  Hit order and the overflow rule are the
+ * reference's (database order, ResultsAggregator.scala:61-69).
+ */
+#define FFO_BULGE_RNA 1
+#define FFO_BULGE_DNA 2
+/* best alignment of one pair; *type 0 none / 1 RNA / 2 DNA, *pos = q (0 when none) */
+void ffo_bulge_align(uint64_t guide, uint64_t target, int flags, int *mm, int *type, int *pos);
+/* brute force over all targets (database order); hits->bulge is filled */
+int ffo_discover_bulge(const ffo_pack *p, const uint64_t *targets, int64_t n_targets, const uint64_t *guides,
+                       int64_t n_guides, int max_mismatch, int max_off_targets, int flags, int n_threads,
+                       ffo_hits **out);
 
 #ifdef __cplusplus
 }

@@ -96,7 +96,7 @@ class _CHits(C.Structure):
                 ("positions", C.POINTER(C.c_uint64)), ("total_count", C.POINTER(C.c_int32)),
                 ("overflowed", C.POINTER(C.c_uint8)), ("n_compares", C.c_uint64),
                 ("n_target_compares", C.c_uint64), ("n_targets_scanned", C.c_uint64),
-                ("saturated", C.c_int), ("bins_visited", C.c_int)]
+                ("saturated", C.c_int), ("bins_visited", C.c_int), ("bulge", C.POINTER(C.c_uint8))]
 
 
 _lib = None
@@ -127,6 +127,11 @@ def lib():
         _lib.ffo_discover_soa.argtypes = [C.POINTER(_CPack), C.c_int, u64p, i64p, u64p, C.c_int64, C.c_int,
                                           C.c_int, C.c_int, C.POINTER(C.POINTER(_CHits))]
         _lib.ffo_hits_free.argtypes = [C.POINTER(_CHits)]
+        _lib.ffo_bulge_align.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int)]
+        _lib.ffo_bulge_align.restype = None
+        _lib.ffo_discover_bulge.argtypes = [C.POINTER(_CPack), u64p, C.c_int64, u64p, C.c_int64, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.POINTER(C.POINTER(_CHits))]
         _lib.ffo_cfd_pair.restype = C.c_double
         _lib.ffo_cfd_pair.argtypes = [C.c_uint64, C.c_uint64]
         _lib.ffo_cfd_guide.argtypes = [C.c_uint64, u64p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -222,6 +227,7 @@ class Hits:
     n_targets_scanned: int = 0
     saturated: bool = False
     bins_visited: int = 0
+    bulge: Optional[np.ndarray] = None   # extension (discover_bulge): 0 none, 0x40|q RNA bulge, 0x80|q DNA bulge
 
     def row(self, g: int) -> Tuple[np.ndarray, np.ndarray]:
         lo, hi = int(self.row_ptr[g]), int(self.row_ptr[g + 1])
@@ -248,6 +254,8 @@ def _take(hp, with_pos: bool) -> Hits:
         positions = np.ctypeslib.as_array(h.positions, shape=(max(npos, 1),))[:npos].copy()
     out = Hits(row_ptr, targets, mm, total, ovf, pos_ptr, positions, int(h.n_compares), int(h.n_target_compares),
                int(h.n_targets_scanned), bool(h.saturated), int(h.bins_visited))
+    if h.bulge:
+        out.bulge = np.ctypeslib.as_array(h.bulge, shape=(max(nh, 1),))[:nh].copy()
     lib().ffo_hits_free(hp)
     return out
 
@@ -323,6 +331,45 @@ def discover_soa(pack: ParameterPack, bin_width: int, targets: np.ndarray, bin_o
                                 max_mismatch, max_off_targets, n_threads, C.byref(hp))
     if rc != 0:
         raise RuntimeError("discover_soa failed rc=%d" % rc)
+    return _take(hp, False)
+
+
+# -- EXTENSION: 1-bp bulge mode (not in the reference; PARITY UNPINNED -- semantics defined in ff_oracle.h) ------
+BULGE_RNA, BULGE_DNA = 1, 2
+
+
+def bulge_align(guide: int, target: int, flags: int = 3) -> Tuple[int, int, int]:
+    """(mismatches, type 0 none / 1 RNA / 2 DNA, bulge position q) of the best alignment (ffo_bulge_align)."""
+    mm, ty, pos = C.c_int(), C.c_int(), C.c_int()
+    lib().ffo_bulge_align(guide, target, flags, C.byref(mm), C.byref(ty), C.byref(pos))
+    return mm.value, ty.value, pos.value
+
+
+def bulge_align_strings(g: str, t: str, flags: int = 3) -> Tuple[int, int, int]:
+    """The same definition on 20-base strings, written as string surgery (independent of the C code):
+    RNA bulge at q = delete guide base q, align with t[1:]; DNA bulge at q = delete target base q, align with g[1:]."""
+    ham = lambda a, b: sum(x != y for x, y in zip(a, b))
+    assert len(g) == 20 and len(t) == 20
+    best = (ham(g, t), 0, 0)
+    if flags & BULGE_RNA:
+        for q in range(1, 19):
+            best = min(best, (ham(g[:q] + g[q + 1:], t[1:]), 1, q))
+    if flags & BULGE_DNA:
+        for q in range(1, 19):
+            best = min(best, (ham(g[1:], t[:q] + t[q + 1:]), 2, q))
+    return best
+
+
+def discover_bulge(pack: ParameterPack, targets: np.ndarray, guides: Sequence[int], max_mismatch: int = 4,
+                   max_off_targets: int = 2000, flags: int = 3, n_threads: int = 1) -> Hits:
+    """Brute-force bulge-mode discover over targets in database order (ffo_discover_bulge)."""
+    g = np.ascontiguousarray(np.asarray(guides, dtype=np.uint64))
+    t = np.ascontiguousarray(targets, dtype=np.uint64)
+    hp = C.POINTER(_CHits)()
+    rc = lib().ffo_discover_bulge(C.byref(_cpack(pack)), _u64p(t), len(t), _u64p(g), len(g), max_mismatch,
+                                  max_off_targets, flags, n_threads, C.byref(hp))
+    if rc != 0:
+        raise RuntimeError("bulge mode needs a 23-bp 3'-PAM Cas9 pack (rc=%d)" % rc)
     return _take(hp, False)
 
 
