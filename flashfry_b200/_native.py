@@ -10,6 +10,8 @@ LIB_PATH = os.environ.get("FLASHFRY_B200_LIB") or os.path.join(HERE, "libflashfr
 
 FF_METRIC_CFD = 1
 FF_METRIC_HSU2013 = 2
+FF_BULGE_RNA = 1
+FF_BULGE_DNA = 2
 
 ERRORS = {0: "FF_OK", -1: "FF_EINVAL", -2: "FF_ENODEVICE", -3: "FF_ECUDA", -4: "FF_EIO", -5: "FF_EFORMAT",
           -6: "FF_ENODB", -7: "FF_EUNSUPPORTED", -8: "FF_ENOMEM"}
@@ -26,7 +28,8 @@ class FFHits(C.Structure):
                 ("targets", C.POINTER(C.c_uint64)), ("mismatches", C.POINTER(C.c_uint8)),
                 ("pos_ptr", C.POINTER(C.c_int64)), ("positions", C.POINTER(C.c_uint64)),
                 ("total_count", C.POINTER(C.c_int32)), ("overflowed", C.POINTER(C.c_uint8)),
-                ("n_compares", C.c_uint64), ("n_candidate_hits", C.c_uint64), ("opaque", C.c_void_p)]
+                ("n_compares", C.c_uint64), ("n_candidate_hits", C.c_uint64), ("opaque", C.c_void_p),
+                ("bulge", C.POINTER(C.c_uint8))]
 
 
 class FFDbInfo(C.Structure):
@@ -40,7 +43,8 @@ class FFDeviceResult(C.Structure):
     _fields_ = [("n_guides", C.c_int64), ("n_hits", C.c_int64), ("n_candidate_hits", C.c_uint64),
                 ("n_compares", C.c_uint64), ("d_row_ptr", C.c_void_p), ("d_targets", C.c_void_p),
                 ("d_mismatches", C.c_void_p), ("d_total_count", C.c_void_p), ("d_overflowed", C.c_void_p),
-                ("d_cfd_max", C.c_void_p), ("d_cfd_specificity", C.c_void_p), ("d_hsu2013", C.c_void_p)]
+                ("d_cfd_max", C.c_void_p), ("d_cfd_specificity", C.c_void_p), ("d_hsu2013", C.c_void_p),
+                ("d_bulge", C.c_void_p)]
 
 
 class FFTimings(C.Structure):
@@ -52,7 +56,7 @@ class FFTimings(C.Structure):
 # every symbol include/flashfry_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_load_database",
            "ff_load_database_arrays", "ff_synth_database", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
-           "ff_discover", "ff_hits_free", "ff_score", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
+           "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_score", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
 
 _lib = None
 
@@ -80,6 +84,8 @@ def lib():
     L.ff_db_contig.restype = C.c_char_p
     L.ff_db_copy_targets.argtypes = [vp, C.c_uint64, C.c_uint64, u64p]
     L.ff_discover.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(FFHits))]
+    L.ff_discover_bulge.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(FFHits))]
+    L.ff_discover_bulge_device.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(FFDeviceResult)]
     L.ff_hits_free.argtypes = [C.POINTER(FFHits)]
     L.ff_hits_free.restype = None
     L.ff_score.argtypes = [vp, u64p, C.POINTER(FFHits), C.c_uint32, dp, dp, dp, dp]

@@ -9,7 +9,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _native as N
-from ._native import FF_METRIC_CFD, FF_METRIC_HSU2013, FlashFryError  # noqa: F401
+from ._native import FF_BULGE_DNA, FF_BULGE_RNA, FF_METRIC_CFD, FF_METRIC_HSU2013, FlashFryError  # noqa: F401
 
 
 @dataclass
@@ -24,6 +24,7 @@ class Hits:
     positions: Optional[np.ndarray]
     n_compares: int
     n_candidate_hits: int
+    bulge: Optional[np.ndarray] = None  # ff_discover_bulge only: 0 none, 0x40|q RNA bulge, 0x80|q DNA bulge
 
     @property
     def n_guides(self) -> int:
@@ -50,6 +51,8 @@ def _take_hits(hp) -> Hits:
         positions = _arr(h.positions, int(pos_ptr[-1]), np.uint64)
     out = Hits(row_ptr, _arr(h.targets, H, np.uint64), _arr(h.mismatches, H, np.uint8), _arr(h.total_count, G, np.int32),
                _arr(h.overflowed, G, np.uint8), pos_ptr, positions, int(h.n_compares), int(h.n_candidate_hits))
+    if h.bulge:
+        out.bulge = _arr(h.bulge, H, np.uint8)
     N.lib().ff_hits_free(hp)
     return out
 
@@ -123,6 +126,22 @@ class Context:
         N.check(N.lib().ff_discover(self._h, g.ctypes.data_as(C.POINTER(C.c_uint64)), len(g), max_mismatch,
                                     maximum_off_targets, int(positions), C.byref(hp)))
         return _take_hits(hp)
+
+    def discover_bulge(self, guides, max_mismatch: int = 4, maximum_off_targets: int = 2000,
+                       bulge_flags: int = N.FF_BULGE_RNA | N.FF_BULGE_DNA, positions: bool = False) -> Hits:
+        """ff_discover_bulge (extension: 1-bp RNA / DNA bulges; see include/flashfry_b200.h)."""
+        g = _u64(guides)
+        hp = C.POINTER(N.FFHits)()
+        N.check(N.lib().ff_discover_bulge(self._h, g.ctypes.data_as(C.POINTER(C.c_uint64)), len(g), max_mismatch,
+                                          maximum_off_targets, bulge_flags, int(positions), C.byref(hp)))
+        return _take_hits(hp)
+
+    def discover_bulge_device(self, d_guides_ptr: int, n_guides: int, max_mismatch: int = 4, maximum_off_targets: int = 2000,
+                              bulge_flags: int = N.FF_BULGE_RNA | N.FF_BULGE_DNA) -> N.FFDeviceResult:
+        r = N.FFDeviceResult()
+        N.check(N.lib().ff_discover_bulge_device(self._h, C.c_void_p(d_guides_ptr), n_guides, max_mismatch, maximum_off_targets,
+                                                 bulge_flags, C.byref(r)))
+        return r
 
     def discover_score(self, guides, max_mismatch: int = 4, maximum_off_targets: int = 2000, positions: bool = False,
                        metrics: int = FF_METRIC_CFD | FF_METRIC_HSU2013):

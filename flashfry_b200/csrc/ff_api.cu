@@ -55,7 +55,7 @@ void HostBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 // discover calls do not pay cudaHostAlloc.
 struct HitsOwner {
   ff_hits pub;
-  HostBuf row_ptr, targets, mm, pos_ptr, positions, total, ovf;
+  HostBuf row_ptr, targets, mm, bulge, pos_ptr, positions, total, ovf;
 };
 static std::mutex g_pool_mu;
 static std::vector<HitsOwner *> g_pool;
@@ -68,7 +68,7 @@ static HitsOwner *owner_get() {
 static void owner_put(HitsOwner *o) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
   if (g_pool.size() < 4) { g_pool.push_back(o); return; }
-  o->row_ptr.release(); o->targets.release(); o->mm.release(); o->pos_ptr.release(); o->positions.release();
+  o->row_ptr.release(); o->targets.release(); o->mm.release(); o->bulge.release(); o->pos_ptr.release(); o->positions.release();
   o->total.release(); o->ovf.release();
   delete o;
 }
@@ -112,7 +112,8 @@ static void add_timings(ff_timings *acc, const ff_timings &t) {
 // The host-facing discover: guides come from host memory, results go back to pinned host memory.  Large guide sets are
 // cut into a few sub-batches; the D2H of sub-batch i runs on the copy stream while sub-batch i+1 is being scanned.
 static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions,
-                         uint32_t metrics, ff_hits **out, double *cfd_max, double *cfd_spec, double *hsu) {
+                         uint32_t metrics, ff_hits **out, double *cfd_max, double *cfd_spec, double *hsu, int bulge_flags = 0,
+                         bool bulge_api = false) {
   if (!c || !out || (n_guides > 0 && !guides)) { set_error("null argument"); return FF_EINVAL; }
   *out = nullptr;
   FF_CUDA(cudaSetDevice(c->device));
@@ -144,7 +145,7 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
     batch_g0[b] = g0;
     if (b >= 2) { cudaError_t e = cudaEventSynchronize(c->slot_copied[slot]); if (e != cudaSuccess) return fail(cuda_fail(e, "event sync", __FILE__, __LINE__)); }
     DeviceResult r;
-    if ((rc = discover_on_device(c, d_guides + g0, gn, max_mm, max_ot, want_positions != 0, slot, &r)) != FF_OK) return fail(rc);
+    if ((rc = discover_on_device(c, d_guides + g0, gn, max_mm, max_ot, want_positions != 0, bulge_flags, slot, &r)) != FF_OK) return fail(rc);
     add_timings(&acc, c->last);
     if (metrics) {
       if ((rc = score_slot(c, d_guides + g0, r, metrics, slot)) != FF_OK) return fail(rc);
@@ -153,12 +154,17 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
     n_compares += r.n_compares; n_cand += r.n_candidate_hits;
     const int64_t H = r.n_hits;
     if ((rc = grow_pinned(c, o->targets, (size_t)hit_off * 8, (size_t)(hit_off + H + 1) * 8)) ||
-        (rc = grow_pinned(c, o->mm, (size_t)hit_off, (size_t)(hit_off + H + 1))))
+        (rc = grow_pinned(c, o->mm, (size_t)hit_off, (size_t)(hit_off + H + 1))) ||
+        (bulge_api && (rc = grow_pinned(c, o->bulge, (size_t)hit_off, (size_t)(hit_off + H + 1)))))
       return fail(rc);
     // the compute stream is idle here (discover_on_device synchronises), so the slot's contents are final
     cudaError_t e = cudaMemcpyAsync(o->row_ptr.as<int64_t>() + g0, r.d_row_ptr, (gn + 1) * 8, cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->targets.as<uint64_t>() + hit_off, r.d_targets, H * 8, cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->mm.as<uint8_t>() + hit_off, r.d_mismatches, H, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && bulge_api && H > 0) {
+      if (r.d_bulge) e = cudaMemcpyAsync(o->bulge.as<uint8_t>() + hit_off, r.d_bulge, H, cudaMemcpyDeviceToHost, cs);
+      else memset(o->bulge.as<uint8_t>() + hit_off, 0, (size_t)H);
+    }
     if (e == cudaSuccess && gn > 0) e = cudaMemcpyAsync(o->total.as<int32_t>() + g0, r.d_total_count, gn * 4, cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess && gn > 0) e = cudaMemcpyAsync(o->ovf.as<uint8_t>() + g0, r.d_overflowed, gn, cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess && metrics && gn > 0) {
@@ -194,6 +200,7 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   h.positions = with_pos ? o->positions.as<uint64_t>() : nullptr;
   h.total_count = o->total.as<int32_t>(); h.overflowed = o->ovf.as<uint8_t>();
   h.n_compares = n_compares; h.n_candidate_hits = n_cand;
+  h.bulge = bulge_api ? o->bulge.as<uint8_t>() : nullptr;
   h.opaque = o;
   *out = &h;
   return FF_OK;
@@ -205,7 +212,7 @@ using namespace ff;
 
 extern "C" {
 
-int ff_abi_version(void) { return 1; }
+int ff_abi_version(void) { return 2; }
 const char *ff_last_error(void) { return g_err; }
 
 int ff_create(ff_ctx **out, int device_id) {
@@ -248,10 +255,11 @@ void ff_destroy(ff_ctx *c) {
   c->db.release();
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys, &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->out_tidx, &c->pos_cnt,
-                    &c->pos_ptr, &c->out_positions, &c->cfd_per_ot, &c->hsu_per_ot, &c->scratch_guides};
+                    &c->pos_ptr, &c->out_positions, &c->cfd_per_ot, &c->hsu_per_ot, &c->scratch_guides, &c->running, &c->active, &c->active2,
+                    &c->act_flags, &c->seg_end, &c->kept_keys, &c->kept_sorted, &c->n_sel};
   for (DevBuf *b : bufs) b->release();
   for (auto &os : c->out) {
-    DevBuf *ob[] = {&os.row_ptr, &os.total_count, &os.overflowed, &os.out_targets, &os.out_mm, &os.cfd_max, &os.cfd_spec, &os.hsu};
+    DevBuf *ob[] = {&os.row_ptr, &os.total_count, &os.overflowed, &os.out_targets, &os.out_mm, &os.out_bulge, &os.cfd_max, &os.cfd_spec, &os.hsu};
     for (DevBuf *b : ob) b->release();
   }
   for (auto &ev : c->slot_copied) if (ev) cudaEventDestroy(ev);
@@ -328,6 +336,12 @@ int ff_discover_score(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int m
   return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, metrics, out, cfd_max, cfd_spec, hsu);
 }
 
+int ff_discover_bulge(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int bulge_flags, int want_positions,
+                      ff_hits **out) {
+  if (bulge_flags & ~(FF_BULGE_RNA | FF_BULGE_DNA)) { set_error("unknown bulge flag"); return FF_EINVAL; }
+  return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, 0, out, nullptr, nullptr, nullptr, bulge_flags, true);
+}
+
 void ff_hits_free(ff_hits *h) {
   if (!h || !h->opaque) return;
   owner_put(static_cast<HitsOwner *>(h->opaque));
@@ -401,14 +415,29 @@ int ff_discover_device(ff_ctx *c, const uint64_t *d_guides, int64_t n_guides, in
   if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
   FF_CUDA(cudaSetDevice(c->device));
   DeviceResult r;
-  FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, 0, &r));
+  FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, 0, 0, &r));
   FF_TRY(score_slot(c, d_guides, r, metrics, 0));
+  out->d_bulge = nullptr;
   out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
   out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
   out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
   out->d_cfd_max = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_max.as<double>() : nullptr;
   out->d_cfd_specificity = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_spec.as<double>() : nullptr;
   out->d_hsu2013 = (metrics & FF_METRIC_HSU2013) ? c->out[0].hsu.as<double>() : nullptr;
+  return FF_OK;
+}
+
+int ff_discover_bulge_device(ff_ctx *c, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot, int bulge_flags,
+                             ff_device_result *out) {
+  if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  DeviceResult r;
+  FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, bulge_flags, 0, &r));
+  out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
+  out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
+  out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
+  out->d_cfd_max = out->d_cfd_specificity = out->d_hsu2013 = nullptr;
+  out->d_bulge = r.d_bulge;
   return FF_OK;
 }
 

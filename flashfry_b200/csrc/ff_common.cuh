@@ -61,6 +61,8 @@ struct SeedIndex {
   uint32_t *d_canon = nullptr;  // [n] database-order index of every entry; nullptr when the order IS database order
   uint32_t *d_masks = nullptr;  // [4^w] XOR masks sorted by Hamming distance (in bases): mask | distance << 24
   int cum[16] = {0};            // cum[h] = # masks at distance <= h (h = 0..w)
+  uint32_t *d_masks_w1 = nullptr;  // the same table over w-1 bases (bulge patterns: one key base is a wildcard)
+  int cum_w1[16] = {0};
   void release();
 };
 
@@ -76,10 +78,16 @@ struct Database {
   uint64_t *d_positions = nullptr; // [n_positions]
   SeedIndex A;                  // keyed by the first a protospacer bases, other = the last P-a bases
   SeedIndex B;                  // keyed by the last P-a bases, other = the first a bases
+  // database-order windows (early termination of overflowed guides): the index-A key space is cut into kCells equal
+  // cells; d_cell_off[key_b * (kCells + 1) + c] = first entry of B bucket key_b whose database index lies in cell >= c.
+  // Built on first use (3'-PAM databases only: their index-A order is database order).
+  uint32_t *d_cell_off = nullptr;
   uint64_t device_bytes = 0;
   std::vector<std::string> contigs;
   void release();
 };
+
+constexpr int kCells = 64;  // database-order cells of the windowed scan (4^3: the first three key bases)
 
 struct Hits;  // host-side result owner (ff_api.cu)
 
@@ -98,9 +106,11 @@ struct ff_ctx {
   ff::DevBuf pos_cnt, pos_ptr, out_positions;
   ff::DevBuf cfd_per_ot, hsu_per_ot;
   ff::DevBuf scratch_guides;  // H2D staging target for ff_discover
+  // windowed / bulge discover: per-guide running totals, the active guide list (two copies), kept keys, scratch
+  ff::DevBuf running, active, active2, act_flags, seg_end, kept_keys, kept_sorted, n_sel;
   // results of a discover call; two sets so that the D2H of one guide sub-batch overlaps the scan of the next
   struct OutSlot {
-    ff::DevBuf row_ptr, total_count, overflowed, out_targets, out_mm, cfd_max, cfd_spec, hsu;
+    ff::DevBuf row_ptr, total_count, overflowed, out_targets, out_mm, out_bulge, cfd_max, cfd_spec, hsu;
   } out[2];
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t slot_copied[2] = {nullptr, nullptr};  // D2H of the slot's previous contents has finished

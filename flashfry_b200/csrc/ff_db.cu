@@ -44,12 +44,12 @@ int pack_from_index(int idx, Pack *o) {
 }
 
 void SeedIndex::release() {
-  cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks);
+  cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks); cudaFree(d_masks_w1);
   *this = SeedIndex();
 }
 
 void Database::release() {
-  cudaFree(d_targets); cudaFree(d_pos_off); cudaFree(d_positions);
+  cudaFree(d_targets); cudaFree(d_pos_off); cudaFree(d_positions); cudaFree(d_cell_off);
   A.release(); B.release();
   *this = Database();
 }
@@ -146,10 +146,14 @@ static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, const uin
   make_masks(key_bases, &masks, ix->cum);
   FF_CUDA(cudaMalloc(&ix->d_masks, masks.size() * 4));
   FF_CUDA(cudaMemcpyAsync(ix->d_masks, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice, st));
+  std::vector<uint32_t> masks_w1;
+  make_masks(key_bases - 1, &masks_w1, ix->cum_w1);
+  FF_CUDA(cudaMalloc(&ix->d_masks_w1, masks_w1.size() * 4));
+  FF_CUDA(cudaMemcpyAsync(ix->d_masks_w1, masks_w1.data(), masks_w1.size() * 4, cudaMemcpyHostToDevice, st));
   FF_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_sorted);
   FF_CUDA(cudaGetLastError());
-  ctx->db.device_bytes += ((size_t)n_keys + 1) * 4 + (n + 64) * 4 + (identity ? 0 : (n + 1) * 4) + masks.size() * 4;
+  ctx->db.device_bytes += ((size_t)n_keys + 1) * 4 + (n + 64) * 4 + (identity ? 0 : (n + 1) * 4) + masks.size() * 4 + masks_w1.size() * 4;
   return FF_OK;
 }
 
@@ -212,6 +216,38 @@ int db_build_index(ff_ctx *ctx) {
   }
   FF_CUDA(cudaGetLastError());
   db.resident = true;
+  return FF_OK;
+}
+
+// d_cell_off[key_b * (kCells + 1) + c] = first entry of B bucket key_b whose database index is >= the first database
+// index of cell c (cell c = index-A keys [c, c + 1) * 4^a / kCells); entries of a B bucket are in database order
+// (stable sort), so a window of cells is a contiguous run of every bucket.
+__global__ void k_cell_offsets(const uint32_t *__restrict__ off_a, const uint32_t *__restrict__ off_b, const uint32_t *__restrict__ canon_b,
+                               uint32_t n_keys_b, uint32_t keys_per_cell, uint32_t *__restrict__ out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)n_keys_b * (kCells + 1)) return;
+  const uint32_t kb = (uint32_t)(i / (kCells + 1)), c = (uint32_t)(i % (kCells + 1));
+  const uint32_t want = off_a[c * keys_per_cell];  // first database index of cell c (c == kCells: n_targets)
+  uint32_t lo = off_b[kb], hi = off_b[kb + 1];
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (canon_b[mid] < want) lo = mid + 1; else hi = mid;
+  }
+  out[i] = lo;
+}
+
+int db_build_cell_offsets(ff_ctx *ctx) {
+  Database &db = ctx->db;
+  if (db.d_cell_off) return FF_OK;
+  if (db.pack.five_prime || db.A.d_canon || db.A.key_bases < 3) { set_error("database-order windows need a 3'-PAM database"); return FF_EUNSUPPORTED; }
+  const uint32_t n_keys_b = 1u << (2 * db.B.key_bases);
+  const uint32_t keys_per_cell = (1u << (2 * db.A.key_bases)) / kCells;
+  const uint64_t n = (uint64_t)n_keys_b * (kCells + 1);
+  FF_CUDA(cudaMalloc(&db.d_cell_off, n * 4));
+  k_cell_offsets<<<nblk(n), 256, 0, ctx->stream>>>(db.A.d_off, db.B.d_off, db.B.d_canon, n_keys_b, keys_per_cell, db.d_cell_off);
+  FF_CUDA(cudaStreamSynchronize(ctx->stream));
+  FF_CUDA(cudaGetLastError());
+  db.device_bytes += n * 4;
   return FF_OK;
 }
 

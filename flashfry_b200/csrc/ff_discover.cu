@@ -112,13 +112,17 @@ __device__ __forceinline__ int base_dist32(uint32_t x) {  // # non-zero 2-bit di
 // XOR / fold / POPC and ONE branch in the common case.  The rare path (some entry within budget) is a compact rolled
 // loop so that the hot loop stays small in the instruction cache: it applies the bucket-range check (the 16-byte
 // aligned chunk may straddle the neighbouring buckets) and, in pass B, the d1 > hA rule, then emits.
-template <bool PASS_B>
+// PAT (bulge patterns): the probed part may hold the pattern's wildcard base, which `pmask` drops from the count, and
+// the d1 > hA threshold comes with the work item (it differs between pattern classes).
+template <bool PASS_B, bool PAT>
 __device__ __forceinline__ void verify_chunk(const ScanParams &p, const WarpHits &wh, const uint32_t *canon, uint4 v, uint32_t base,
-                                             uint32_t lo, uint32_t hi, uint32_t probe, int budget, uint64_t guide_key) {
+                                             uint32_t lo, uint32_t hi, uint32_t probe, int budget, uint64_t guide_key,
+                                             uint32_t pmask, int pat_lo_d) {
+  if (PAT) { v.x = (v.x ^ probe) & pmask; v.y = (v.y ^ probe) & pmask; v.z = (v.z ^ probe) & pmask; v.w = (v.w ^ probe) & pmask; probe = 0; }
   const int d0 = base_dist32(v.x ^ probe), d1 = base_dist32(v.y ^ probe), d2 = base_dist32(v.z ^ probe), d3 = base_dist32(v.w ^ probe);
   if (min(min(d0, d1), min(d2, d3)) <= budget) {
     // rare path: which of the four entries are inside the bucket and within budget (and, in pass B, have d1 > hA)
-    const int lo_d = PASS_B ? wh.hA : -1;
+    const int lo_d = PASS_B ? (PAT ? pat_lo_d : wh.hA) : -1;
     unsigned int ok = 0;
     ok |= (d0 <= budget && d0 > lo_d && base + 0 >= lo && base + 0 < hi) ? 1u : 0u;
     ok |= (d1 <= budget && d1 > lo_d && base + 1 >= lo && base + 1 < hi) ? 2u : 0u;
@@ -141,17 +145,54 @@ __device__ __forceinline__ void verify_chunk(const ScanParams &p, const WarpHits
 // bucket of the group is requested back to back before any of them is verified, so each lane keeps FF_GROUP 128-bit
 // loads in flight (tools/gather_bw.cu: random 288-byte runs reach 2.4 TB/s with one load in flight per warp, 4.3 TB/s
 // with four).
-template <bool PASS_B>
+// What one (pattern, pass) work item of the bulge / windowed scan adds to the plain scan.
+struct PatItem {
+  const uint32_t *masks;    // mask table of this item: full key width, or width - 1 when the key holds the wildcard base
+  int wild_bit;             // bit offset of the wildcard base inside the key, -1 = none
+  uint32_t pmask;           // applied to (entry ^ probe): drops the wildcard base when it lies in the probed part
+  int lo_d;                 // pass B accepts only d1 > lo_d
+  int c0, c1;               // database-order window: cells [c0, c1) of kCells
+  int cell_shift;           // index-A key >> cell_shift = its cell
+  const uint32_t *cell_off; // pass B: per-bucket offsets at the cell boundaries (nullptr = whole database)
+};
+
+template <bool PASS_B, bool PAT>
 __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &sd, const WarpHits &wh, int lane, uint32_t key,
-                                           uint32_t probe, int seed0, int n, uint64_t guide_key, unsigned long long &compares) {
+                                           uint32_t probe, int seed0, int n, uint64_t guide_key, unsigned long long &compares,
+                                           const PatItem &pi) {
   uint32_t lo = 0, hi = 0;  // lanes >= n keep an empty bucket
   int budget = -1;
-  if (lane < n) {
-    const uint32_t m = sd.masks[seed0 + lane];
-    const uint32_t kk = key ^ (m & 0xFFFFFFu);
-    lo = sd.off[kk];
-    hi = sd.off[kk + 1];
+  if (!PAT) {
+    if (lane < n) {
+      const uint32_t m = sd.masks[seed0 + lane];
+      const uint32_t kk = key ^ (m & 0xFFFFFFu);
+      lo = sd.off[kk];
+      hi = sd.off[kk + 1];
+      budget = p.k - (int)(m >> 24);
+    }
+  } else if (lane < n) {
+    uint32_t m, x;
+    if (pi.wild_bit >= 0) {  // seed = (mask over the other key bases, value of the wildcard base)
+      const int s = seed0 + lane;
+      m = pi.masks[s >> 2];
+      const uint32_t mm = m & 0xFFFFFFu, wb = (uint32_t)pi.wild_bit;
+      x = ((mm >> wb) << (wb + 2)) | (mm & ((1u << wb) - 1u)) | ((uint32_t)(s & 3) << wb);
+    } else {
+      m = pi.masks[seed0 + lane];
+      x = m & 0xFFFFFFu;
+    }
+    const uint32_t kk = key ^ x;
     budget = p.k - (int)(m >> 24);
+    if (!pi.cell_off) {
+      lo = sd.off[kk];
+      hi = sd.off[kk + 1];
+    } else if (PASS_B) {  // the part of the bucket whose database indices lie in the window
+      lo = pi.cell_off[kk * (kCells + 1) + pi.c0];
+      hi = pi.cell_off[kk * (kCells + 1) + pi.c1];
+    } else {              // index A is in database order: a key is inside the window or not
+      const int cell = (int)(kk >> pi.cell_shift);
+      if (cell >= pi.c0 && cell < pi.c1) { lo = sd.off[kk]; hi = sd.off[kk + 1]; }
+    }
   }
   compares += hi - lo;
   static_assert(32 % FF_GROUP == 0, "a group must not wrap around the warp");
@@ -173,7 +214,7 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
     for (int j = 0; j < FF_GROUP; ++j) {
       const int bud = __shfl_sync(0xffffffffu, budget, l0 + j);
       const uint32_t base = (blo[j] & ~3u) + lane4;
-      if (base < bhi[j]) verify_chunk<PASS_B>(p, wh, sd.canon, v[j], base, blo[j], bhi[j], probe, bud, guide_key);
+      if (base < bhi[j]) verify_chunk<PASS_B, PAT>(p, wh, sd.canon, v[j], base, blo[j], bhi[j], probe, bud, guide_key, pi.pmask, pi.lo_d);
     }
     if (!any_long) continue;
     // buckets longer than 128 entries (pass B, repeat-rich part-one keys): stream the rest, FF_TAIL chunks in flight
@@ -194,7 +235,7 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
         }
 #pragma unroll
         for (int c = 0; c < FF_TAIL; ++c)
-          if (c2 + 128u * c < jhi) verify_chunk<PASS_B>(p, wh, sd.canon, w[c], c2 + 128u * c, jlo, jhi, probe, bud, guide_key);
+          if (c2 + 128u * c < jhi) verify_chunk<PASS_B, PAT>(p, wh, sd.canon, w[c], c2 + 128u * c, jlo, jhi, probe, bud, guide_key, pi.pmask, pi.lo_d);
       }
     }
   }
@@ -226,10 +267,10 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_seed_scan(
     const uint64_t guide_key = (uint64_t)g << p.tbits;
     if (bi < p.A.items) {
       const int seed0 = bi * p.A.seeds_per_item;
-      scan_seeds<false>(p, p.A, wh, lane, key_a, key_b, seed0, min(p.A.seeds_per_item, p.A.n_seeds - seed0), guide_key, compares);
+      scan_seeds<false, false>(p, p.A, wh, lane, key_a, key_b, seed0, min(p.A.seeds_per_item, p.A.n_seeds - seed0), guide_key, compares, PatItem{});
     } else {
       const int seed0 = (bi - p.A.items) * p.B.seeds_per_item;
-      scan_seeds<true>(p, p.B, wh, lane, key_b, key_a, seed0, min(p.B.seeds_per_item, p.B.n_seeds - seed0), guide_key, compares);
+      scan_seeds<true, false>(p, p.B, wh, lane, key_b, key_a, seed0, min(p.B.seeds_per_item, p.B.n_seeds - seed0), guide_key, compares, PatItem{});
     }
   }
   flush_warp_hits(wh, lane);
@@ -328,6 +369,42 @@ __global__ void k_gather_positions(const uint32_t *__restrict__ out_tidx, const 
 // ------------------------------------------------------------------------------------------------------------
 static inline unsigned int blocks_for(int64_t n, int threads) { return (unsigned int)((n + threads - 1) / threads); }
 
+// Positions of the emitted hits (only with want_positions and a database image that holds positions).
+static int gather_positions(ff_ctx *ctx, ff_ctx::OutSlot &os, bool want_positions, int64_t n_hits, DeviceResult *res, int64_t *n_pos_out,
+                            int *launches) {
+  Database &db = ctx->db;
+  cudaStream_t st = ctx->stream;
+  const int64_t Hp = n_hits > 0 ? n_hits : 1;
+  size_t tmp_bytes = 0;
+  int64_t n_pos = 0;
+  res->d_pos_ptr = nullptr; res->d_positions = nullptr;
+  if (want_positions && db.d_positions) {
+    FF_TRY(ctx->pos_cnt.reserve((Hp + 1) * 8));
+    FF_TRY(ctx->pos_ptr.reserve((Hp + 1) * 8));
+    FF_CUDA(cudaMemsetAsync(ctx->pos_cnt.p, 0, (Hp + 1) * 8, st));
+    if (n_hits > 0) {
+      k_pos_counts<<<blocks_for(n_hits, 256), 256, 0, st>>>(os.out_targets.as<uint64_t>(), n_hits, ctx->pos_cnt.as<int64_t>());
+      (*launches)++;
+    }
+    FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->pos_cnt.as<int64_t>(), ctx->pos_ptr.as<int64_t>(), n_hits + 1, st));
+    FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
+    FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->pos_cnt.as<int64_t>(), ctx->pos_ptr.as<int64_t>(), n_hits + 1, st));
+    *launches += 2;
+    FF_CUDA(cudaMemcpyAsync(&n_pos, ctx->pos_ptr.as<int64_t>() + n_hits, 8, cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    FF_TRY(ctx->out_positions.reserve((n_pos > 0 ? n_pos : 1) * 8));
+    if (n_hits > 0) {
+      k_gather_positions<<<blocks_for(n_hits * 32, 256), 256, 0, st>>>(ctx->out_tidx.as<uint32_t>(), ctx->pos_ptr.as<int64_t>(), db.d_pos_off,
+                                                                      db.d_positions, n_hits, ctx->out_positions.as<uint64_t>());
+      (*launches)++;
+    }
+    res->d_pos_ptr = ctx->pos_ptr.as<int64_t>();
+    res->d_positions = ctx->out_positions.as<uint64_t>();
+  }
+  *n_pos_out = n_pos;
+  return FF_OK;
+}
+
 // Choose hA (pass A covers d1 <= hA, pass B covers d1 > hA, i.e. d2 <= k - hA - 1) by the expected number of entries
 // streamed per guide: seeds x (average bucket + a fixed per-seed cost).
 static void plan_passes(const Database &db, int k, int *hA_out, int *nA, int *nB) {
@@ -345,8 +422,8 @@ static void plan_passes(const Database &db, int k, int *hA_out, int *nA, int *nB
   }
 }
 
-int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
-                       bool want_positions, int slot, DeviceResult *res) {
+static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
+                          bool want_positions, int slot, DeviceResult *res) {
   Database &db = ctx->db;
   ff_ctx::OutSlot &os = ctx->out[slot & 1];
   if (!db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
@@ -472,30 +549,7 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
     launches++;
   }
   int64_t n_pos = 0;
-  res->d_pos_ptr = nullptr; res->d_positions = nullptr;
-  if (want_positions && db.d_positions) {
-    FF_TRY(ctx->pos_cnt.reserve((Hp + 1) * 8));
-    FF_TRY(ctx->pos_ptr.reserve((Hp + 1) * 8));
-    FF_CUDA(cudaMemsetAsync(ctx->pos_cnt.p, 0, (Hp + 1) * 8, st));
-    if (n_hits > 0) {
-      k_pos_counts<<<blocks_for(n_hits, 256), 256, 0, st>>>(os.out_targets.as<uint64_t>(), n_hits, ctx->pos_cnt.as<int64_t>());
-      launches++;
-    }
-    FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->pos_cnt.as<int64_t>(), ctx->pos_ptr.as<int64_t>(), n_hits + 1, st));
-    FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
-    FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->pos_cnt.as<int64_t>(), ctx->pos_ptr.as<int64_t>(), n_hits + 1, st));
-    launches += 2;
-    FF_CUDA(cudaMemcpyAsync(&n_pos, ctx->pos_ptr.as<int64_t>() + n_hits, 8, cudaMemcpyDeviceToHost, st));
-    FF_CUDA(cudaStreamSynchronize(st));
-    FF_TRY(ctx->out_positions.reserve((n_pos > 0 ? n_pos : 1) * 8));
-    if (n_hits > 0) {
-      k_gather_positions<<<blocks_for(n_hits * 32, 256), 256, 0, st>>>(ctx->out_tidx.as<uint32_t>(), ctx->pos_ptr.as<int64_t>(), db.d_pos_off,
-                                                                      db.d_positions, n_hits, ctx->out_positions.as<uint64_t>());
-      launches++;
-    }
-    res->d_pos_ptr = ctx->pos_ptr.as<int64_t>();
-    res->d_positions = ctx->out_positions.as<uint64_t>();
-  }
+  FF_TRY(gather_positions(ctx, os, want_positions, n_hits, res, &n_pos, &launches));
   FF_CUDA(cudaEventRecord(ctx->ev[4], st));
   FF_CUDA(cudaStreamSynchronize(st));
   FF_CUDA(cudaGetLastError());
@@ -517,8 +571,10 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
   res->n_candidate_hits = (uint64_t)n_cand; res->n_compares = h_cnt[1];
   res->d_row_ptr = os.row_ptr.as<int64_t>(); res->d_targets = os.out_targets.as<uint64_t>();
   res->d_mismatches = os.out_mm.as<uint8_t>(); res->d_total_count = os.total_count.as<int32_t>();
-  res->d_overflowed = os.overflowed.as<uint8_t>();
+  res->d_overflowed = os.overflowed.as<uint8_t>(); res->d_bulge = nullptr;
   return FF_OK;
 }
+
+#include "ff_general.inl"
 
 }  // namespace ff

@@ -24,6 +24,7 @@ struct DeviceResult {
   const int64_t *d_row_ptr = nullptr;
   const uint64_t *d_targets = nullptr;
   const uint8_t *d_mismatches = nullptr;
+  const uint8_t *d_bulge = nullptr;  // bulge mode only
   const int32_t *d_total_count = nullptr;
   const uint8_t *d_overflowed = nullptr;
   const int64_t *d_pos_ptr = nullptr;
@@ -31,8 +32,9 @@ struct DeviceResult {
 };
 
 // ff_discover.cu
+// bulge_flags: 0 = the reference's mismatch-only search; FF_BULGE_RNA | FF_BULGE_DNA = the 1-bp bulge extension
 int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
-                       bool want_positions, int slot, DeviceResult *res);
+                       bool want_positions, int bulge_flags, int slot, DeviceResult *res);
 
 // ff_score.cu : CFD + Hsu2013 over a CSR hit list resident in HBM.  Any output may be null.
 int score_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, const int64_t *d_row_ptr,
@@ -46,6 +48,7 @@ int hit_aggregates_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gu
 int db_from_host_arrays(ff_ctx *ctx, const Pack &pack, int bin_width, const uint64_t *targets, uint64_t n_targets,
                         const uint64_t *positions, uint64_t n_positions, const std::vector<std::string> &contigs);
 int db_build_index(ff_ctx *ctx);  // d_targets (+ d_positions) already in HBM -> d_tlow, d_sub_off, tables, d_pos_off
+int db_build_cell_offsets(ff_ctx *ctx);  // lazily: per-bucket offsets at the database-order cell boundaries (windowed scan)
 int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path);
 int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed);
 

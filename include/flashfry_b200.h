@@ -42,6 +42,9 @@ extern "C" {
 #define FF_METRIC_CFD 1u      /* Doench2016CFDScore: DoenchCFD_maxOT, DoenchCFD_specificityscore */
 #define FF_METRIC_HSU2013 2u  /* CrisprMitEduOffTarget: Hsu2013 */
 
+#define FF_BULGE_RNA 1 /* ff_discover_bulge: allow one looped-out guide base */
+#define FF_BULGE_DNA 2 /* ff_discover_bulge: allow one looped-out genomic base */
+
 typedef struct ff_ctx ff_ctx;
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -104,6 +107,8 @@ typedef struct ff_hits {
                                   modules/OffTargetDiscovery.scala:137; NOT equal to the reference's count: pruning differs) */
   uint64_t n_candidate_hits;   /* hits before the overflow cut */
   void *opaque;
+  const uint8_t *bulge;        /* [n_hits], ff_discover_bulge only (else NULL): 0 = no bulge, 0x40|q = RNA bulge at guide
+                                  base q, 0x80|q = DNA bulge at genomic base q; mismatches[] then counts the aligned pairs */
 } ff_hits;
 
 /* guides: BitEncoding.bitEncodeString(bases, count = 1) longs in ResultsAggregator order (any order is accepted;
@@ -111,6 +116,21 @@ typedef struct ff_hits {
 int ff_discover(ff_ctx *ctx, const uint64_t *guides, int64_t n_guides, int max_mismatch, int max_off_targets,
                 int want_positions, ff_hits **out);
 void ff_hits_free(ff_hits *hits);
+
+/* ---- EXTENSION: 1-bp bulge mode (BASELINE.json configs[3]) --------------------------------------------------
+ * NOT a replacement of anything: the reference has no gap / bulge / edit-distance search (no match for
+ * bulge|gap|indel|levenshtein under src/main), so there is no reference behaviour to be bit-exact with.  Semantics
+ * (the tests hold a brute-force, base-by-base statement of the same definition): for 23-bp Cas9 packs (20-base protospacer g / t,
+ * base 0 PAM-distal, 3' PAM), with q in 1..18,
+ *   no bulge       mm = #{ j : g[j] != t[j] }                                       (= BitEncoding.mismatches)
+ *   RNA bulge at q guide base q looped out: mm = hamming(g[0..q) + g(q..19], t[1..19]); t[0] is outside the alignment
+ *   DNA bulge at q genomic base q looped out: mm = hamming(g[1..19], t[0..q) + t(q..19]); g[0] would pair with the base
+ *                  upstream of the stored 23-mer, which a FlashFry database does not hold, so it is not scored
+ * A target is a hit when its best allowed alignment -- smallest (mm, type none < RNA < DNA, q) -- has
+ * mm <= max_mismatch.  Rows are in database order and cut by the reference's overflow rule, exactly like ff_discover;
+ * bulge_flags = 0 gives ff_discover's results (with hits->bulge all zero).  Other enzymes: FF_EUNSUPPORTED. */
+int ff_discover_bulge(ff_ctx *ctx, const uint64_t *guides, int64_t n_guides, int max_mismatch, int max_off_targets,
+                      int bulge_flags, int want_positions, ff_hits **out);
 
 /* ---- score (replaces ScoreModel.scoreGuides for Doench2016CFDScore and CrisprMitEduOffTarget) ------------ */
 /* hits: row g = the off-targets of guides[g] (from ff_discover or re-read from a discover TSV; only n_guides,
@@ -145,10 +165,15 @@ typedef struct {
   const int32_t *d_total_count;
   const uint8_t *d_overflowed;
   const double *d_cfd_max, *d_cfd_specificity, *d_hsu2013; /* NULL unless metrics requested */
+  const uint8_t *d_bulge;     /* ff_discover_bulge_device only, else NULL */
 } ff_device_result;
 /* d_guides already in HBM; results stay in HBM.  metrics may be 0. */
 int ff_discover_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mismatch,
                        int max_off_targets, uint32_t metrics, ff_device_result *out);
+
+/* The bulge extension on device-resident guides (no scoring: CFD / Hsu2013 are not defined for bulged alignments). */
+int ff_discover_bulge_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mismatch,
+                             int max_off_targets, int bulge_flags, ff_device_result *out);
 
 /* Device-time of the kernels of the last discover call on this context, from CUDA events recorded on the
  * context's stream (ms).  scan = the bin-scan kernel (dominant), prep = guide sort/bucketing, order = hit sort,

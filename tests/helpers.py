@@ -75,3 +75,32 @@ def assert_hits_equal(gpu, ref, check_positions=False):
     if check_positions:
         assert (np.asarray(gpu.pos_ptr) == np.asarray(ref.pos_ptr)).all(), "pos_ptr differs"
         assert (np.asarray(gpu.positions) == np.asarray(ref.positions)).all(), "positions differ"
+
+
+def family_database(oracle, seed: int, n_seeds: int, variants_per_seed: int):
+    """A spCas9-NGG database whose targets are variants of a few seed protospacers: 0..5 substitutions and, for two
+    thirds of them, one deleted or inserted base (the 20-base window stays PAM-anchored).  Returns
+    (targets u64 sorted with counts, seed guides u64)."""
+    rng = np.random.default_rng(seed)
+    seeds = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(n_seeds)]
+    vals = set()
+    for s in seeds:
+        for _ in range(variants_per_seed):
+            t = list(s)
+            kind = int(rng.integers(0, 3))
+            q = int(rng.integers(1, 19))
+            if kind == 1:    # a guide base has no partner: delete it, a new base enters at the 5' end
+                t = ["ACGT"[int(rng.integers(0, 4))]] + t[:q] + t[q + 1:]
+            elif kind == 2:  # an extra genomic base: insert one, the 5'-most base leaves the window
+                t = t[1:q + 1] + ["ACGT"[int(rng.integers(0, 4))]] + t[q + 1:]
+            for _ in range(int(rng.integers(0, 6))):
+                t[int(rng.integers(0, 20))] = "ACGT"[int(rng.integers(0, 4))]
+            assert len(t) == 20
+            vals.add(oracle.encode("".join(t) + "ACGT"[int(rng.integers(0, 4))] + "GG", 1) & 0xFFFFFFFFFFFF)
+    v = np.asarray(sorted(vals), np.uint64)
+    counts = rng.integers(1, 4, len(v)).astype(np.uint64)
+    big = rng.random(len(v)) < 0.002
+    counts[big] = rng.integers(500, 3000, int(big.sum())).astype(np.uint64)
+    targets = v | (counts << np.uint64(48))
+    guides = np.asarray([oracle.encode(s + "TGG", 1) for s in seeds], np.uint64)
+    return targets, guides

@@ -1,0 +1,163 @@
+"""GPU tests of the general discover path: the 1-bp bulge EXTENSION and database-order windows.
+
+The bulge mode does not exist in the reference, so these are NOT reference-parity tests: the CUDA
+path is compared with the brute-force definition in oracle/ff_oracle.c (ffo_discover_bulge), which tests/
+test_oracle_pins.py cross-checks against an independent string-surgery restatement.  The windowed scan IS
+reference behaviour (overflowed guides leave the traversal, OrderedBinTraversalFactory.scala:107-119) and must give
+exactly the rows of the whole-database scan.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ff():
+    import flashfry_b200.api as api
+    return api
+
+
+@pytest.fixture(scope="module")
+def family_db(oracle):
+    """~60 k targets built from 48 seed protospacers with substitutions and single-base indels, so that guides have many
+    mismatch-only, RNA-bulge and DNA-bulge neighbours; occurrence counts are mixed (a few above 1000)."""
+    return helpers.family_database(oracle, seed=11, n_seeds=48, variants_per_seed=1400)
+
+
+@pytest.fixture(scope="module")
+def family_ctx(ff, family_db):
+    ctx = ff.Context(0)
+    ctx.load_database_arrays(3, family_db[0])
+    yield ctx
+    ctx.close()
+
+
+def _env(**kw):
+    class _E:
+        def __enter__(self):
+            self.old = {k: os.environ.get(k) for k in kw}
+            for k, v in kw.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = str(v)
+
+        def __exit__(self, *a):
+            for k, v in self.old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return _E()
+
+
+def assert_bulge_equal(got, ref):
+    helpers.assert_hits_equal(got, ref)
+    assert got.bulge is not None and (np.asarray(got.bulge) == np.asarray(ref.bulge)).all(), "bulge codes differ"
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("k", [0, 2, 4])
+def test_bulge_matches_definition(family_ctx, family_db, oracle, flags, k):
+    targets, seeds = family_db
+    pack = oracle.PACK_BY_INDEX[3]
+    guides = np.concatenate([seeds[:16], helpers.planted_guides(pack, targets, 100 + k, 16, max_subs=3),
+                             helpers.random_guides(oracle, pack, 5, 4)])
+    ref = oracle.discover_bulge(pack, targets, guides, k, 10 ** 6, flags, n_threads=os.cpu_count() or 1)
+    got = family_ctx.discover_bulge(guides, k, 10 ** 6, flags)
+    assert_bulge_equal(got, ref)
+    assert not np.asarray(ref.overflowed).any()
+    if k >= 2:
+        b = np.asarray(ref.bulge)
+        assert int((b != 0).sum()) > 50, "the inputs must exercise bulged alignments"
+        if flags & 1:
+            assert ((b & 0xC0) == 0x40).any()
+        if flags & 2:
+            assert ((b & 0xC0) == 0x80).any()
+
+
+@pytest.mark.parametrize("max_ot", [0, 1, 7, 300])
+def test_bulge_overflow_cut(family_ctx, family_db, oracle, max_ot):
+    targets, seeds = family_db
+    pack = oracle.PACK_BY_INDEX[3]
+    guides = seeds[16:40]
+    ref = oracle.discover_bulge(pack, targets, guides, 3, max_ot, 3, n_threads=os.cpu_count() or 1)
+    got = family_ctx.discover_bulge(guides, 3, max_ot, 3)
+    assert_bulge_equal(got, ref)
+    assert np.asarray(ref.overflowed).any()
+
+
+@pytest.mark.parametrize("cells", [1, 5, 16])
+def test_bulge_windows_equal_whole_database_scan(family_ctx, family_db, oracle, cells):
+    """Database-order windows + dropping full guides give exactly the rows of the one-window scan."""
+    targets, seeds = family_db
+    pack = oracle.PACK_BY_INDEX[3]
+    guides = np.concatenate([seeds[:24], helpers.planted_guides(pack, targets, 9, 24, max_subs=2)])
+    with _env(FF_WINDOW_CELLS=64):
+        whole = family_ctx.discover_bulge(guides, 3, 150, 3)
+    with _env(FF_WINDOW_CELLS=cells):
+        win = family_ctx.discover_bulge(guides, 3, 150, 3)
+    assert_bulge_equal(win, whole)
+    ref = oracle.discover_bulge(pack, targets, guides, 3, 150, 3, n_threads=os.cpu_count() or 1)
+    assert_bulge_equal(win, ref)
+
+
+@pytest.mark.parametrize("cells", [1, 7, 64])
+@pytest.mark.parametrize("max_ot", [5, 2000])
+def test_windowed_mismatch_search_equals_plain(family_ctx, family_db, oracle, cells, max_ot):
+    """The reference's own (mismatch-only) search through the general path -- windows, active-guide compaction --
+    equals the plain kernel's rows and the oracle's restatement of the reference loops."""
+    targets, seeds = family_db
+    pack = oracle.PACK_BY_INDEX[3]
+    guides = np.concatenate([seeds, helpers.planted_guides(pack, targets, 3, 64, max_subs=4), helpers.random_guides(oracle, pack, 8, 32)])
+    plain = family_ctx.discover(guides, 4, max_ot)
+    with _env(FF_FORCE_GENERAL=1, FF_WINDOW_CELLS=cells):
+        gen = family_ctx.discover(guides, 4, max_ot)
+    helpers.assert_hits_equal(gen, plain)
+    ref = oracle.discover_soa(pack, 7, targets, oracle.bin_offsets_from_sorted(pack, 7, targets), guides, 4, max_ot)
+    helpers.assert_hits_equal(gen, ref)
+
+
+def test_bulge_flags_zero_is_plain_discover(family_ctx, family_db, oracle):
+    targets, seeds = family_db
+    plain = family_ctx.discover(seeds, 4, 2000)
+    got = family_ctx.discover_bulge(seeds, 4, 2000, 0)
+    helpers.assert_hits_equal(got, plain)
+    assert got.bulge is not None and not np.asarray(got.bulge).any()
+
+
+def test_bulge_with_positions(ff, oracle, tmp_path):
+    """Positions of bulge hits are the positions of the stored targets (gathered by database index)."""
+    contigs = helpers.random_genome(77, 120_000, repeat_unit=50, n_repeats=200)
+    fa = str(tmp_path / "g.fa")
+    helpers.write_fasta(fa, contigs)
+    dbp = str(tmp_path / "db")
+    oracle.build_database(fa, dbp, "spcas9ngg")
+    db = oracle.read_database(dbp)
+    targets, _, pos_off, positions = db.soa()
+    guides = helpers.planted_guides(db.pack, targets, 4, 40, max_subs=2)
+    with ff.Context(0) as ctx:
+        ctx.load_database(dbp)
+        got = ctx.discover_bulge(guides, 3, 2000, 3, positions=True)
+    ref = oracle.discover_bulge(db.pack, targets, guides, 3, 2000, 3)
+    assert_bulge_equal(got, ref)
+    key = targets & np.uint64(0xFFFFFFFFFFFF)
+    for h in range(len(got.targets)):
+        t = int(np.searchsorted(key, got.targets[h] & np.uint64(0xFFFFFFFFFFFF)))
+        want = positions[int(pos_off[t]):int(pos_off[t + 1])]
+        assert (got.positions[int(got.pos_ptr[h]):int(got.pos_ptr[h + 1])] == want).all()
+
+
+def test_bulge_unsupported_enzyme(ff, oracle):
+    pack = oracle.PACK_BY_INDEX[1]  # Cpf1: 5' PAM, 24-mer
+    t = np.sort(np.random.default_rng(1).integers(0, 1 << 48, 1000, dtype=np.uint64)) | (np.uint64(1) << np.uint64(48))
+    with ff.Context(0) as ctx:
+        ctx.load_database_arrays(5, np.unique(t & np.uint64((1 << 44) - 1)) | (np.uint64(1) << np.uint64(48)))
+        with pytest.raises(ff.FlashFryError) as e:
+            ctx.discover_bulge(t[:4], 3, 2000, 3)
+        assert e.value.code == -7

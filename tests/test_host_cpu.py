@@ -31,7 +31,7 @@ def test_library_exports_every_symbol_of_the_header(built):
         assert hasattr(lib, name), "missing export: " + name
     from flashfry_b200 import _native
     assert set(_native.SYMBOLS) == declared
-    assert lib.ff_abi_version() == 1
+    assert lib.ff_abi_version() == 2
 
 
 def test_no_gpu_means_loud_failure_not_a_fallback(built):

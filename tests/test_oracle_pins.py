@@ -238,3 +238,40 @@ def test_bit_position_known_answers(oracle, vec):
         assert oracle.pos_decode(enc) == (cid, c["start"], c["len"], c["fwd"])
     assert oracle.pos_encode(2, 1000, 23, True) == (2 << 32) | 1000 | (23 << 52)
     assert oracle.pos_encode(1, 5, 23, False) >> 60 == 1
+
+
+# ---- EXTENSION (no reference behaviour; parity unpinned): the bulge-mode definition the CUDA path is tested against
+def test_bulge_alignment_definition_is_self_consistent(oracle):
+    """ffo_bulge_align (C, base by base) == the string-surgery restatement (delete guide base q / delete target base q);
+    with no bulge allowed it is BitEncoding.mismatches."""
+    import random
+    rnd = random.Random(5)
+    pack = oracle.PACK_BY_INDEX[3]
+    for _ in range(3000):
+        g = "".join(rnd.choice("ACGT") for _ in range(20))
+        t = list(g)
+        r = rnd.random()
+        q = rnd.randrange(1, 19)
+        if r < 0.3:
+            t = [rnd.choice("ACGT")] + list(g[:q] + g[q + 1:])
+        elif r < 0.6:
+            t = list(g[1:q + 1]) + [rnd.choice("ACGT")] + list(g[q + 1:])
+        for _ in range(rnd.randrange(0, 5)):
+            t[rnd.randrange(20)] = rnd.choice("ACGT")
+        t = "".join(t)
+        ge, te = oracle.encode(g + "AGG"), oracle.encode(t + "TGG", 7)
+        for flags in (0, 1, 2, 3):
+            assert oracle.bulge_align(ge, te, flags) == oracle.bulge_align_strings(g, t, flags)
+        assert oracle.bulge_align(ge, te, 0) == (oracle.mismatches(pack, ge, te), 0, 0)
+
+
+def test_bulge_discover_without_bulges_is_the_reference_search(oracle):
+    """flags = 0 reduces the extension's brute force to the reference's discover (same rows, same overflow cut)."""
+    import helpers
+    pack = oracle.PACK_BY_INDEX[3]
+    targets, seeds = helpers.family_database(oracle, seed=3, n_seeds=12, variants_per_seed=400)
+    for max_ot in (5, 2000):
+        ref = oracle.discover_soa(pack, 7, targets, oracle.bin_offsets_from_sorted(pack, 7, targets), seeds, 4, max_ot)
+        got = oracle.discover_bulge(pack, targets, seeds, 4, max_ot, 0)
+        helpers.assert_hits_equal(got, ref)
+        assert not got.bulge.any()
