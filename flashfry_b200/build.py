@@ -39,7 +39,7 @@ def _newer(src_files, target) -> bool:
 
 
 def _headers():
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp", ".inl"))]
     hs.append(os.path.join(HERE, "..", "include", "flashfry_b200.h"))
     host = os.path.join(CSRC, "host")
     if os.path.isdir(host):

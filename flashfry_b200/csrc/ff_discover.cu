@@ -195,6 +195,18 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
     }
   }
   compares += hi - lo;
+  if (PAT) {
+    // windows leave most buckets of a batch empty: move the non-empty ones to the front lanes so that the group loop
+    // below runs over those only
+    const unsigned int nz = __ballot_sync(0xffffffffu, hi > lo);
+    n = __popc(nz);
+    if (n == 0) return;
+    const unsigned int src = __fns(nz, 0, lane + 1) & 31u;
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    budget = __shfl_sync(0xffffffffu, budget, src);
+    if (lane >= n) { lo = 0; hi = 0; budget = -1; }
+  }
   static_assert(32 % FF_GROUP == 0, "a group must not wrap around the warp");
   const uint32_t lane4 = 4u * lane;
   // does any bucket of this batch need more than its first 128-entry chunk?  (never, for part-one buckets of a

@@ -35,6 +35,7 @@ struct GeneralParams {
   int a_bases, P;
   int c0, c1, cell_shift;
   const uint32_t *cell_off;  // nullptr = the whole database in one window
+  int debug_skip;            // experiments only: 1 = skip pass A items, 2 = skip pass B items
 };
 
 // The template a pattern lays over the stored protospacer (wildcard digit = 0) and the wildcard position (-1: none).
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_pattern_sc
     const bool wild_a = w >= 0 && w < a, wild_b = w >= a;
     PatItem pi;
     pi.c0 = gp.c0; pi.c1 = gp.c1; pi.cell_shift = gp.cell_shift; pi.cell_off = gp.cell_off;
+    if (gp.debug_skip && ((bi < c.itemsA) == (gp.debug_skip == 1))) continue;
     if (bi < c.itemsA) {
       const int seed0 = bi * 32;
       pi.masks = wild_a ? gp.a_masks_w1 : p.A.masks;
@@ -162,12 +164,18 @@ __global__ void k_copy_kept(const uint64_t *__restrict__ keys, const int64_t *__
 }
 
 __global__ void k_still_collecting(const uint32_t *__restrict__ active, int64_t n_active, const long long *__restrict__ running, int max_ot,
-                                   uint32_t *__restrict__ ids, uint8_t *__restrict__ flags) {
+                                   uint32_t *__restrict__ ids, uint8_t *__restrict__ flags, unsigned long long *__restrict__ collected) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n_active) return;
-  const uint32_t g = active ? active[i] : (uint32_t)i;
-  ids[i] = g;
-  flags[i] = running[g] < max_ot ? 1 : 0;
+  long long mine = 0;
+  if (i < n_active) {
+    const uint32_t g = active ? active[i] : (uint32_t)i;
+    ids[i] = g;
+    const bool open = running[g] < max_ot;
+    flags[i] = open ? 1 : 0;
+    if (open) mine = running[g];
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(collected, (unsigned long long)mine);  // what the open guides hold so far
 }
 
 __global__ void k_finish_totals(const long long *__restrict__ running, int64_t n_guides, int max_ot, int32_t *__restrict__ total_count,
@@ -277,8 +285,6 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
     const double n = (double)db.n_targets;
     const double bucket_a = n / (double)(1ull << (2 * a)), bucket_b = n / (double)(1ull << (2 * b));
     const double per_seed = 24.0;
-    int spi = bucket_b > 2048 ? 1 : bucket_b > 512 ? 4 : bucket_b > 128 ? 8 : 32;
-    if (const char *e = getenv("FF_B_SPI")) spi = std::max(1, atoi(e));
     for (int cls = 0; cls < 3; ++cls) {
       double best = -1.0;
       PatternPlan::Cls &c = pl.c[cls];
@@ -289,9 +295,7 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
         const double cost = sa * (bucket_a + per_seed) + sb * (bucket_b + per_seed);
         if (best < 0 || cost < best) { best = cost; c.hA = h; c.nA = (int)sa; c.nB = (int)sb; }
       }
-      c.spiB = spi;
       c.itemsA = (c.nA + 31) / 32;
-      c.itemsB = (c.nB + spi - 1) / spi;
     }
     int np = 0;
     auto add = [&](int type, int q, int cls) { pl.type[np] = (uint8_t)type; pl.q[np] = (uint8_t)q; pl.cls[np] = (uint8_t)cls; np++; };
@@ -299,10 +303,17 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
     if (bulge_flags & FF_BULGE_RNA) for (int q = 1; q <= P - 2; ++q) add(1, q, 1);
     if (bulge_flags & FF_BULGE_DNA) for (int q = 1; q <= P - 2; ++q) add(2, q, q < a ? 1 : 2);
     pl.n_patterns = np;
-    pl.item0[0] = 0;
-    for (int i = 0; i < np; ++i) pl.item0[i + 1] = pl.item0[i] + pl.c[pl.cls[i]].itemsA + pl.c[pl.cls[i]].itemsB;
-    pl.items_per_guide = pl.item0[np];
   }
+  // part-two seeds per work item follow the length of the bucket run inside a window
+  auto plan_items = [&](int cells) {
+    const double run = (double)db.n_targets / (double)(1ull << (2 * b)) * (double)cells / (double)kCells;
+    int spi = run > 2048 ? 1 : run > 512 ? 4 : run > 128 ? 8 : 32;
+    if (const char *e = getenv("FF_B_SPI")) spi = std::max(1, atoi(e));
+    for (int cls = 0; cls < 3; ++cls) { pl.c[cls].spiB = spi; pl.c[cls].itemsB = (pl.c[cls].nB + spi - 1) / spi; }
+    pl.item0[0] = 0;
+    for (int i = 0; i < pl.n_patterns; ++i) pl.item0[i + 1] = pl.item0[i] + pl.c[pl.cls[i]].itemsA + pl.c[pl.cls[i]].itemsB;
+    pl.items_per_guide = pl.item0[pl.n_patterns];
+  };
   ScanParams &sp = gp.sp;
   sp.guides = d_guides; sp.n_guides = G;
   sp.A.off = db.A.d_off; sp.A.other = db.A.d_other; sp.A.canon = db.A.d_canon; sp.A.masks = db.A.d_masks;
@@ -321,14 +332,20 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
   const int n_bulge_patterns = pl.n_patterns - 1;
   const double prob = ball_probability(P, k_eff) + n_bulge_patterns * ball_probability(P - 1, std::min(k_eff, P - 1));
   const double exp_hits = (double)db.n_targets * prob;  // candidates per guide (duplicates between patterns included)
+  // Templates of neighbouring bulge positions differ in one base, so their hit sets overlap: ~0.45 of the candidates are
+  // distinct targets (measured on the bench index).  The first window aims at 1.25 x maximumOffTargets occurrences for
+  // a typical guide; later windows are sized from what the remaining guides have collected so far.
+  const double exp_occ = exp_hits * (n_bulge_patterns ? 0.45 : 1.0) * 1.3;
   int cells_per_window = kCells;
-  if (can_window && max_ot > 0 && exp_hits * 1.3 > 0.75 * (double)max_ot)
-    cells_per_window = std::max(1, std::min(kCells, (int)((double)kCells * 0.5 * (double)max_ot / (exp_hits * 1.3))));
-  if (const char *e = getenv("FF_WINDOW_CELLS")) { const int v = atoi(e); if (v >= 1 && can_window) cells_per_window = std::min(v, kCells); }
+  if (can_window && max_ot > 0 && exp_occ > 0.75 * (double)max_ot)
+    cells_per_window = std::max(1, std::min(kCells, (int)std::ceil((double)kCells * 1.25 * (double)max_ot / exp_occ)));
+  bool fixed_window = false;
+  if (const char *e = getenv("FF_WINDOW_CELLS")) { const int v = atoi(e); if (v >= 1 && can_window) { cells_per_window = std::min(v, kCells); fixed_window = true; } }
   const bool windowed = cells_per_window < kCells;
   if (windowed) FF_TRY(db_build_cell_offsets(ctx));
   gp.cell_off = windowed ? db.d_cell_off : nullptr;
   gp.cell_shift = 2 * a - 6;  // kCells = 4^3
+  if (const char *e = getenv("FF_DEBUG_SKIP")) gp.debug_skip = atoi(e);
 
   // ---- workspaces
   FF_TRY(ctx->counters.reserve(64));
@@ -356,8 +373,9 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
   float scan_ms = 0.f;
   size_t tmp_bytes = 0;
   const int max_grid = ctx->sm_count * 8;
-  for (int c0 = 0; c0 < kCells && n_active > 0; c0 += cells_per_window) {
-    const int c1 = std::min(kCells, c0 + cells_per_window);
+  for (int c0 = 0, c1 = 0; c0 < kCells && n_active > 0; c0 = c1) {
+    c1 = std::min(kCells, c0 + cells_per_window);
+    plan_items(c1 - c0);
     gp.c0 = c0; gp.c1 = c1; gp.active = d_active; gp.n_active = n_active;
     {
       const double want = (double)n_active * (exp_hits * 1.4 * (double)(c1 - c0) / (double)kCells + 64.0);
@@ -442,16 +460,27 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
     if (c1 < kCells) {
       uint32_t *ids = ctx->active2.as<uint32_t>();
       uint32_t *next = ctx->active.as<uint32_t>();
-      k_still_collecting<<<blocks_for(n_active, 256), 256, 0, st>>>(d_active, n_active, ctx->running.as<long long>(), max_ot, ids, ctx->act_flags.as<uint8_t>());
+      FF_CUDA(cudaMemsetAsync(d_cnt + 2, 0, 8, st));
+      k_still_collecting<<<blocks_for(n_active, 256), 256, 0, st>>>(d_active, n_active, ctx->running.as<long long>(), max_ot, ids, ctx->act_flags.as<uint8_t>(), d_cnt + 2);
       FF_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, ids, ctx->act_flags.as<uint8_t>(), next, ctx->n_sel.as<int64_t>(), n_active, st));
       FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
       FF_CUDA(cub::DeviceSelect::Flagged(ctx->cub_tmp.p, tmp_bytes, ids, ctx->act_flags.as<uint8_t>(), next, ctx->n_sel.as<int64_t>(), n_active, st));
       launches += 3;
       int64_t n_next = 0;
+      unsigned long long collected = 0;
       FF_CUDA(cudaMemcpyAsync(&n_next, ctx->n_sel.p, 8, cudaMemcpyDeviceToHost, st));
+      FF_CUDA(cudaMemcpyAsync(&collected, d_cnt + 2, 8, cudaMemcpyDeviceToHost, st));
       FF_CUDA(cudaStreamSynchronize(st));
       d_active = next;
       n_active = n_next;
+      if (!fixed_window && n_active > 0) {
+        // the open guides collected `mean` occurrences over c1 cells: size the next window for what they still need
+        const double mean = (double)collected / (double)n_active;
+        const double rate = mean / (double)c1;
+        const double need = ((double)max_ot - mean) * 1.25;
+        cells_per_window = rate > 0 ? (int)std::ceil(need / rate) : kCells;
+        cells_per_window = std::max(1, std::min(kCells, cells_per_window));
+      }
     }
   }
   FF_CUDA(cudaEventRecord(ctx->ev[2], st));

@@ -161,3 +161,39 @@ def test_bulge_unsupported_enzyme(ff, oracle):
         with pytest.raises(ff.FlashFryError) as e:
             ctx.discover_bulge(t[:4], 3, 2000, 3)
         assert e.value.code == -7
+
+
+def test_bulge_properties_on_a_large_synthetic_index(ff, oracle):
+    """5e6-target synthetic index, k = 5 + both bulges (the shape of BASELINE configs[3], scaled down): every reported
+    hit re-verifies against the definition, rows are strictly increasing in database order, totals follow the overflow
+    rule, and four guides are checked against the brute force completely."""
+    pack = oracle.PACK_BY_INDEX[3]
+    with ff.Context(0) as ctx:
+        ctx.synth_database(3, 5_000_000, 42)
+        targets = ctx.copy_targets()
+        guides = np.concatenate([helpers.random_guides(oracle, pack, 21, 200), helpers.planted_guides(pack, targets, 22, 56, max_subs=3)])
+        got = ctx.discover_bulge(guides, 5, 300, 3)
+        with _env(FF_WINDOW_CELLS=64):
+            whole = ctx.discover_bulge(guides, 5, 300, 3)
+    assert_bulge_equal(got, whole)
+    assert np.asarray(got.overflowed).mean() > 0.5  # ~2000 expected hits per guide: windows and early exit are exercised
+    seq = np.uint64(0xFFFFFFFFFFFF)
+    for g in range(len(guides)):
+        lo, hi = int(got.row_ptr[g]), int(got.row_ptr[g + 1])
+        t = got.targets[lo:hi]
+        assert (np.diff((t & seq).astype(np.int64)) > 0).all()
+        cnt = (t >> np.uint64(48)).astype(np.int64)
+        assert int(cnt.sum()) == int(got.total_count[g])
+        assert bool(got.overflowed[g]) == (int(cnt.sum()) >= 300)
+        if hi > lo:
+            assert int(cnt[:-1].sum()) < 300  # the shortest prefix that reaches the limit
+        for i in range(lo, min(hi, lo + 40)):
+            mm, ty, q = oracle.bulge_align(int(guides[g]), int(got.targets[i]), 3)
+            assert mm == int(got.mismatches[i]) <= 5
+            assert int(got.bulge[i]) == (0 if ty == 0 else ((0x40 if ty == 1 else 0x80) | q))
+    sub = np.asarray([0, 1, 200, 201])
+    ref = oracle.discover_bulge(pack, targets, guides[sub], 5, 300, 3, n_threads=os.cpu_count() or 1)
+    for j, g in enumerate(sub):
+        lo, hi = int(got.row_ptr[g]), int(got.row_ptr[g + 1])
+        rlo, rhi = int(ref.row_ptr[j]), int(ref.row_ptr[j + 1])
+        assert (got.targets[lo:hi] == ref.targets[rlo:rhi]).all() and (got.bulge[lo:hi] == ref.bulge[rlo:rhi]).all()
