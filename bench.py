@@ -274,6 +274,27 @@ def run_native(args):
                                        "score_kernel_ms": float(np.median([b for _, b in fs])),
                                        "guides_per_s": G / (float(np.median([a for a, _ in fs])) / 1e3),
                                        "metrics": "DoenchCFD_maxOT, DoenchCFD_specificityscore, Hsu2013 (FP64, bit-identical to the oracle)"}
+        # BASELINE.json configs[3]: <= 5 mismatches + one 1-bp RNA/DNA bulge on the same batch.  An EXTENSION: the reference
+        # has no bulge search, so this line is never part of a parity claim (semantics: include/flashfry_b200.h).
+        if not args.no_bulge:
+            bs = []
+            for _ in range(3):
+                rb = ctx.discover_bulge_device(d_guides.data_ptr(), G, 5, args.max_ot, 3)
+                t = ctx.timings()
+                bs.append((t.total_ms, t.scan_ms, t.scan_launches))
+            bms = float(np.median([a for a, _, _ in bs]))
+            for _ in range(2):  # the first call allocates the pinned result buffers (pooled afterwards)
+                t0 = time.perf_counter()
+                N.check(N.lib().ff_discover_bulge(ctx._h, gp, G, 5, args.max_ot, 3, 0, C.byref(hp)))
+                bh = int(hp.contents.n_hits)
+                N.lib().ff_hits_free(hp)
+                be2e = time.perf_counter() - t0
+            out["bulge_mode"] = {"workload": "configs[3]: %d guides, <=5 mismatches + one 1-bp RNA or DNA bulge, maxOT %d, same index" % (G, args.max_ot),
+                                 "total_ms": bms, "scan_ms": float(np.median([b for _, b, _ in bs])), "windows": int(bs[-1][2]),
+                                 "guides_per_s": G / (bms / 1e3), "hits": int(rb.n_hits), "candidate_hits": int(rb.n_candidate_hits),
+                                 "overflowed_guides_note": "nearly every guide reaches maximumOffTargets: the scan walks database-order windows and drops full guides",
+                                 "e2e_guides_per_s": G / be2e, "e2e_d2h_bytes": (G + 1) * 8 + bh * 10 + G * 5,
+                                 "parity": "extension, no reference semantics: checked against a brute-force definition in tests/test_gpu_bulge.py"}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(ctx, guides, args, threads=1, budget_guides=args.cpu_guides)
     ctx.close()
@@ -366,9 +387,10 @@ def main():
     ap.add_argument("--guides", type=int, default=100_000)
     ap.add_argument("--k", type=int, default=4)
     ap.add_argument("--max-ot", dest="max_ot", type=int, default=2000)
-    ap.add_argument("--cpu-guides", type=int, default=512, help="guides in the cpu_baseline sample (single thread)")
+    ap.add_argument("--cpu-guides", type=int, default=2048, help="guides in the cpu_baseline sample (single thread)")
     ap.add_argument("--ref-guides", type=int, default=2048, help="guides per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bulge", action="store_true", help="skip the configs[3] (bulge extension) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
