@@ -58,6 +58,28 @@ def _run(cmd, verbose):
     return r.stdout
 
 
+def build_variant(name: str, defines) -> str:
+    """Experiment support: compile the library with extra -D flags into gpurun_variants/<name>/ (git-ignored, ships to
+    the GPU box); select it at run time with FLASHFRY_B200_LIB=<path>."""
+    out_dir = os.path.join(HERE, "..", "gpurun_variants", name)
+    os.makedirs(out_dir, exist_ok=True)
+    cc = nvcc()
+    objs = []
+    jobs = []
+    for src in CU_SOURCES:
+        o = os.path.join(out_dir, src.replace(".cu", ".o"))
+        objs.append(o)
+        jobs.append([cc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", o])
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        list(ex.map(lambda c: _run(c, False), jobs))
+    lib = os.path.join(out_dir, "libflashfry_b200.so")
+    _run([cc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-lpthread",
+                                               "-Xcompiler", "-fPIC", "-cudart", "static"], False)
+    for o in objs:
+        os.remove(o)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     cc = nvcc()
@@ -91,4 +113,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":  # python -m flashfry_b200.build --variant NAME FF_X=1 FF_Y=2
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -52,6 +52,8 @@ struct Pack {
 };
 int pack_from_index(int enzyme_index, Pack *out);  // StandardScanParameters.scala:61-70
 
+constexpr int kCells = 64;  // cells of a key space: the value of the first three key bases (4^3)
+
 // One half of the seed index: targets ordered by `key` (a run of consecutive protospacer bases), the complementary
 // part of the protospacer stored next to it.
 struct SeedIndex {
@@ -63,6 +65,11 @@ struct SeedIndex {
   int cum[16] = {0};            // cum[h] = # masks at distance <= h (h = 0..w)
   uint32_t *d_masks_w1 = nullptr;  // the same table over w-1 bases (bulge patterns: one key base is a wildcard)
   int cum_w1[16] = {0};
+  // cell-major scan: the same masks grouped by the value of their first three bases (64 groups = the 64 database-order
+  // cells a seed can land in relative to the guide's own cell), inside a group sorted by distance
+  uint32_t *d_gmasks = nullptr;    // [4^w]
+  int goff[kCells + 1] = {0};      // first mask of every group
+  int gcum[kCells][16] = {{0}};    // gcum[g][h] = # masks of group g at distance <= h
   void release();
 };
 
@@ -87,8 +94,6 @@ struct Database {
   void release();
 };
 
-constexpr int kCells = 64;  // database-order cells of the windowed scan (4^3: the first three key bases)
-
 struct Hits;  // host-side result owner (ff_api.cu)
 
 }  // namespace ff
@@ -108,6 +113,7 @@ struct ff_ctx {
   ff::DevBuf scratch_guides;  // H2D staging target for ff_discover
   // windowed / bulge discover: per-guide running totals, the active guide list (two copies), kept keys, scratch
   ff::DevBuf running, active, active2, act_flags, seg_end, kept_keys, kept_sorted, n_sel;
+  ff::DevBuf cell_ws;  // cell-major scan: guide classes, class-ordered guide lists, segment table
   // results of a discover call; two sets so that the D2H of one guide sub-batch overlaps the scan of the next
   struct OutSlot {
     ff::DevBuf row_ptr, total_count, overflowed, out_targets, out_mm, out_bulge, cfd_max, cfd_spec, hsu;

@@ -44,7 +44,7 @@ int pack_from_index(int idx, Pack *o) {
 }
 
 void SeedIndex::release() {
-  cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks); cudaFree(d_masks_w1);
+  cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks); cudaFree(d_masks_w1); cudaFree(d_gmasks);
   *this = SeedIndex();
 }
 
@@ -150,10 +150,31 @@ static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, const uin
   make_masks(key_bases - 1, &masks_w1, ix->cum_w1);
   FF_CUDA(cudaMalloc(&ix->d_masks_w1, masks_w1.size() * 4));
   FF_CUDA(cudaMemcpyAsync(ix->d_masks_w1, masks_w1.data(), masks_w1.size() * 4, cudaMemcpyHostToDevice, st));
+  // grouped copy: (first three bases, distance, value) order; `masks` is already in (distance, value) order, so a stable
+  // counting sort by group keeps the distance order inside every group
+  std::vector<uint32_t> gmasks(masks.size());
+  {
+    const int gshift = 2 * key_bases - 6;
+    std::vector<int> cnt(kCells + 1, 0);
+    for (uint32_t m : masks) cnt[((m & 0xFFFFFFu) >> gshift) + 1]++;
+    for (int g = 0; g < kCells; ++g) cnt[g + 1] += cnt[g];
+    for (int g = 0; g <= kCells; ++g) ix->goff[g] = cnt[g];
+    std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+    memset(ix->gcum, 0, sizeof ix->gcum);
+    for (uint32_t m : masks) {
+      const int g = (int)((m & 0xFFFFFFu) >> gshift);
+      gmasks[cur[g]++] = m;
+      ix->gcum[g][std::min(15, (int)(m >> 24))]++;
+    }
+    for (int g = 0; g < kCells; ++g)
+      for (int h = 1; h < 16; ++h) ix->gcum[g][h] += ix->gcum[g][h - 1];
+  }
+  FF_CUDA(cudaMalloc(&ix->d_gmasks, gmasks.size() * 4));
+  FF_CUDA(cudaMemcpyAsync(ix->d_gmasks, gmasks.data(), gmasks.size() * 4, cudaMemcpyHostToDevice, st));
   FF_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_sorted);
   FF_CUDA(cudaGetLastError());
-  ctx->db.device_bytes += ((size_t)n_keys + 1) * 4 + (n + 64) * 4 + (identity ? 0 : (n + 1) * 4) + masks.size() * 4 + masks_w1.size() * 4;
+  ctx->db.device_bytes += ((size_t)n_keys + 1) * 4 + (n + 64) * 4 + (identity ? 0 : (n + 1) * 4) + 2 * masks.size() * 4 + masks_w1.size() * 4;
   return FF_OK;
 }
 

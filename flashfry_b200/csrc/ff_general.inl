@@ -56,7 +56,12 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_pattern_sc
   __shared__ unsigned int s_hitn[kScanWarps];
   const ScanParams &p = gp.sp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, 0};
+#ifdef FF_RING
+  __shared__ uint4 s_ring[kScanWarps * FF_RING * 32];
+  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, 0, s_ring + warp * FF_RING * 32};
+#else
+  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, 0, nullptr};
+#endif
   if (lane == 0) s_hitn[warp] = 0;
   __syncwarp();
   unsigned long long compares = 0;

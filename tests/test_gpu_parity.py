@@ -501,3 +501,42 @@ def test_hit_aggregates_minot_and_in_genome(ff, oracle):
         got = ("UNK" if c2[i] == 2 ** 31 - 1 else str(c2[i]), str(n2[i]), ",".join(str(x) for x in h2[i]))
         assert got == want, (i, got, want)
     assert i2[4] == 7
+
+
+@pytest.mark.parametrize("k", [0, 1, 3, 4, 5, 6])
+def test_cell_major_scan_equals_guide_major_and_oracle(small_ctx, small_db, oracle, k, monkeypatch):
+    """The cell-major kernel (k_cell_scan: the same (guide, seed) pairs visited cell by cell for L2 reuse) is selected
+    for large batches on large indexes; forced here on the small FlashFry-format database."""
+    _, db, _ = small_db
+    targets = db.soa()[0]
+    guides = np.concatenate([helpers.random_guides(oracle, db.pack, 17 + k, 333),
+                             helpers.planted_guides(db.pack, targets, 71 + k, 400, max_subs=5)])
+    ref = oracle.discover_blocks(db, guides, k, 2000)
+    monkeypatch.setenv("FF_CELL_SCAN", "1")
+    for ppi in ("4", "32"):
+        monkeypatch.setenv("FF_CELL_PPI_B", ppi)
+        got = small_ctx.discover(guides, k, 2000, positions=True)
+        helpers.assert_hits_equal(got, ref, check_positions=True)
+    monkeypatch.setenv("FF_CELL_SCAN", "0")
+    helpers.assert_hits_equal(small_ctx.discover(guides, k, 2000, positions=True), ref, check_positions=True)
+
+
+def test_cell_major_scan_other_enzymes_and_edge_cases(ff, oracle, tmp_path, monkeypatch):
+    monkeypatch.setenv("FF_CELL_SCAN", "1")
+    contigs = helpers.random_genome(78, 250_000, repeat_unit=70, n_repeats=150)
+    fa = str(tmp_path / "g.fa")
+    helpers.write_fasta(fa, contigs)
+    for enzyme in ("cpf1", "spcas9ngg19", "spcas9"):
+        dbp = str(tmp_path / ("db_" + enzyme))
+        oracle.build_database(fa, dbp, enzyme)
+        db = oracle.read_database(dbp)
+        targets = db.soa()[0]
+        guides = helpers.planted_guides(db.pack, targets, 5, 300, max_subs=4)
+        with ff.Context(0) as ctx:
+            ctx.load_database(dbp)
+            for k, max_ot in ((4, 2000), (3, 2), (0, 2000)):
+                ref = oracle.discover_blocks(db, guides, k, max_ot)
+                helpers.assert_hits_equal(ctx.discover(guides, k, max_ot, positions=True), ref, check_positions=True)
+            one = ctx.discover(guides[:1], 4, 2000)
+            helpers.assert_hits_equal(one, oracle.discover_blocks(db, guides[:1], 4, 2000))
+            assert ctx.discover(guides[:0], 4, 2000).n_guides == 0
