@@ -26,7 +26,6 @@ struct CellParams {
   const uint32_t *perm_a, *perm_b;      // guide indices listed by class
   const int *cls_off;                   // [2][kCells + 1] first guide of every class
   const long long *seg_item0;           // [kSegs + 1] first work item of every segment; [kSegs] = number of items
-  int debug_cell;                       // experiments: >= 0 = only this cell of the part-one phase
   unsigned long long *next_item;        // work counter: warps claim items in order, so the whole grid stays inside ~one cell
 };
 
@@ -231,7 +230,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_cell_scan(
   const ScanParams &p = cp.sp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   BucketRec *recs = s_recs + warp * 32;
-  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, p.hA, nullptr};
+  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, p.hA};
   if (lane == 0) s_hitn[warp] = 0;
   __syncwarp();
   unsigned long long compares = 0;
@@ -259,9 +258,6 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_cell_scan(
    for (long long item = (long long)first; item < (long long)first + FF_CELL_CLAIM && item < n_items; ++item) {
     while (cp.seg_item0[seg + 1] <= item) ++seg;  // the next claimed item may open the next (non-empty) segment
     const int phase = seg / (kCells * kCells), cell = (seg / kCells) % kCells, cls = seg % kCells;
-    if (cp.debug_cell >= 0 && (phase != 0 || cell != cp.debug_cell)) continue;
-    if (cp.debug_cell == -2 && phase != 0) continue;
-    if (cp.debug_cell == -3 && phase != 1) continue;
     const int grp = cell ^ cls;
     const int n = phase ? cp.ng_b[grp] : cp.ng_a[grp];
     const int ppi = phase ? cp.ppi_b : 32;
@@ -323,8 +319,6 @@ static int cell_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int nA_h, int nB
     cp->ng_a[g] = db.A.gcum[g][std::min(15, nA_h)];
     cp->ng_b[g] = nB_h < 0 ? 0 : db.B.gcum[g][std::min(15, nB_h)];
   }
-  cp->debug_cell = -1;
-  if (const char *e = getenv("FF_DEBUG_CELL")) cp->debug_cell = atoi(e);
   cp->ppi_b = sp.B.seeds_per_item >= 32 ? 32 : std::max(4, sp.B.seeds_per_item * 2);
   if (const char *e = getenv("FF_CELL_PPI_B")) cp->ppi_b = std::max(1, std::min(32, atoi(e)));
   FF_TRY(ctx->cell_ws.reserve((size_t)G * 4 * 6 + (2 * kCells + 2 * (kCells + 1)) * 4 + (kSegs + 1) * 8 + 512));

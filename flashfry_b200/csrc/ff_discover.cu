@@ -73,7 +73,6 @@ struct WarpHits {  // everything the (rare) emit path needs, passed by value so 
   unsigned long long *hit_count;
   unsigned long long hit_cap;
   int hA;
-  uint4 *ring;                   // FF_RING builds: this warp's chunk ring (shared)
 };
 
 __device__ __forceinline__ void emit_hit(const WarpHits &wh, uint64_t key) {
@@ -99,22 +98,9 @@ __device__ __forceinline__ void flush_warp_hits(const WarpHits &wh, int lane) {
   __syncwarp();
 }
 
-#ifndef FF_LDG_MODE
-#define FF_LDG_MODE 0
-#endif
 __device__ __forceinline__ uint4 ldg128(const uint32_t *p) {
   uint4 v;
-#if FF_LDG_MODE == 0
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-#elif FF_LDG_MODE == 1
-  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-#elif FF_LDG_MODE == 2
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-#elif FF_LDG_MODE == 3
-  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-#endif
   return v;
 }
 
@@ -221,43 +207,6 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
     budget = __shfl_sync(0xffffffffu, budget, src);
     if (lane >= n) { lo = 0; hi = 0; budget = -1; }
   }
-#ifdef FF_RING
-  // Stream every 128-entry chunk of the batch's buckets through a per-warp ring in shared memory: cp.async (16 bytes per
-  // lane, L1 bypassed) runs FF_RING chunks ahead of the compare, so the load latency of a chunk overlaps the verification
-  // of the chunks before it.  A lane only ever reads back the 16 bytes it requested itself, so no barrier is needed --
-  // cp.async.wait_group orders a lane's own copies.
-  {
-    const uint32_t lane4 = 4u * lane;
-    uint4 *ring = wh.ring;  // [FF_RING][32]
-    int ij = 0, cj = 0;               // issue / consume cursors: bucket
-    uint32_t ic = 0, cc = 0;          //                          chunk inside the bucket
-    for (int step = 0;; ++step) {
-      if (ij < n) {
-        const uint32_t blo = __shfl_sync(0xffffffffu, lo, ij) & ~3u, bhi = __shfl_sync(0xffffffffu, hi, ij);
-        const uint32_t base = blo + 128u * ic + lane4;
-        if (base < bhi) {
-          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (step % FF_RING) * 32 + lane);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(sd.other + base) : "memory");
-        }
-        ++ic;
-        if (blo + 128u * ic >= bhi) { ++ij; ic = 0; }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (step < FF_RING - 1) continue;
-      asm volatile("cp.async.wait_group %0;" ::"n"(FF_RING - 1) : "memory");
-      if (cj >= n) break;
-      const uint32_t jlo = __shfl_sync(0xffffffffu, lo, cj), jhi = __shfl_sync(0xffffffffu, hi, cj);
-      const int bud = __shfl_sync(0xffffffffu, budget, cj);
-      const uint32_t base = (jlo & ~3u) + 128u * cc + lane4;
-      if (base < jhi) {
-        const uint4 v = ring[((step - (FF_RING - 1)) % FF_RING) * 32 + lane];
-        verify_chunk<PASS_B, PAT>(p, wh, sd.canon, v, base, jlo, jhi, probe, bud, guide_key, pi.pmask, pi.lo_d);
-      }
-      ++cc;
-      if ((jlo & ~3u) + 128u * cc >= jhi) { ++cj; cc = 0; }
-    }
-  }
-#else
   static_assert(32 % FF_GROUP == 0, "a group must not wrap around the warp");
   const uint32_t lane4 = 4u * lane;
   // does any bucket of this batch need more than its first 128-entry chunk?  (never, for part-one buckets of a
@@ -288,7 +237,6 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
       const int bud = __shfl_sync(0xffffffffu, budget, l0 + j);
 #ifndef FF_TAIL
 #define FF_TAIL 4
-#endif
       for (uint32_t c2 = (jlo & ~3u) + lane4 + 128u; c2 < jhi; c2 += 128u * FF_TAIL) {
         uint4 w[FF_TAIL];
 #pragma unroll
@@ -314,12 +262,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_seed_scan(
   __shared__ uint64_t s_hits[kScanWarps * kHW];
   __shared__ unsigned int s_hitn[kScanWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#ifdef FF_RING
-  __shared__ uint4 s_ring[kScanWarps * FF_RING * 32];
-  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, p.hA, s_ring + warp * FF_RING * 32};
-#else
-  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, p.hA, nullptr};
-#endif
+  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, p.hA};
   if (lane == 0) s_hitn[warp] = 0;
   __syncwarp();
   unsigned long long compares = 0;

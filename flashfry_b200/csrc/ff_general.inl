@@ -35,7 +35,6 @@ struct GeneralParams {
   int a_bases, P;
   int c0, c1, cell_shift;
   const uint32_t *cell_off;  // nullptr = the whole database in one window
-  int debug_skip;            // experiments only: 1 = skip pass A items, 2 = skip pass B items
 };
 
 // The template a pattern lays over the stored protospacer (wildcard digit = 0) and the wildcard position (-1: none).
@@ -56,12 +55,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_pattern_sc
   __shared__ unsigned int s_hitn[kScanWarps];
   const ScanParams &p = gp.sp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#ifdef FF_RING
-  __shared__ uint4 s_ring[kScanWarps * FF_RING * 32];
-  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, 0, s_ring + warp * FF_RING * 32};
-#else
-  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, 0, nullptr};
-#endif
+  WarpHits wh{s_hits + warp * kHW, &s_hitn[warp], p.hits, p.hit_count, p.hit_cap, 0};
   if (lane == 0) s_hitn[warp] = 0;
   __syncwarp();
   unsigned long long compares = 0;
@@ -86,7 +80,6 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_pattern_sc
     const bool wild_a = w >= 0 && w < a, wild_b = w >= a;
     PatItem pi;
     pi.c0 = gp.c0; pi.c1 = gp.c1; pi.cell_shift = gp.cell_shift; pi.cell_off = gp.cell_off;
-    if (gp.debug_skip && ((bi < c.itemsA) == (gp.debug_skip == 1))) continue;
     if (bi < c.itemsA) {
       const int seed0 = bi * 32;
       pi.masks = wild_a ? gp.a_masks_w1 : p.A.masks;
@@ -350,7 +343,6 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
   if (windowed) FF_TRY(db_build_cell_offsets(ctx));
   gp.cell_off = windowed ? db.d_cell_off : nullptr;
   gp.cell_shift = 2 * a - 6;  // kCells = 4^3
-  if (const char *e = getenv("FF_DEBUG_SKIP")) gp.debug_skip = atoi(e);
 
   // ---- workspaces
   FF_TRY(ctx->counters.reserve(64));
