@@ -251,7 +251,10 @@ def run_native(args):
         roof = {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "alg_bytes_per_launch": scan_bytes, "kernel_ms": scan_avg_ms,
                 "kernel_share_of_step": scan_avg_ms / ms_per_step, "traffic": None,
-                "entries_streamed_per_launch": compares, "entries_per_guide": compares / max(G, 1)}
+                "entries_streamed_per_launch": compares, "entries_per_guide": compares / max(G, 1),
+                # the second ceiling -- one 32-bit POPC per compared entry, 16 lanes/clk/SM x 148 SMs x 1.9 GHz
+                "compares_per_s": compares / (scan_avg_ms / 1e3), "compare_ceiling_per_s": 4.5e12,
+                "compare_frac": compares / (scan_avg_ms / 1e3) / 4.5e12}
         tr = ncu_traffic()
         if (tr and tr.get("targets") == n_t and tr.get("max_mismatch") == args.k and tr.get("kernel") == scan_kernel
                 and tr.get("guides_in_profiled_launch") == G):

@@ -123,9 +123,12 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   if (n_guides > 0) FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, n_guides * 8, cudaMemcpyHostToDevice, c->stream));
   const uint64_t *d_guides = c->scratch_guides.as<uint64_t>();
 
-  int64_t min_batch = 16384;
+  // Sub-batches of DECREASING size (50 / 30 / 20 %): the D2H of a sub-batch hides behind the scan of the next one, so
+  // only the last -- smallest -- copy is exposed, while the large first batches keep the scan's bucket reuse high.
+  int64_t min_batch = 20000;
   if (const char *e = getenv("FF_SUBBATCH_MIN")) min_batch = std::max<long long>(1, atoll(e));
-  int nb = want_positions ? 1 : (int)std::min<int64_t>(4, std::max<int64_t>(1, n_guides / min_batch));
+  const int nb = want_positions ? 1 : (int)std::min<int64_t>(3, std::max<int64_t>(1, n_guides / min_batch));
+  static const int kCut[4][4] = {{0, 0, 0, 0}, {0, 100, 100, 100}, {0, 60, 100, 100}, {0, 50, 80, 100}};  // cumulative %
 
   HitsOwner *o = owner_get();
   if (!o) { set_error("out of host memory"); return FF_ENOMEM; }
@@ -140,7 +143,7 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   std::vector<int64_t> batch_hit_off(nb + 1, 0), batch_g0(nb + 1, 0);
   cudaStream_t cs = c->copy_stream;
   for (int b = 0; b < nb; ++b) {
-    const int64_t g0 = G * b / nb, g1 = G * (b + 1) / nb, gn = g1 - g0;
+    const int64_t g0 = G * kCut[nb][b] / 100, g1 = G * kCut[nb][b + 1] / 100, gn = g1 - g0;
     const int slot = b & 1;
     batch_g0[b] = g0;
     if (b >= 2) { cudaError_t e = cudaEventSynchronize(c->slot_copied[slot]); if (e != cudaSuccess) return fail(cuda_fail(e, "event sync", __FILE__, __LINE__)); }

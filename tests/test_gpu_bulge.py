@@ -197,3 +197,16 @@ def test_bulge_properties_on_a_large_synthetic_index(ff, oracle):
         lo, hi = int(got.row_ptr[g]), int(got.row_ptr[g + 1])
         rlo, rhi = int(ref.row_ptr[j]), int(ref.row_ptr[j + 1])
         assert (got.targets[lo:hi] == ref.targets[rlo:rhi]).all() and (got.bulge[lo:hi] == ref.bulge[rlo:rhi]).all()
+
+
+def test_bulge_sub_batches_equal_single_batch(family_ctx, family_db, oracle, monkeypatch):
+    """The host entry point pipelines guide sub-batches (D2H of one behind the scan of the next) in bulge mode too."""
+    targets, seeds = family_db
+    pack = oracle.PACK_BY_INDEX[3]
+    guides = np.concatenate([seeds, helpers.planted_guides(pack, targets, 31, 50, max_subs=3)])
+    monkeypatch.setenv("FF_SUBBATCH_MIN", "1000000")
+    one = family_ctx.discover_bulge(guides, 3, 400, 3)
+    for min_batch in ("40", "20"):
+        monkeypatch.setenv("FF_SUBBATCH_MIN", min_batch)
+        many = family_ctx.discover_bulge(guides, 3, 400, 3)
+        assert_bulge_equal(many, one)
