@@ -55,7 +55,7 @@ class FFTimings(C.Structure):
 
 # every symbol include/flashfry_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_load_database",
-           "ff_load_database_arrays", "ff_synth_database", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
+           "ff_save_image", "ff_load_image", "ff_load_database_arrays", "ff_synth_database", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
            "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_score", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
 
 _lib = None
@@ -76,6 +76,8 @@ def lib():
     L.ff_last_error.restype = C.c_char_p
     L.ff_set_stream.argtypes = [vp, vp]
     L.ff_load_database.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.ff_save_image.argtypes = [vp, C.c_char_p]
+    L.ff_load_image.argtypes = [vp, C.c_char_p]
     L.ff_load_database_arrays.argtypes = [vp, C.c_int, C.c_int, u64p, C.c_uint64, u64p, C.c_uint64,
                                           C.POINTER(C.c_char_p), C.c_int]
     L.ff_synth_database.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64]

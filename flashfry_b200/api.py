@@ -92,6 +92,12 @@ class Context:
     def load_database(self, db_path: str, header_path: Optional[str] = None):
         N.check(N.lib().ff_load_database(self._h, db_path.encode(), header_path.encode() if header_path else None))
 
+    def save_image(self, path: str):
+        N.check(N.lib().ff_save_image(self._h, path.encode()))
+
+    def load_image(self, path: str):
+        N.check(N.lib().ff_load_image(self._h, path.encode()))
+
     def load_database_arrays(self, enzyme_index: int, targets, positions=None, contigs: Sequence[str] = (), bin_width: int = 7):
         t = _u64(targets)
         p = _u64(positions) if positions is not None else None

@@ -287,6 +287,19 @@ int ff_load_database(ff_ctx *c, const char *db_path, const char *header_path) {
   return db_load_files(c, db_path, hp.c_str());
 }
 
+int ff_save_image(ff_ctx *c, const char *image_path) {
+  if (!c || !image_path) { set_error("null argument"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  FF_CUDA(cudaStreamSynchronize(c->stream));
+  return db_save_image(c, image_path);
+}
+
+int ff_load_image(ff_ctx *c, const char *image_path) {
+  if (!c || !image_path) { set_error("null argument"); return FF_EINVAL; }
+  FF_CUDA(cudaSetDevice(c->device));
+  return db_load_image(c, image_path);
+}
+
 int ff_load_database_arrays(ff_ctx *c, int enzyme_index, int bin_width, const uint64_t *targets, uint64_t n_targets,
                             const uint64_t *positions, uint64_t n_positions, const char *const *contigs, int n_contigs) {
   if (!c || (!targets && n_targets)) { set_error("null argument"); return FF_EINVAL; }

@@ -25,6 +25,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
+#include <mutex>
 #include <thread>
 
 #include "ff_common.cuh"
@@ -116,6 +118,41 @@ static void make_masks(int bases, std::vector<uint32_t> *out, int *cum) {
   }
 }
 
+// Mask tables of one key width: all masks by distance, the same over width - 1 bases (bulge wildcards), and grouped by
+// the first three bases ((group, distance, value) order: `masks` is already in (distance, value) order, so a stable
+// counting sort by group keeps the distance order inside every group).
+struct MaskTables {
+  std::vector<uint32_t> masks, masks_w1, gmasks;
+  int cum[16], cum_w1[16], goff[kCells + 1], gcum[kCells][16];
+};
+
+static const MaskTables &mask_tables(int key_bases) {
+  static std::mutex mu;
+  static std::map<int, MaskTables> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key_bases);
+  if (it != cache.end()) return it->second;
+  MaskTables &t = cache[key_bases];
+  make_masks(key_bases, &t.masks, t.cum);
+  make_masks(key_bases - 1, &t.masks_w1, t.cum_w1);
+  t.gmasks.resize(t.masks.size());
+  const int gshift = 2 * key_bases - 6;
+  std::vector<int> cnt(kCells + 1, 0);
+  for (uint32_t m : t.masks) cnt[((m & 0xFFFFFFu) >> gshift) + 1]++;
+  for (int g = 0; g < kCells; ++g) cnt[g + 1] += cnt[g];
+  for (int g = 0; g <= kCells; ++g) t.goff[g] = cnt[g];
+  std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+  memset(t.gcum, 0, sizeof t.gcum);
+  for (uint32_t m : t.masks) {
+    const int g = (int)((m & 0xFFFFFFu) >> gshift);
+    t.gmasks[cur[g]++] = m;
+    t.gcum[g][std::min(15, (int)(m >> 24))]++;
+  }
+  for (int g = 0; g < kCells; ++g)
+    for (int h = 1; h < 16; ++h) t.gcum[g][h] += t.gcum[g][h - 1];
+  return t;
+}
+
 static unsigned int nblk(uint64_t n) { return (unsigned int)((n + 255) / 256); }
 
 // Build one half of the seed index from per-target keys.  identity: entries stay in database order (keys must already be sorted).
@@ -142,33 +179,17 @@ static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, const uin
     sorted_keys = d_sorted;
   }
   k_key_offsets<<<nblk((uint64_t)n_keys + 1), 256, 0, st>>>(sorted_keys, n, n_keys, ix->d_off);
-  std::vector<uint32_t> masks;
-  make_masks(key_bases, &masks, ix->cum);
+  // the mask tables depend on the key width only: built once per process, re-uploaded per database
+  const MaskTables &mt = mask_tables(key_bases);
+  const std::vector<uint32_t> &masks = mt.masks, &masks_w1 = mt.masks_w1, &gmasks = mt.gmasks;
+  memcpy(ix->cum, mt.cum, sizeof ix->cum);
+  memcpy(ix->cum_w1, mt.cum_w1, sizeof ix->cum_w1);
+  memcpy(ix->goff, mt.goff, sizeof ix->goff);
+  memcpy(ix->gcum, mt.gcum, sizeof ix->gcum);
   FF_CUDA(cudaMalloc(&ix->d_masks, masks.size() * 4));
   FF_CUDA(cudaMemcpyAsync(ix->d_masks, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice, st));
-  std::vector<uint32_t> masks_w1;
-  make_masks(key_bases - 1, &masks_w1, ix->cum_w1);
   FF_CUDA(cudaMalloc(&ix->d_masks_w1, masks_w1.size() * 4));
   FF_CUDA(cudaMemcpyAsync(ix->d_masks_w1, masks_w1.data(), masks_w1.size() * 4, cudaMemcpyHostToDevice, st));
-  // grouped copy: (first three bases, distance, value) order; `masks` is already in (distance, value) order, so a stable
-  // counting sort by group keeps the distance order inside every group
-  std::vector<uint32_t> gmasks(masks.size());
-  {
-    const int gshift = 2 * key_bases - 6;
-    std::vector<int> cnt(kCells + 1, 0);
-    for (uint32_t m : masks) cnt[((m & 0xFFFFFFu) >> gshift) + 1]++;
-    for (int g = 0; g < kCells; ++g) cnt[g + 1] += cnt[g];
-    for (int g = 0; g <= kCells; ++g) ix->goff[g] = cnt[g];
-    std::vector<int> cur(cnt.begin(), cnt.end() - 1);
-    memset(ix->gcum, 0, sizeof ix->gcum);
-    for (uint32_t m : masks) {
-      const int g = (int)((m & 0xFFFFFFu) >> gshift);
-      gmasks[cur[g]++] = m;
-      ix->gcum[g][std::min(15, (int)(m >> 24))]++;
-    }
-    for (int g = 0; g < kCells; ++g)
-      for (int h = 1; h < 16; ++h) ix->gcum[g][h] += ix->gcum[g][h - 1];
-  }
   FF_CUDA(cudaMalloc(&ix->d_gmasks, gmasks.size() * 4));
   FF_CUDA(cudaMemcpyAsync(ix->d_gmasks, gmasks.data(), gmasks.size() * 4, cudaMemcpyHostToDevice, st));
   FF_CUDA(cudaStreamSynchronize(st));
@@ -501,6 +522,77 @@ int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
     }
   });
   return db_from_host_arrays(ctx, pack, h.bin_width, targets.data(), n_targets, positions.data(), n_positions, h.contigs);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SoA image side-car: the decoded database as flat little-endian arrays.  Loading it is one
+// sequential read + H2D + index build, without the BGZF inflate and the [target, position x count]* block walk that
+// dominate a cold start from FlashFry's own files.  Layout: 64-byte header {magic "FFB200IM", u32 version, i32 enzyme,
+// i32 bin width, u32 contigs, u64 targets, u64 positions, u64 bytes of the contig table}, the contig table (NUL-
+// terminated names), zero padding to a multiple of 8, targets u64[], positions u64[].
+static const char kImageMagic[8] = {'F', 'F', 'B', '2', '0', '0', 'I', 'M'};
+struct ImageHeader {
+  char magic[8];
+  uint32_t version;
+  int32_t enzyme_index, bin_width;
+  uint32_t n_contigs;
+  uint64_t n_targets, n_positions, contig_bytes;
+  uint8_t pad[16];
+};
+static_assert(sizeof(ImageHeader) == 64, "image header is 64 bytes");
+
+int db_save_image(ff_ctx *ctx, const char *path) {
+  Database &db = ctx->db;
+  if (!db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
+  std::vector<uint64_t> targets(db.n_targets + 1), positions(db.n_positions + 1);
+  FF_CUDA(cudaMemcpy(targets.data(), db.d_targets, db.n_targets * 8, cudaMemcpyDeviceToHost));
+  if (db.d_positions && db.n_positions) FF_CUDA(cudaMemcpy(positions.data(), db.d_positions, db.n_positions * 8, cudaMemcpyDeviceToHost));
+  std::string names;
+  for (const std::string &c : db.contigs) { names += c; names.push_back('\0'); }
+  while (names.size() % 8) names.push_back('\0');
+  ImageHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, kImageMagic, 8);
+  h.version = 1; h.enzyme_index = db.pack.enzyme_index; h.bin_width = db.bin_width; h.n_contigs = (uint32_t)db.contigs.size();
+  h.n_targets = db.n_targets; h.n_positions = db.d_positions ? db.n_positions : 0; h.contig_bytes = names.size();
+  FILE *f = fopen(path, "wb");
+  if (!f) { set_error("cannot create %s", path); return FF_EIO; }
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+  ok = ok && (names.empty() || fwrite(names.data(), 1, names.size(), f) == names.size());
+  ok = ok && (h.n_targets == 0 || fwrite(targets.data(), 8, h.n_targets, f) == h.n_targets);
+  ok = ok && (h.n_positions == 0 || fwrite(positions.data(), 8, h.n_positions, f) == h.n_positions);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) { set_error("short write on %s", path); return FF_EIO; }
+  return FF_OK;
+}
+
+int db_load_image(ff_ctx *ctx, const char *path) {
+  FILE *f = fopen(path, "rb");
+  if (!f) { set_error("cannot open %s", path); return FF_EIO; }
+  ImageHeader h;
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kImageMagic, 8) != 0 || h.version != 1) {
+    fclose(f);
+    set_error("%s is not a flashfry_b200 database image (bad magic or version)", path);
+    return FF_EFORMAT;
+  }
+  Pack pack;
+  if (pack_from_index(h.enzyme_index, &pack) != FF_OK) { fclose(f); return FF_EFORMAT; }
+  if (h.contig_bytes > (1u << 28) || h.n_targets > 0xFFFF0000ull) { fclose(f); set_error("implausible sizes in image %s", path); return FF_EFORMAT; }
+  std::string names(h.contig_bytes, '\0');
+  std::vector<uint64_t> targets(h.n_targets + 1), positions(h.n_positions + 1);
+  bool ok = h.contig_bytes == 0 || fread(&names[0], 1, h.contig_bytes, f) == h.contig_bytes;
+  ok = ok && (h.n_targets == 0 || fread(targets.data(), 8, h.n_targets, f) == h.n_targets);
+  ok = ok && (h.n_positions == 0 || fread(positions.data(), 8, h.n_positions, f) == h.n_positions);
+  fclose(f);
+  if (!ok) { set_error("truncated database image %s", path); return FF_EFORMAT; }
+  std::vector<std::string> contigs;
+  for (size_t i = 0, k = 0; k < h.n_contigs && i < names.size(); ++k) {
+    contigs.emplace_back(names.c_str() + i);
+    i += contigs.back().size() + 1;
+  }
+  if (contigs.size() != h.n_contigs) { set_error("contig table of %s is damaged", path); return FF_EFORMAT; }
+  // the index build re-validates order and counts on the device (FF_EFORMAT on a damaged image)
+  return db_from_host_arrays(ctx, pack, h.bin_width, targets.data(), h.n_targets, h.n_positions ? positions.data() : nullptr, h.n_positions, contigs);
 }
 
 // ------------------------------------------------------------------------------------------------------------

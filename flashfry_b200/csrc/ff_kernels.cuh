@@ -49,6 +49,8 @@ int db_from_host_arrays(ff_ctx *ctx, const Pack &pack, int bin_width, const uint
                         const uint64_t *positions, uint64_t n_positions, const std::vector<std::string> &contigs);
 int db_build_index(ff_ctx *ctx);  // d_targets (+ d_positions) already in HBM -> d_tlow, d_sub_off, tables, d_pos_off
 int db_build_cell_offsets(ff_ctx *ctx);  // lazily: per-bucket offsets at the database-order cell boundaries (windowed scan)
+int db_save_image(ff_ctx *ctx, const char *path);  // SoA side-car of the resident database
+int db_load_image(ff_ctx *ctx, const char *path);
 int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path);
 int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed);
 

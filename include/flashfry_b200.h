@@ -61,6 +61,12 @@ int ff_set_stream(ff_ctx *ctx, void *cuda_stream);
  * block types of reference/binary/blocks/BlockManager.scala:362-442) + text side-car
  * (reference/binary/BinaryHeader.scala:115-160); inflates on host threads and makes it resident in HBM. */
 int ff_load_database(ff_ctx *ctx, const char *db_path, const char *header_path);
+/* Database image side-car (not a FlashFry format; a cache of the decoded database): ff_save_image writes the resident
+ * database (targets, positions, contig names) as flat little-endian arrays, ff_load_image makes it resident again with
+ * one sequential read + H2D, skipping the BGZF inflate and block walk of ff_load_database.  The index build
+ * re-validates the content (FF_EFORMAT on a damaged image). */
+int ff_save_image(ff_ctx *ctx, const char *image_path);
+int ff_load_image(ff_ctx *ctx, const char *image_path);
 /* Same residency from caller-provided arrays in database order (targets carry their 16-bit count; positions may be
  * NULL).  contigs may be NULL.  Used by tests and by hosts that already hold the decoded blocks. */
 int ff_load_database_arrays(ff_ctx *ctx, int enzyme_index, int bin_width, const uint64_t *targets,

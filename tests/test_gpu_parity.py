@@ -540,3 +540,57 @@ def test_cell_major_scan_other_enzymes_and_edge_cases(ff, oracle, tmp_path, monk
             one = ctx.discover(guides[:1], 4, 2000)
             helpers.assert_hits_equal(one, oracle.discover_blocks(db, guides[:1], 4, 2000))
             assert ctx.discover(guides[:0], 4, 2000).n_guides == 0
+
+
+def test_cell_major_scan_skewed_batches(ff, oracle, monkeypatch):
+    """Guide batches that break the cell-major kernel's balance assumptions: thousands of copies of one guide (one guide
+    class, one hot bucket per seed, hit buffer regrown and the scan repeated), all guides in two classes, one guide."""
+    monkeypatch.setenv("FF_CELL_SCAN", "1")
+    pack = oracle.PACK_BY_INDEX[3]
+    targets, seeds = helpers.family_database(oracle, seed=19, n_seeds=24, variants_per_seed=900)
+    bin_off = oracle.bin_offsets_from_sorted(pack, 7, targets)
+    with ff.Context(0) as ctx:
+        ctx.load_database_arrays(3, targets)
+        same = np.repeat(seeds[:1], 3000)
+        two = np.concatenate([np.repeat(seeds[1:2], 500), helpers.planted_guides(pack, targets[:2000], 3, 500, max_subs=2)])
+        for guides, max_ot in ((same, 2000), (same, 10 ** 6), (two, 50), (seeds[:1], 2000)):
+            ref = oracle.discover_soa(pack, 7, targets, bin_off, guides, 4, max_ot)
+            got = ctx.discover(guides, 4, max_ot)
+            helpers.assert_hits_equal(got, ref)
+        assert int(ref.row_ptr[-1]) > 0
+
+
+def test_database_image_round_trip(ff, oracle, small_db, tmp_path):
+    """ff_save_image / ff_load_image: the side-car brings back the same resident database (targets, positions, contigs),
+    so discover gives the same rows and positions; damaged images are refused."""
+    dbp, db, _ = small_db
+    targets = db.soa()[0]
+    guides = helpers.planted_guides(db.pack, targets, 12, 200, max_subs=4)
+    img = str(tmp_path / "small.ffimg")
+    with ff.Context(0) as ctx:
+        ctx.load_database(dbp)
+        ref = ctx.discover(guides, 4, 2000, positions=True)
+        ctx.save_image(img)
+    with ff.Context(0) as ctx:
+        ctx.load_image(img)
+        info = ctx.info()
+        assert info.enzyme_index == 3 and info.n_targets == len(targets) and ctx.contigs() == db.contigs
+        assert (ctx.copy_targets() == targets).all()
+        helpers.assert_hits_equal(ctx.discover(guides, 4, 2000, positions=True), ref, check_positions=True)
+        raw = open(img, "rb").read()
+        bad = str(tmp_path / "bad.ffimg")
+        open(bad, "wb").write(b"XX" + raw[2:])
+        with pytest.raises(ff.FlashFryError) as e:
+            ctx.load_image(bad)
+        assert e.value.code == -5
+        open(bad, "wb").write(raw[:len(raw) // 2])
+        with pytest.raises(ff.FlashFryError) as e:
+            ctx.load_image(bad)
+        assert e.value.code == -5
+        swapped = bytearray(raw)
+        off = 64 + ((sum(len(c) + 1 for c in db.contigs) + 7) // 8) * 8
+        swapped[off:off + 8], swapped[off + 8:off + 16] = raw[off + 8:off + 16], raw[off:off + 8]  # break the target order
+        open(bad, "wb").write(bytes(swapped))
+        with pytest.raises(ff.FlashFryError) as e:
+            ctx.load_image(bad)
+        assert e.value.code == -5
