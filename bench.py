@@ -324,7 +324,7 @@ def run_native(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        _emit(out)
 
 
 def cpu_baseline(ctx, guides, args, threads, budget_guides):
@@ -371,7 +371,7 @@ def run_reference(args):
         ctx = ff.Context(int(os.environ.get("LOCAL_RANK", "0")))
         ctx.synth_database(ENZYME, args.targets, SEED_DB)
     except Exception as e:  # noqa: BLE001
-        print(json.dumps({"impl": "reference", "unavailable": "cannot materialise the synthetic index: %s" % e}))
+        _emit({"impl": "reference", "unavailable": "cannot materialise the synthetic index: %s" % e})
         return
     t = ctx.copy_targets()
     n_t = len(t)
@@ -394,16 +394,29 @@ def run_reference(args):
     v = n / (ms / 1e3)
     sample_txt = ("%d-guide batches of the same %d-guide workload vs the full %d-target index per step, oracle port of the "
                   "reference loop order on %d host threads" % (n, len(guides), n_t, threads))
-    print(json.dumps({"impl": "reference", "metric": "guides/sec at <=4 mismatches vs hg38-sized index", "value": v, "unit": "guides/s",
+    _emit({"impl": "reference", "metric": "guides/sec at <=4 mismatches vs hg38-sized index", "value": v, "unit": "guides/s",
                       "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": v / 53.7, "dtype": "u64", "data": "synthetic",
                       "config": {"workload": "configs[2] bounded sample: " + sample_txt, "targets": n_t, "max_mismatch": args.k,
                                  "maximum_off_targets": args.max_ot},
                       "cpu_baseline": {"value": v, "unit": "guides/s", "cores": threads, "kind": "port", "sample": sample_txt},
-                      "e2e": {"value": v, "unit": "guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": "guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+def _emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL's version banner ...) was sent
+    to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

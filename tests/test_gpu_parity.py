@@ -186,6 +186,23 @@ def test_chr22_1000_guides_config(ff, oracle, chr22_db_path):
         got = ctx.discover(guides, 4, 2000)
         helpers.assert_hits_equal(got, ref)
         assert ref.overflowed.sum() >= 1 or int(ref.total_count.max()) > 100
+        # the same batch through the cell-major kernel and through the windowed general path: a real genome's skewed
+        # buckets (repeats, poly-N runs of the seed keys) instead of the uniform synthetic index
+        for env in ({"FF_CELL_SCAN": "1"}, {"FF_FORCE_GENERAL": "1", "FF_WINDOW_CELLS": "3"}):
+            os.environ.update(env)
+            try:
+                helpers.assert_hits_equal(ctx.discover(guides, 4, 2000), ref)
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+        planted = helpers.planted_guides(db.pack, targets, 1003, 300, max_subs=2)
+        ref_b = oracle.discover_bulge(db.pack, targets, planted[:6], 3, 2000, 3, n_threads=os.cpu_count() or 1)
+        got_b = ctx.discover_bulge(planted, 3, 2000, 3)
+        for g in range(6):
+            lo, hi = int(got_b.row_ptr[g]), int(got_b.row_ptr[g + 1])
+            rlo, rhi = int(ref_b.row_ptr[g]), int(ref_b.row_ptr[g + 1])
+            assert (got_b.targets[lo:hi] == ref_b.targets[rlo:rhi]).all() and (got_b.bulge[lo:hi] == ref_b.bulge[rlo:rhi]).all()
+            assert (got_b.mismatches[lo:hi] == ref_b.mismatches[rlo:rhi]).all()
 
 
 def test_scorers_bit_exact_on_fake_sites(ff, oracle):
