@@ -165,9 +165,12 @@ __device__ __forceinline__ void verify_flat(const ScanParams &p, const WarpHits 
   }
 }
 
+constexpr int kFlatChunks = 2;  // 16-byte chunks a lane takes per slot: 2 = one whole, aligned 32-byte sector per lane
+constexpr int kFlatRounds = 2;  // slots in flight per lane
 template <bool PASS_B, int U>
 __device__ __forceinline__ void stream_flat(const ScanParams &p, const SeedSide &sd, const WarpHits &wh, BucketRec *recs, int lane, uint32_t lo,
                                             uint32_t hi, int budget, uint32_t probe, uint32_t gid) {
+  constexpr uint32_t kSlot = 4u * kFlatChunks;  // entries per lane slot
   {  // squeeze out empty buckets
     const unsigned int nz = __ballot_sync(0xffffffffu, hi > lo);
     const int n = __popc(nz);
@@ -182,7 +185,8 @@ __device__ __forceinline__ void stream_flat(const ScanParams &p, const SeedSide 
       if (lane >= n) { lo = 0; hi = 0; }
     }
   }
-  const uint32_t c = hi > lo ? (hi - (lo & ~3u) + 3u) >> 2 : 0u;
+  const uint32_t s0 = lo & ~(kSlot - 1u);  // slots are aligned to their own size (32 bytes for kFlatChunks = 2)
+  const uint32_t c = hi > lo ? (hi - s0 + kSlot - 1u) / kSlot : 0u;
   uint32_t P = c;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -190,14 +194,14 @@ __device__ __forceinline__ void stream_flat(const ScanParams &p, const SeedSide 
     if (lane >= o) P += t;
   }
   const uint32_t T = __shfl_sync(0xffffffffu, P, 31);
-  const uint32_t A = (lo & ~3u) - 4u * (P - c);
+  const uint32_t A = s0 - kSlot * (P - c);
   const uint32_t pb = probe | ((uint32_t)budget << 24);
   __syncwarp();
   recs[lane] = BucketRec{lo, hi, gid, 0u};
   __syncwarp();
   const uint32_t le_mask = 0xffffffffu >> (31 - lane);  // lanes <= lane
   for (uint32_t x0 = 0; x0 < T; x0 += 32u * U) {
-    uint4 v[U];
+    uint4 v[U][kFlatChunks];
     uint32_t base[U], pbj[U];
     int jj[U];
 #pragma unroll
@@ -210,14 +214,21 @@ __device__ __forceinline__ void stream_flat(const ScanParams &p, const SeedSide 
       jj[u] = j;
       const uint32_t Aj = __shfl_sync(0xffffffffu, A, j);
       pbj[u] = __shfl_sync(0xffffffffu, pb, j);
-      base[u] = Aj + 4u * (r0 + lane);
-      v[u] = make_uint4(0, 0, 0, 0);
-      if (r0 + lane < T) v[u] = ldg128(sd.other + base[u]);
+      base[u] = Aj + kSlot * (r0 + lane);
+#pragma unroll
+      for (int w = 0; w < kFlatChunks; ++w) {
+        // (past the bucket's last chunk the padded array still holds neighbouring entries: the range check rejects them)
+        v[u][w] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (r0 + lane < T) v[u][w] = ldg128(sd.other + base[u] + 4u * w);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (x0 + 32u * u + lane < T)
-        verify_flat<PASS_B>(p, wh, sd.canon, v[u], base[u], recs, jj[u], pbj[u] & 0xFFFFFFu, (int)(pbj[u] >> 24));
+      if (x0 + 32u * u + lane < T) {
+#pragma unroll
+        for (int w = 0; w < kFlatChunks; ++w)
+          verify_flat<PASS_B>(p, wh, sd.canon, v[u][w], base[u] + 4u * w, recs, jj[u], pbj[u] & 0xFFFFFFu, (int)(pbj[u] >> 24));
+      }
   }
   __syncwarp();
   if (*wh.count >= kHW / 2) flush_warp_hits(wh, lane);
@@ -235,15 +246,13 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_cell_scan(
   __syncwarp();
   unsigned long long compares = 0;
   const long long n_items = cp.seg_item0[kSegs];
-#ifndef FF_CELL_CLAIM
-#define FF_CELL_CLAIM 2
-#endif
-  // Items are claimed from a global counter, FF_CELL_CLAIM at a time: a static stride lets fast warps run cells ahead
+  constexpr int kClaim = 2;
+  // Items are claimed from a global counter, kClaim at a time: a static stride lets fast warps run cells ahead
   // of slow ones (measured: L2 hit rate 24 %, 23 GB of HBM reads), claiming in order keeps all resident warps within
   // a fraction of a cell.
   for (;;) {
     unsigned long long first = 0;
-    if (lane == 0) first = atomicAdd(cp.next_item, (unsigned long long)FF_CELL_CLAIM);
+    if (lane == 0) first = atomicAdd(cp.next_item, (unsigned long long)kClaim);
     first = __shfl_sync(0xffffffffu, first, 0);
     if ((long long)first >= n_items) break;
     int seg = 0;
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_cell_scan(
       }
     }
 #pragma unroll 1
-   for (long long item = (long long)first; item < (long long)first + FF_CELL_CLAIM && item < n_items; ++item) {
+   for (long long item = (long long)first; item < (long long)first + kClaim && item < n_items; ++item) {
     while (cp.seg_item0[seg + 1] <= item) ++seg;  // the next claimed item may open the next (non-empty) segment
     const int phase = seg / (kCells * kCells), cell = (seg / kCells) % kCells, cls = seg % kCells;
     const int grp = cell ^ cls;
@@ -283,23 +292,10 @@ __global__ void __launch_bounds__(kScanThreads, FF_SCAN_MIN_BLOCKS) k_cell_scan(
     }
     compares += hi - lo;
     const int n_here = (int)min((long long)ppi, n_pairs - (item - cp.seg_item0[seg]) * ppi);
-#ifndef FF_FLAT_UA
-#define FF_FLAT_UA 4
-#endif
-#ifndef FF_FLAT_UB
-#define FF_FLAT_UB 0
-#endif
-#if FF_FLAT_UB > 0
-    if (phase) stream_flat<true, FF_FLAT_UB>(p, p.B, wh, recs, lane, lo, hi, budget, probe, gid);
-#else
+    // part one: short buckets, flattened so that every lane is busy; part two: long buckets, the per-bucket loop
+    // (A/B on the GPU: flattening the long buckets gains nothing)
     if (phase) stream_pairs<true>(p, p.B, wh, lane, lo, hi, budget, probe, gid, n_here);
-#endif
-#if FF_FLAT_UA > 0
-    else stream_flat<false, FF_FLAT_UA>(p, p.A, wh, recs, lane, lo, hi, budget, probe, gid);
-#else
-    else stream_pairs<false>(p, p.A, wh, lane, lo, hi, budget, probe, gid, n_here);
-#endif
-    (void)n_here;
+    else stream_flat<false, kFlatRounds>(p, p.A, wh, recs, lane, lo, hi, budget, probe, gid);
    }
   }
   flush_warp_hits(wh, lane);
