@@ -200,3 +200,30 @@ def test_host_mirror_site_finder_reference_vectors(built, tmp_path):
             assert g[2] == want and int(g[1]) == a and g[3] == ("FWD" if kind == "fwd" else "RVS")
         if "context_defined" in c:
             assert [g[4] != "NONE" for g in got] == c["context_defined"]
+
+
+def test_integration_sources_match_the_document_and_the_jni_shim_type_checks():
+    """INTEGRATION.md's Java / C / Scala blocks are shipped as files under integration/; the JNI shim must compile
+    (syntax + types) against the C ABI header with a minimal stand-in for <jni.h> (this image has no JDK), and every
+    JNI entry point must have its `native` declaration in NativeBridge.java."""
+    import subprocess
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```(java|c|scala)\n(.*?)```", md, re.S)
+    files = {"java": ["integration/java/flashfry/NativeBridge.java"], "c": ["integration/jni/flashfry_b200_jni.c"],
+             "scala": ["integration/scala/GpuTraverser.scala", "integration/scala/GpuScoreModel.scala"]}
+    seen = {"java": 0, "c": 0, "scala": 0}
+    for lang, body in blocks:
+        path = os.path.join(ROOT, files[lang][seen[lang]])
+        seen[lang] += 1
+        assert open(path).read().endswith(body), path + " drifted from INTEGRATION.md"
+    assert seen == {"java": 1, "c": 1, "scala": 2}
+    shim = os.path.join(ROOT, "integration", "jni", "flashfry_b200_jni.c")
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([gcc, "-std=c11", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter",
+                        "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"), shim],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    java = open(os.path.join(ROOT, "integration", "java", "flashfry", "NativeBridge.java")).read()
+    natives = set(re.findall(r"public static native [\w\[\]]+\s+(\w+)\(", java))
+    exported = set(re.findall(r"Java_flashfry_NativeBridge_(\w+)\(", open(shim).read()))
+    assert natives == exported and len(natives) >= 10
