@@ -26,7 +26,8 @@ struct CellParams {
   const uint32_t *perm_a, *perm_b;      // guide indices listed by class
   const int *cls_off;                   // [2][kCells + 1] first guide of every class
   const long long *seg_item0;           // [kSegs + 1] first work item of every segment; [kSegs] = number of items
-  unsigned long long *next_item;        // work counter: warps claim items in order, so the whole grid stays inside ~one cell
+  unsigned long long *next_item;        // [2] work counters (one per index half): warps claim items in order, so the whole
+                                        // grid stays inside ~one cell
 };
 
 __global__ void k_guide_classes(const uint64_t *__restrict__ guides, int64_t n, int proto_shift, uint64_t proto_mask, int b_bits, int a_bits,
@@ -239,7 +240,13 @@ __device__ __forceinline__ void stream_flat(const ScanParams &p, const SeedSide 
 #ifndef FF_CELL_MIN_BLOCKS
 #define FF_CELL_MIN_BLOCKS 6
 #endif
-__global__ void __launch_bounds__(kScanThreads, FF_CELL_MIN_BLOCKS) k_cell_scan(CellParams cp) {
+// One launch per index half (PHASE 0: part one, 1: part two): each instantiation carries only its own streaming loop,
+// which keeps it inside the 40-register budget with fewer spills than a kernel that holds both.
+#ifndef FF_CELL_MIN_BLOCKS_B
+#define FF_CELL_MIN_BLOCKS_B FF_CELL_MIN_BLOCKS
+#endif
+template <int PHASE>
+__global__ void __launch_bounds__(kScanThreads, PHASE ? FF_CELL_MIN_BLOCKS_B : FF_CELL_MIN_BLOCKS) k_cell_scan(CellParams cp) {
   __shared__ uint64_t s_hits[kScanWarps * kHW];
   __shared__ unsigned int s_hitn[kScanWarps];
   __shared__ BucketRec s_recs[kScanWarps * 32];
@@ -250,19 +257,19 @@ __global__ void __launch_bounds__(kScanThreads, FF_CELL_MIN_BLOCKS) k_cell_scan(
   if (lane == 0) s_hitn[warp] = 0;
   __syncwarp();
   unsigned long long compares = 0;
-  const long long n_items = cp.seg_item0[kSegs];
+  const long long item_lo = cp.seg_item0[PHASE * kCells * kCells], n_items = cp.seg_item0[(PHASE + 1) * kCells * kCells];
   constexpr int kClaim = 2;
   // Items are claimed from a global counter, kClaim at a time: a static stride lets fast warps run cells ahead
   // of slow ones (measured: L2 hit rate 24 %, 23 GB of HBM reads), claiming in order keeps all resident warps within
   // a fraction of a cell.
   for (;;) {
     unsigned long long first = 0;
-    if (lane == 0) first = atomicAdd(cp.next_item, (unsigned long long)kClaim);
-    first = __shfl_sync(0xffffffffu, first, 0);
+    if (lane == 0) first = atomicAdd(cp.next_item + PHASE, (unsigned long long)kClaim);
+    first = __shfl_sync(0xffffffffu, first, 0) + (unsigned long long)item_lo;
     if ((long long)first >= n_items) break;
-    int seg = 0;
+    int seg = PHASE * kCells * kCells;
     {  // the segment that holds the first claimed item: the last one whose first item is <= item
-      int hi_s = kSegs - 1;
+      int hi_s = (PHASE + 1) * kCells * kCells - 1;
       while (seg < hi_s) {
         const int mid = (seg + hi_s + 1) >> 1;
         if (cp.seg_item0[mid] <= (long long)first) seg = mid; else hi_s = mid - 1;
@@ -271,7 +278,8 @@ __global__ void __launch_bounds__(kScanThreads, FF_CELL_MIN_BLOCKS) k_cell_scan(
 #pragma unroll 1
    for (long long item = (long long)first; item < (long long)first + kClaim && item < n_items; ++item) {
     while (cp.seg_item0[seg + 1] <= item) ++seg;  // the next claimed item may open the next (non-empty) segment
-    const int phase = seg / (kCells * kCells), cell = (seg / kCells) % kCells, cls = seg % kCells;
+    constexpr int phase = PHASE;
+    const int cell = (seg / kCells) % kCells, cls = seg % kCells;
     const int grp = cell ^ cls;
     const int n = phase ? cp.ng_b[grp] : cp.ng_a[grp];
     const int ppi = phase ? cp.ppi_b : 32;
@@ -299,7 +307,7 @@ __global__ void __launch_bounds__(kScanThreads, FF_CELL_MIN_BLOCKS) k_cell_scan(
     const int n_here = (int)min((long long)ppi, n_pairs - (item - cp.seg_item0[seg]) * ppi);
     // part one: short buckets, flattened so that every lane is busy; part two: long buckets, the per-bucket loop
     // (A/B on the GPU: flattening the long buckets gains nothing)
-    if (phase) stream_pairs<true>(p, p.B, wh, lane, lo, hi, budget, probe, gid, n_here);
+    if (PHASE) stream_pairs<true>(p, p.B, wh, lane, lo, hi, budget, probe, gid, n_here);
     else stream_flat<false, kFlatRounds>(p, p.A, wh, recs, lane, lo, hi, budget, probe, gid);
    }
   }

@@ -521,8 +521,9 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     if (G > 0) {
       if (cell_major) {
         cp.sp = sp;
-        FF_CUDA(cudaMemsetAsync(cp.next_item, 0, 8, st));
-        k_cell_scan<<<max_grid, kScanThreads, 0, st>>>(cp);
+        FF_CUDA(cudaMemsetAsync(cp.next_item, 0, 16, st));
+        k_cell_scan<0><<<max_grid, kScanThreads, 0, st>>>(cp);
+        if (nB > 0) { k_cell_scan<1><<<max_grid, kScanThreads, 0, st>>>(cp); launches++; }
       } else {
         k_seed_scan<<<grid, kScanThreads, 0, st>>>(sp);
       }
