@@ -125,9 +125,17 @@ __device__ __forceinline__ void stream_pairs(const ScanParams &p, const SeedSide
           w[c] = make_uint4(0, 0, 0, 0);
           if (c2 + 128u * c < jhi) w[c] = ldg128(sd.other + c2 + 128u * c);
         }
+        int best = 64;  // (chunks past the bucket end hold zeros: a chance match only costs a trip through the rare path)
 #pragma unroll
-        for (int c = 0; c < FF_TAIL; ++c)
-          if (c2 + 128u * c < jhi) verify_chunk<PASS_B, false>(p, wh, sd.canon, w[c], c2 + 128u * c, jlo, jhi, pr, bud, gk, 0u, 0);
+        for (int c = 0; c < FF_TAIL; ++c) {
+          const int d0 = base_dist32(w[c].x ^ pr), d1 = base_dist32(w[c].y ^ pr), d2 = base_dist32(w[c].z ^ pr), d3 = base_dist32(w[c].w ^ pr);
+          best = min(best, min(min(d0, d1), min(d2, d3)));
+        }
+        if (best <= bud) {
+#pragma unroll
+          for (int c = 0; c < FF_TAIL; ++c)
+            if (c2 + 128u * c < jhi) verify_chunk<PASS_B, false>(p, wh, sd.canon, w[c], c2 + 128u * c, jlo, jhi, pr, bud, gk, 0u, 0);
+        }
       }
     }
   }
@@ -226,9 +234,18 @@ __device__ __forceinline__ void stream_flat(const ScanParams &p, const SeedSide 
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (x0 + 32u * u + lane < T) {
+        const uint32_t pr = pbj[u] & 0xFFFFFFu;
+        const int bud = (int)(pbj[u] >> 24);
+        int best = 64;
 #pragma unroll
-        for (int w = 0; w < kFlatChunks; ++w)
-          verify_flat<PASS_B>(p, wh, sd.canon, v[u][w], base[u] + 4u * w, recs, jj[u], pbj[u] & 0xFFFFFFu, (int)(pbj[u] >> 24));
+        for (int w = 0; w < kFlatChunks; ++w) {
+          const int d0 = base_dist32(v[u][w].x ^ pr), d1 = base_dist32(v[u][w].y ^ pr), d2 = base_dist32(v[u][w].z ^ pr), d3 = base_dist32(v[u][w].w ^ pr);
+          best = min(best, min(min(d0, d1), min(d2, d3)));
+        }
+        if (best <= bud) {  // ONE branch per slot (A/B: 5.1 -> 4.8 ms); rare: redo the slot's chunks with the full checks
+#pragma unroll
+          for (int w = 0; w < kFlatChunks; ++w) verify_flat<PASS_B>(p, wh, sd.canon, v[u][w], base[u] + 4u * w, recs, jj[u], pr, bud);
+        }
       }
   }
   __syncwarp();
