@@ -59,6 +59,12 @@ int runDiscover(int argc, char **argv) {
   if (!(minGC >= 0 && minGC <= 1.0) || !(maxGC >= 0 && maxGC <= 1.0)) throw IllegalStateException("assertion failed");  // :81-82
   const bool positions = a.flag("positionOutput");
   const int device = atoi(a.get("device", "0").c_str());
+  int bulgeFlags = 0;  // extension, not a FlashFry option: --bulge rna,dna
+  for (auto &tok : split(a.get("bulge", ""), ',')) {
+    if (tok == "rna") bulgeFlags |= FF_BULGE_RNA;
+    else if (tok == "dna") bulgeFlags |= FF_BULGE_DNA;
+    else if (!tok.empty()) throw std::invalid_argument("--bulge takes rna, dna or rna,dna");
+  }
 
   fprintf(stderr, "Reading the header....\n");
   BinaryHeader header = BinaryHeader::readHeader(a.get("database") + ".header");
@@ -77,7 +83,7 @@ int runDiscover(int argc, char **argv) {
   fprintf(stderr, "scanning against the known targets from the genome with %zu guides\n", guideStorage.wrappedGuides.size());
   NativeContext nc(device);
   const auto t0 = std::chrono::steady_clock::now();
-  const uint64_t compares = GpuTraverser::scan(nc, a.get("database"), guideStorage, maxMismatch, positions);
+  const uint64_t compares = GpuTraverser::scan(nc, a.get("database"), guideStorage, maxMismatch, positions, bulgeFlags);
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   fprintf(stderr, "Performed a total of %llu guide to target comparisons (load + scan %.3f s)\n", (unsigned long long)compares, secs);
   fprintf(stderr, "Writing final output for %zu guides\n", guideStorage.wrappedGuides.size());
@@ -138,6 +144,7 @@ void usage() {
           "flashfry_b200_cli <discover|score> [options]\n"
           "  discover --fasta FILE --database FILE --output FILE [--positionOutput] [--forceLinear] [--maxMismatch 4]\n"
           "           [--flankingSequence 6] [--maximumOffTargets 2000] [--minGC 0.0] [--maxGC 1.0] [--device 0]\n"
+          "           [--bulge rna,dna]   (extension, not in FlashFry: one 1-bp bulge on top of the mismatches; tokens gain _R<q> / _D<q>)\n"
           "  score    --input FILE --output FILE --scoringMetrics hsu2013,doench2016cfd[,minot,dangerous] --database FILE\n"
           "           [--maxMismatch N] [--includeOTs] [--numericOutput] [--device 0]\n");
 }

@@ -146,6 +146,10 @@ struct CRISPRHit {
   std::vector<uint64_t> coordinates;
   bool validOffTargetCoordinates = true;
   std::vector<std::pair<std::string, std::string>> scores;  // addScore :103-109
+  // bulge extension only (not in the reference): mismatches of the best alignment and its code (0 none, 0x40|q RNA
+  // bulge at guide base q, 0x80|q DNA bulge at genomic base q); -1 = plain mismatch search
+  int bulgeMismatches = -1;
+  uint8_t bulge = 0;
   int getOffTargetCount() const { return (int)coordinates.size(); }
 };
 
@@ -348,14 +352,16 @@ struct NativeContext {
 // argument of the reference is not needed (the native side does its own pruning); the contract is the same: on return
 // every aggregator.wrappedGuides(i) holds its CRISPRHit list in database order, cut by the overflow rule.
 struct GpuTraverser {
+  // bulgeFlags != 0 selects the 1-bp bulge extension (ff_discover_bulge); 0 is the reference's search
   static uint64_t scan(NativeContext &nc, const std::string &binaryFile, ResultsAggregator &aggregator, int maxMismatch,
-                       bool wantPositions) {
+                       bool wantPositions, int bulgeFlags = 0) {
     ffCheck(ff_load_database(nc.ctx, binaryFile.c_str(), (binaryFile + ".header").c_str()));
     std::vector<uint64_t> guides;
     int maxOT = 2000;
     for (auto &g : aggregator.wrappedGuides) { guides.push_back(g.longEncoding); maxOT = g.overflow; }
     ff_hits *h = nullptr;
-    ffCheck(ff_discover(nc.ctx, guides.data(), (int64_t)guides.size(), maxMismatch, maxOT, wantPositions ? 1 : 0, &h));
+    if (bulgeFlags) ffCheck(ff_discover_bulge(nc.ctx, guides.data(), (int64_t)guides.size(), maxMismatch, maxOT, bulgeFlags, wantPositions ? 1 : 0, &h));
+    else ffCheck(ff_discover(nc.ctx, guides.data(), (int64_t)guides.size(), maxMismatch, maxOT, wantPositions ? 1 : 0, &h));
     for (int64_t g = 0; g < h->n_guides; ++g) {
       CRISPRSiteOT &ot = aggregator.wrappedGuides[g];
       for (int64_t i = h->row_ptr[g]; i < h->row_ptr[g + 1]; ++i) {
@@ -364,6 +370,7 @@ struct GpuTraverser {
         const int count = (int)(int16_t)(h->targets[i] >> 48);
         if (h->pos_ptr) hit.coordinates.assign(h->positions + h->pos_ptr[i], h->positions + h->pos_ptr[i + 1]);
         else { hit.coordinates.assign((size_t)count, 0); hit.validOffTargetCoordinates = false; }
+        if (bulgeFlags) { hit.bulgeMismatches = h->mismatches[i]; hit.bulge = h->bulge ? h->bulge[i] : 0; }
         ot.addOT(std::move(hit));
       }
       if (ot.currentTotal != h->total_count[g] || ot.full() != (h->overflowed[g] != 0))
@@ -542,7 +549,11 @@ struct TabDelimitedOutput {  // :104-160
   std::string hitToOutput(const CRISPRHit &hit, uint64_t guide) const {  // CRISPRHit.toOutput :54-101
     int count = 0;
     const std::string bases = bitEncoding.bitDecodeString(hit.sequence, &count);
-    std::string s = bases + "_" + std::to_string(count) + "_" + std::to_string(bitEncoding.mismatches(guide, hit.sequence));
+    std::string s = bases + "_" + std::to_string(count) + "_" +
+                    std::to_string(hit.bulgeMismatches >= 0 ? hit.bulgeMismatches : bitEncoding.mismatches(guide, hit.sequence));
+    // bulge extension: a fourth field names the looped-out base (R = guide base, D = genomic base); FlashFry's own
+    // `score` cannot re-read such tokens -- CFD / Hsu2013 are not defined for bulged alignments
+    if (hit.bulge) s += std::string("_") + ((hit.bulge & 0xC0) == 0x40 ? "R" : "D") + std::to_string(hit.bulge & 0x3F);
     if (!writePositions) return s;
     if (hit.validOffTargetCoordinates && !hit.coordinates.empty()) {
       s += "<";

@@ -210,3 +210,50 @@ def test_bulge_sub_batches_equal_single_batch(family_ctx, family_db, oracle, mon
         monkeypatch.setenv("FF_SUBBATCH_MIN", min_batch)
         many = family_ctx.discover_bulge(guides, 3, 400, 3)
         assert_bulge_equal(many, one)
+
+
+def test_cli_discover_with_bulge_option(ff, oracle, tmp_path):
+    """`flashfry_b200_cli discover --bulge rna,dna` (an extension of FlashFry's command line): every row's tokens
+    SEQ_count_mm[_R<q>|_D<q>] equal ff_discover_bulge's rows for the same guides."""
+    import subprocess
+    cli = os.path.join(os.path.dirname(os.path.abspath(ff.__file__)), "flashfry_b200_cli")
+    contigs = helpers.random_genome(91, 150_000, repeat_unit=50, n_repeats=100)
+    fa = str(tmp_path / "g.fa")
+    helpers.write_fasta(fa, contigs)
+    dbp = str(tmp_path / "db")
+    oracle.build_database(fa, dbp, "spcas9ngg")
+    db = oracle.read_database(dbp)
+    targets = db.soa()[0]
+    rng = np.random.default_rng(4)
+    with open(str(tmp_path / "guides.fa"), "w") as fh:
+        for i in range(12):
+            seq, _ = oracle.decode(int(targets[int(rng.integers(0, len(targets)))]), 23)
+            s = list(seq)
+            for _ in range(int(rng.integers(0, 3))):
+                s[int(rng.integers(0, 20))] = "ACGT"[int(rng.integers(0, 4))]
+            fh.write(">g%d\n%s\n" % (i, "ATATATATAT" + "".join(s) + "ATATATATAT"))
+    out = str(tmp_path / "out.tsv")
+    r = subprocess.run([cli, "discover", "--fasta", str(tmp_path / "guides.fa"), "--database", dbp, "--output", out, "--maxMismatch", "3",
+                        "--bulge", "rna,dna"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l.rstrip("\n").split("\t") for l in open(out)][1:]
+    assert len(rows) >= 12
+    guides = np.asarray([oracle.encode(row[3], 1) for row in rows], np.uint64)
+    with ff.Context(0) as ctx:
+        ctx.load_database(dbp)
+        ref = ctx.discover_bulge(guides, 3, 2000, 3)
+    n_bulged = 0
+    for g, row in enumerate(rows):
+        toks = [t for t in row[-1].split(",") if t]
+        lo, hi = int(ref.row_ptr[g]), int(ref.row_ptr[g + 1])
+        assert len(toks) == hi - lo and int(row[-2]) == int(ref.total_count[g])
+        for t, i in zip(toks, range(lo, hi)):
+            f = t.split("_")
+            assert oracle.encode(f[0], int(f[1])) == int(ref.targets[i]) and int(f[2]) == int(ref.mismatches[i])
+            code = int(ref.bulge[i])
+            if code:
+                n_bulged += 1
+                assert f[3] == ("R" if (code & 0xC0) == 0x40 else "D") + str(code & 0x3F)
+            else:
+                assert len(f) == 3
+    assert n_bulged > 0
