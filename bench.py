@@ -12,9 +12,13 @@ A "step" = one discover call over one batch of guides per GPU; with N GPUs every
 
 `value`  : whole-job guides/s with guides already in HBM and results left in HBM (CUDA events, max over ranks).
 `e2e`    : the same metric through the C ABI with HOST buffers (ff_discover: H2D of the guides, D2H of the hit lists).
-`roofline`: the dominant kernel (k_seed_scan) against the measured HBM copy bandwidth.  Algorithmic bytes per launch =
-            for every (guide, seed) the two 4-byte index entries + 4 bytes per index entry streamed from the seed's
-            bucket + 8 bytes per guide + 8 bytes per candidate hit written.
+`roofline`: the dominant kernel (k_cell_scan, the cell-major seed scan: one launch per index half, timed together with CUDA
+            events on the launching stream) against the measured HBM copy bandwidth.  Algorithmic bytes per call = for
+            every (guide, seed) the two 4-byte index entries + 4 bytes per index entry streamed from the seed's bucket
+            + 8 bytes per guide + 8 bytes per candidate hit written; `traffic` = the HBM bytes ncu
+            measured for the same call (L2 serves the repeated bucket reads, so it is below the algorithmic bytes).
+`bulge_mode`, `fused_discover_score`: BASELINE.json configs[3] (an extension, no reference semantics) and configs[4] on
+            the same batch.
 """
 import argparse
 import json
