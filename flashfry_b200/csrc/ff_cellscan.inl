@@ -121,11 +121,9 @@ __device__ __forceinline__ void stream_pairs(const ScanParams &p, const SeedSide
       for (uint32_t c2 = (jlo & ~3u) + lane4 + 128u; c2 < jhi; c2 += 128u * FF_TAIL) {
         uint4 w[FF_TAIL];
 #pragma unroll
-        for (int c = 0; c < FF_TAIL; ++c) {
-          w[c] = make_uint4(0, 0, 0, 0);
-          if (c2 + 128u * c < jhi) w[c] = ldg128(sd.other + c2 + 128u * c);
-        }
-        int best = 64;  // (chunks past the bucket end hold zeros: a chance match only costs a trip through the rare path)
+        for (int c = 0; c < FF_TAIL; ++c)  // chunks past the bucket end re-read its first chunk (unconditional loads, see stream_flat)
+          w[c] = ldg128(sd.other + (c2 + 128u * c < jhi ? c2 + 128u * c : (jlo & ~3u) + lane4));
+        int best = 64;  // (a chance match in a re-read chunk only costs a trip through the rare path, which skips it)
 #pragma unroll
         for (int c = 0; c < FF_TAIL; ++c) {
           const int d0 = base_dist32(w[c].x ^ pr), d1 = base_dist32(w[c].y ^ pr), d2 = base_dist32(w[c].z ^ pr), d3 = base_dist32(w[c].w ^ pr);
@@ -203,6 +201,7 @@ __device__ __forceinline__ void stream_flat(const ScanParams &p, const SeedSide 
     if (lane >= o) P += t;
   }
   const uint32_t T = __shfl_sync(0xffffffffu, P, 31);
+  const uint32_t safe = __shfl_sync(0xffffffffu, s0, 0);  // first slot of the batch (lane 0 holds a non-empty bucket)
   const uint32_t A = s0 - kSlot * (P - c);
   const uint32_t pb = probe | ((uint32_t)budget << 24);
   __syncwarp();
@@ -224,12 +223,13 @@ __device__ __forceinline__ void stream_flat(const ScanParams &p, const SeedSide 
       const uint32_t Aj = __shfl_sync(0xffffffffu, A, j);
       pbj[u] = __shfl_sync(0xffffffffu, pb, j);
       base[u] = Aj + kSlot * (r0 + lane);
+      // Lanes past the last slot re-read the batch's first slot instead of being predicated off: an unconditional load
+      // needs neither the eight register initialisations nor the eight conditional moves a predicated one costs per
+      // slot, and the compare below skips those lanes anyway.
+      const uint32_t from = r0 + lane < T ? base[u] : safe;
 #pragma unroll
-      for (int w = 0; w < kFlatChunks; ++w) {
-        // (past the bucket's last chunk the padded array still holds neighbouring entries: the range check rejects them)
-        v[u][w] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        if (r0 + lane < T) v[u][w] = ldg128(sd.other + base[u] + 4u * w);
-      }
+      for (int w = 0; w < kFlatChunks; ++w)  // (past a bucket's last chunk the padded array holds neighbouring entries: the range check rejects them)
+        v[u][w] = ldg128(sd.other + from + 4u * w);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)

@@ -21,5 +21,5 @@ for it in range(3):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     tm = ctx.timings()
-    print("G=%d k=%d flags=%d: %.1f ms wall, scan %.1f ms, order %.1f, cut %.1f, total %.1f; hits %d cand %d compares/guide %.0f launches %d scan_launches %d  -> %.0f guides/s" % (
+    print("G=%d k=%d flags=%d: %.1f ms wall, scan %.2f ms, order %.2f, cut %.2f, total %.2f; hits %d cand %d compares/guide %.0f launches %d scan_launches %d  -> %.0f guides/s" % (
         G, k, flags, dt * 1e3, tm.scan_ms, tm.order_ms, tm.cut_ms, tm.total_ms, r.n_hits, r.n_candidate_hits, r.n_compares / G, tm.kernel_launches, tm.scan_launches, G / dt), flush=True)
