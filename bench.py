@@ -321,6 +321,29 @@ def run_native(args):
                                  "overflowed_guides_note": "nearly every guide reaches maximumOffTargets: the scan walks database-order windows and drops full guides",
                                  "e2e_guides_per_s": G / be2e, "e2e_d2h_bytes": (G + 1) * 8 + bh * 10 + G * 5,
                                  "parity": "extension, no reference semantics: checked against a brute-force definition in tests/test_gpu_bulge.py"}
+        # BASELINE.json configs[1]: 1 000 synthetic + 100 planted guides vs the chr22 quick-start database, when the database
+        # built by __graft_entry__.build() travelled with the tree (33.5 MB of targets: L2-resident after the first pass)
+        chr22 = os.path.join(ROOT, "tests", "golden", "_chr22", "chr22_cas9ngg_database")
+        if os.path.exists(chr22) and os.path.exists(chr22 + ".header"):
+            try:
+                c2 = ff.Context(local)
+                t0 = time.perf_counter()
+                c2.load_database(chr22)
+                load_s = time.perf_counter() - t0
+                t22 = c2.copy_targets()
+                g22 = make_guides(1100, 1001, t22[:: max(1, len(t22) // 4096)], 1002, planted_frac=100.0 / 1100.0)
+                d22 = torch.from_numpy(g22.view(np.int64)).to(dev)
+                ts = []
+                for _ in range(8):
+                    r22 = c2.discover_device(d22.data_ptr(), len(g22), args.k, args.max_ot, 0)
+                    ts.append(c2.timings().total_ms)
+                out["chr22_1000_guides"] = {"workload": "configs[1]: 1 000 synthetic + 100 planted guides vs the chr22 quick-start index (%d targets), k<=%d" % (len(t22), args.k),
+                                            "total_ms": float(np.median(ts[2:])), "guides_per_s": len(g22) / (float(np.median(ts[2:])) / 1e3),
+                                            "hits": int(r22.n_hits), "cold_load_s": load_s,
+                                            "parity": "tests/test_gpu_parity.py::test_chr22_1000_guides_config (bit-exact vs the oracle)"}
+                c2.close()
+            except Exception as e:  # noqa: BLE001 -- a side measurement must not take the bench line down
+                out["chr22_1000_guides"] = {"error": str(e)}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(ctx, guides, args, threads=1, budget_guides=args.cpu_guides)
     ctx.close()
