@@ -123,12 +123,16 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   if (n_guides > 0) FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, n_guides * 8, cudaMemcpyHostToDevice, c->stream));
   const uint64_t *d_guides = c->scratch_guides.as<uint64_t>();
 
-  // Sub-batches of DECREASING size (50 / 30 / 20 %): the D2H of a sub-batch hides behind the scan of the next one, so
+  // Sub-batches of DECREASING size (65 / 25 / 10 %): the D2H of a sub-batch hides behind the scan of the next one, so
   // only the last -- smallest -- copy is exposed, while the large first batches keep the scan's bucket reuse high.
   int64_t min_batch = 20000;
   if (const char *e = getenv("FF_SUBBATCH_MIN")) min_batch = std::max<long long>(1, atoll(e));
   const int nb = want_positions ? 1 : (int)std::min<int64_t>(3, std::max<int64_t>(1, n_guides / min_batch));
-  static const int kCut[4][4] = {{0, 0, 0, 0}, {0, 100, 100, 100}, {0, 60, 100, 100}, {0, 50, 80, 100}};  // cumulative %
+  int kCut[4][4] = {{0, 0, 0, 0}, {0, 100, 100, 100}, {0, 60, 100, 100}, {0, 65, 90, 100}};  // cumulative % (A/B on the GPU: 7.5 ms per 100 000 guides; 50/30/20: 7.8 ms)
+  if (const char *e = getenv("FF_SUBBATCH_CUTS")) {  // experiments: "c1,c2" = cumulative % of the first two of three sub-batches
+    int c1 = 0, c2 = 0;
+    if (sscanf(e, "%d,%d", &c1, &c2) == 2 && c1 > 0 && c1 < c2 && c2 < 100) { kCut[3][1] = c1; kCut[3][2] = c2; }
+  }
 
   HitsOwner *o = owner_get();
   if (!o) { set_error("out of host memory"); return FF_ENOMEM; }

@@ -465,7 +465,7 @@ def test_pipelined_sub_batches_equal_single_batch(ff, oracle, small_db, monkeypa
         ctx.load_database(small_db[0])
         monkeypatch.setenv("FF_SUBBATCH_MIN", "1000000")
         one, c1, s1, h1 = ctx.discover_score(guides, 4, 2000)
-        for min_batch in ("200", "100", "7"):  # 2 sub-batches (60 / 40 %), 3 sub-batches (50 / 30 / 20 %)
+        for min_batch in ("200", "100", "7"):  # 2 sub-batches (60 / 40 %), 3 sub-batches (65 / 25 / 10 %)
             monkeypatch.setenv("FF_SUBBATCH_MIN", min_batch)
             many, c4, s4, h4 = ctx.discover_score(guides, 4, 2000)
             helpers.assert_hits_equal(many, ref)
