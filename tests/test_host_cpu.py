@@ -227,3 +227,20 @@ def test_integration_sources_match_the_document_and_the_jni_shim_type_checks():
     natives = set(re.findall(r"public static native [\w\[\]]+\s+(\w+)\(", java))
     exported = set(re.findall(r"Java_flashfry_NativeBridge_(\w+)\(", open(shim).read()))
     assert natives == exported and len(natives) >= 10
+
+
+def test_library_carries_sm_100a_code_for_every_hot_kernel(built):
+    """The product is hand-written CUDA compiled for sm_100a only: the shared object must hold sm_100a cubins with the
+    scan / ordering / scoring kernels (no PTX-JIT fallback, no other architectures)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([cuobjdump, "--list-elf", built], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", elfs))
+    assert archs == {"sm_100a"}, archs
+    syms = subprocess.run([cuobjdump, "-symbols", built], capture_output=True, text=True).stdout
+    for kernel in ("k_cell_scan", "k_seed_scan", "k_pattern_scan", "k_overflow_cut", "k_cut_window", "k_sort_segments", "k_gather",
+                   "k_score", "k_hit_aggregates", "k_cell_offsets"):
+        assert kernel in syms, "kernel missing from the library: " + kernel
