@@ -51,7 +51,7 @@ def test_product_never_imports_the_oracle():
         if "_obj" in base or "__pycache__" in base:
             continue
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".inl")):
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert not bad.search(txt), os.path.join(base, f)
     assert not bad.search(open(os.path.join(ROOT, "include", "flashfry_b200.h")).read())
