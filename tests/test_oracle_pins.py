@@ -275,3 +275,41 @@ def test_bulge_discover_without_bulges_is_the_reference_search(oracle):
         got = oracle.discover_bulge(pack, targets, seeds, 4, max_ot, 0)
         helpers.assert_hits_equal(got, ref)
         assert not got.bulge.any()
+
+
+def test_bulge_templates_are_equivalent_to_the_alignments(oracle):
+    """The CUDA path searches bulges as 20-position TEMPLATES with one wildcard (csrc/ff_general.inl pattern_template):
+    RNA bulge at q -> [*, g0..g(q-1), g(q+1)..g19], DNA bulge at q -> [g1..gq, *, g(q+1)..g19].  Restated here with the
+    same bit formulas and checked against the string definition: the masked mismatch count of (template, target) must
+    equal the mismatch count of the corresponding alignment, for every q."""
+    import random
+    rnd = random.Random(11)
+    P = 20
+    full = (1 << (2 * P)) - 1
+
+    def enc(s):
+        v = 0
+        for ch in s:
+            v = (v << 2) | "ACGT".index(ch)
+        return v
+
+    def template(proto, typ, q):
+        lo_mask = (1 << (2 * (P - 1 - q))) - 1
+        if typ == 1:
+            return (((proto >> 2) & ~lo_mask & ((1 << (2 * (P - 1))) - 1)) | (proto & lo_mask)), 0
+        hi_mask = full & ~((1 << (2 * (P - q))) - 1)
+        return ((((proto << 2) & full) & hi_mask) | (proto & lo_mask)), q
+
+    def masked_mm(a, b, wild):
+        x = (a ^ b) & ~(3 << (2 * (P - 1 - wild)))
+        return bin((x | (x >> 1)) & int("01" * P, 2)).count("1")
+
+    ham = lambda a, b: sum(x != y for x, y in zip(a, b))
+    for _ in range(400):
+        g = "".join(rnd.choice("ACGT") for _ in range(P))
+        t = "".join(rnd.choice("ACGT") if rnd.random() < 0.3 else c for c in g)
+        for q in range(1, P - 1):
+            tr, wr = template(enc(g), 1, q)
+            assert masked_mm(tr, enc(t), wr) == ham(g[:q] + g[q + 1:], t[1:])
+            td, wd = template(enc(g), 2, q)
+            assert masked_mm(td, enc(t), wd) == ham(g[1:], t[:q] + t[q + 1:])
