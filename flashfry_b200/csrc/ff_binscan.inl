@@ -1,0 +1,583 @@
+// Bin-major, bit-sliced seed scan (included by ff_discover.cu, inside namespace ff) -- the large-batch scan.
+//
+// What it replaces in the reference: the loop nest bin -> sub-bin -> target x guide of
+// reference/binary/blocks/BlockManager.scala:143-254 driven by OrderedBinTraversalFactory.scala:146-177 (same order of
+// the outer loop -- bins of the first seven bases in AAAAAAA..TTTTTTT order -- nothing else in common).
+//
+// The same (guide, seed) pairs as k_seed_scan, organised so that neither HBM nor the instruction issue slots are spent
+// on anything but the compares:
+//   * COMPARE.  `other` (the protospacer part a seed does not key on) is stored BIT-SLICED: entries in groups of 32,
+//     one 32-bit word per bit plane.  One lane compares its pair's probe against 32 entries at once: per base two LOP3
+//     (mismatch plane = (lo ^ Gl) | (hi ^ Gh), Gl / Gh = the probe's bits spread to full words, per lane), then a
+//     carry-save adder tree over the 9..11 mismatch planes and a 4-bit carry chain for "count <= budget": ~40 LOP3 per
+//     32 entries instead of XOR + fold + POPC + min per entry (5 x 32) -- the POPC pipe (16 lanes / clk / SM), which
+//     bounded the previous kernel's ceiling, is not used at all.
+//   * PART ONE (index A, short buckets: k_bin_scan).  A CTA claims one BIN -- all keys that share their first
+//     key_bases - 4 bases (7 bases = FlashFry's own bin width for the 20-mers) -- and stages the bin's slice of the
+//     bit-sliced array (~41 KB on a human-sized index) in shared memory with one TMA bulk copy (cp.async.bulk +
+//     mbarrier).  The pairs that land in the bin are ENUMERATED, not sorted: guides are listed by the bin of their own
+//     key; a bin F is reached from the guide classes F ^ m, m over the bin-part masks within the seed budget, and each
+//     such guide contributes the masks over the last four key bases within the remaining budget.  Lanes take one pair
+//     each and stream its bucket (2..5 groups) out of shared memory.  Every byte of the index is read from HBM once.
+//   * PART TWO (index B, long buckets: k_pair_scan).  The few pairs (28 per guide at k = 4) are counting-sorted by
+//     bucket; lanes take consecutive sorted pairs, so the ~10 pairs of a bucket sit in neighbouring lanes, read the
+//     same addresses in the same instruction (one L1 wavefront) and every bucket comes from HBM once.
+//   * HITS.  A lane that finds hits pushes (hit word, group, guide) into a per-warp queue in shared memory; the warp
+//     drains the queue with all lanes when it is half full: one global atomic per ~32 hit words.
+
+#define FF_FA(a, b, c, s, cy) { const uint32_t _x = (a) ^ (b); s = _x ^ (c); cy = ((a) & (b)) | (_x & (c)); }
+
+// bit-sliced population count of NB one-bit planes -> 4-bit count (c3 c2 c1 c0)
+template <int NB> struct PlaneCount;
+template <> struct PlaneCount<9> {
+  static __device__ __forceinline__ void run(const uint32_t (&m)[9], uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3) {
+    uint32_t s1, k1, s2, k2, s3, k3, k4, t, k5;
+    FF_FA(m[0], m[1], m[2], s1, k1) FF_FA(m[3], m[4], m[5], s2, k2) FF_FA(m[6], m[7], m[8], s3, k3)
+    FF_FA(s1, s2, s3, c0, k4)
+    FF_FA(k1, k2, k3, t, k5)
+    c1 = t ^ k4;
+    const uint32_t k6 = t & k4;
+    c2 = k5 ^ k6; c3 = k5 & k6;
+  }
+};
+template <> struct PlaneCount<10> {
+  static __device__ __forceinline__ void run(const uint32_t (&m)[10], uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3) {
+    uint32_t s1, k1, s2, k2, s3, k3, u, k4, t, k5, k6;
+    FF_FA(m[0], m[1], m[2], s1, k1) FF_FA(m[3], m[4], m[5], s2, k2) FF_FA(m[6], m[7], m[8], s3, k3)
+    FF_FA(s1, s2, s3, u, k4)
+    c0 = u ^ m[9];
+    const uint32_t k7 = u & m[9];
+    FF_FA(k1, k2, k3, t, k5)
+    FF_FA(t, k4, k7, c1, k6)
+    c2 = k5 ^ k6; c3 = k5 & k6;
+  }
+};
+template <> struct PlaneCount<11> {
+  static __device__ __forceinline__ void run(const uint32_t (&m)[11], uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3) {
+    uint32_t s1, k1, s2, k2, s3, k3, u, k4, k7, t, k5, k6;
+    FF_FA(m[0], m[1], m[2], s1, k1) FF_FA(m[3], m[4], m[5], s2, k2) FF_FA(m[6], m[7], m[8], s3, k3)
+    FF_FA(s1, s2, s3, u, k4)
+    FF_FA(u, m[9], m[10], c0, k7)
+    FF_FA(k1, k2, k3, t, k5)
+    FF_FA(t, k4, k7, c1, k6)
+    c2 = k5 ^ k6; c3 = k5 & k6;
+  }
+};
+
+// What a lane holds for its pair: the probe's bits spread to words, and 15 - budget for the carry chain.
+template <int NB> struct LaneProbe {
+  uint32_t gl[NB], gh[NB], kb[4];
+  __device__ __forceinline__ void set(uint32_t probe, int budget) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      gl[i] = (uint32_t)((int32_t)(probe << (31 - 2 * i)) >> 31);
+      gh[i] = (uint32_t)((int32_t)(probe << (30 - 2 * i)) >> 31);
+      asm volatile("" : "+r"(gl[i]), "+r"(gh[i]));  // keep them in registers: ptxas otherwise recomputes them inside the group loop
+    }
+    const uint32_t kk = 15u - (uint32_t)min(max(budget, 0), 15);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      kb[b] = (uint32_t)((int32_t)(kk << (31 - b)) >> 31);
+      asm volatile("" : "+r"(kb[b]));
+    }
+  }
+  // bit e set <=> entry e of the group is within budget.  w = the group's plane words (w[2i] low bit, w[2i+1] high bit of base i)
+  __device__ __forceinline__ uint32_t match(const uint32_t (&w)[2 * NB]) const {
+    uint32_t m[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) m[i] = (w[2 * i] ^ gl[i]) | (w[2 * i + 1] ^ gh[i]);
+    uint32_t c0, c1, c2, c3;
+    PlaneCount<NB>::run(m, c0, c1, c2, c3);
+    // count + (15 - budget) carries out of four bits <=> count > budget
+    uint32_t cy = c0 & kb[0];
+    cy = (c1 & kb[1]) | (cy & (c1 | kb[1]));
+    cy = (c2 & kb[2]) | (cy & (c2 | kb[2]));
+    cy = (c3 & kb[3]) | (cy & (c3 | kb[3]));
+    return ~cy;
+  }
+};
+
+struct HitSink {
+  uint64_t *hits;
+  unsigned long long *hit_count;
+  unsigned long long hit_cap;
+  int tbits;
+};
+
+constexpr int kQCap = 64;  // queue entries per warp; drained at >= 32, and an iteration adds at most 32
+
+// entries: x = hit word (range-checked), y = group, z = guide index, w = probe (part two: for the exact d1 > hA test)
+template <bool PASS_B>
+__device__ __forceinline__ void drain_queue(const HitSink &hs, uint4 *q, unsigned int *qn, int lane, const uint32_t *__restrict__ canon,
+                                            const uint32_t *__restrict__ other, int lo_d) {
+  __syncwarp();
+  const unsigned int n = *qn;
+  for (unsigned int i0 = 0; i0 < n; i0 += 32) {
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 + lane < n) e = q[i0 + lane];
+    uint32_t vm = e.x;
+    if (PASS_B) {  // pass B accepts only d1 > hA (the pairs with d1 <= hA belong to pass A)
+      uint32_t t = vm;
+      while (t) {
+        const int b = __ffs((int)t) - 1;
+        t &= t - 1u;
+        if (base_dist32(other[e.y * 32u + (uint32_t)b] ^ e.w) <= lo_d) vm &= ~(1u << b);
+      }
+    }
+    const int c = __popc(vm);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(hs.hit_count, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    unsigned long long pos = base + (unsigned long long)(incl - c);
+    const uint64_t gk = (uint64_t)e.z << hs.tbits;
+    while (vm) {
+      const int b = __ffs((int)vm) - 1;
+      vm &= vm - 1u;
+      const uint32_t idx = e.y * 32u + (uint32_t)b;
+      if (pos < hs.hit_cap) hs.hits[pos] = gk | (canon ? canon[idx] : idx);
+      ++pos;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) *qn = 0;
+  __syncwarp();
+}
+
+// Stream the groups of this lane's bucket [lo, hi) (empty for idle lanes).  `base` points at group `g_base`; the loop
+// is warp-uniform (longest bucket of the warp), lanes past their own bucket re-read its last group and drop the result.
+template <int NB, int STRIDE, bool PASS_B, bool SMEM>
+__device__ __forceinline__ void stream_groups(const uint32_t *base, uint32_t g_base, uint32_t lo, uint32_t hi, const LaneProbe<NB> &lp,
+                                              uint32_t gid, uint32_t probe, const HitSink &hs, uint4 *q, unsigned int *qn, int lane,
+                                              const uint32_t *canon, const uint32_t *other, int lo_d) {
+  const int n = hi > lo ? (int)(((hi - 1u) >> 5) - (lo >> 5)) : -1;  // index of the lane's last iteration
+  const int T = __reduce_max_sync(0xffffffffu, n);
+  const uint32_t g0 = n >= 0 ? (lo >> 5) : g_base;
+  for (int it = 0; it <= T; ++it) {
+    const uint32_t g = g0 + (uint32_t)min(it, max(n, 0));
+    const uint32_t *pg = base + (size_t)(g - g_base) * STRIDE;
+    uint32_t w[2 * NB];
+    if (STRIDE % 4 == 0) {
+#pragma unroll
+      for (int j = 0; j < (2 * NB + 3) / 4; ++j) {
+        const uint4 v = SMEM ? *reinterpret_cast<const uint4 *>(pg + 4 * j) : __ldg(reinterpret_cast<const uint4 *>(pg + 4 * j));
+        w[4 * j] = v.x; w[4 * j + 1] = v.y;
+        if (4 * j + 2 < 2 * NB) { w[4 * j + 2] = v.z; w[4 * j + 3] = v.w; }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const uint2 v = SMEM ? *reinterpret_cast<const uint2 *>(pg + 2 * j) : __ldg(reinterpret_cast<const uint2 *>(pg + 2 * j));
+        w[2 * j] = v.x; w[2 * j + 1] = v.y;
+      }
+    }
+    uint32_t hm = lp.match(w);
+    if (it > n) hm = 0u;
+    if (hm) {  // which of the group's entries belong to the bucket
+      if (g == (lo >> 5)) hm &= 0xFFFFFFFFu << (lo & 31u);
+      if (g == ((hi - 1u) >> 5)) hm &= 0xFFFFFFFFu >> (31u - ((hi - 1u) & 31u));
+      if (hm) q[atomicAdd(qn, 1u)] = make_uint4(hm, g, gid, probe);
+    }
+    __syncwarp();
+    if (*qn >= 32u) drain_queue<PASS_B>(hs, q, qn, lane, canon, other, lo_d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// part one: bins of index A through shared memory
+constexpr int kBinThreads = 384;
+constexpr int kBinWarps = kBinThreads / 32;
+constexpr int kNbrCap = 1160;       // bin-part masks within the seed budget (7 bases, distance <= 3: 1156)
+constexpr int kSliceGroups = 832;   // groups of 32 entries a CTA can stage (x 72 B = 58.5 KB; a human-sized bin is ~572)
+
+struct BinParams {
+  const uint32_t *planes, *off, *canon, *himasks, *lomasks;
+  int n_hi;            // bin-part masks within the budget
+  int cum_hi[5];       // cum_hi[d] = # bin-part masks at distance <= d (d <= hA <= 3)
+  int nm[4];           // nm[d] = # last-four-bases masks a guide reached at bin distance d contributes
+  int hA, k;
+  uint32_t n_bins;
+  const uint2 *sg;     // guides listed by the bin of their own key: x = probe | (last four key bases) << 24, y = guide index
+  const int *cls_off;  // [n_bins + 1]
+  HitSink hs;
+  unsigned long long *n_compares;
+  unsigned int *next_bin;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct BinShared {
+  unsigned long long mbar;
+  uint32_t bin, b0, b1, glob, g_base, bytes;
+  uint32_t R[6], PB[6];
+  uint32_t wtot[kBinWarps];
+  unsigned int qn[kBinWarps];
+  uint32_t off[260];
+  uint32_t lom[256];
+  uint32_t pre[kNbrCap + 4];
+  uint32_t start[kNbrCap + 4];
+  uint4 q[kBinWarps][kQCap];
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
+  constexpr int STRIDE = 2 * NB;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint32_t *slice = reinterpret_cast<uint32_t *>(smem_raw);
+  BinShared &sh = *reinterpret_cast<BinShared *>(smem_raw + (size_t)kSliceGroups * STRIDE * 4);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sh.mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 256) sh.lom[tid] = bp.lomasks[tid];
+  if (lane == 0) sh.qn[warp] = 0;
+  uint32_t phase = 0;
+  unsigned long long compares = 0;
+  uint4 *q = sh.q[warp];
+  unsigned int *qn = &sh.qn[warp];
+  for (;;) {
+    __syncthreads();  // the previous bin is finished: its slice and tables may be overwritten
+    if (tid == 0) sh.bin = atomicAdd(bp.next_bin, 1u);
+    __syncthreads();
+    const uint32_t bin = sh.bin;
+    if (bin >= bp.n_bins) break;
+    for (int i = tid; i <= 256; i += kBinThreads) sh.off[i] = bp.off[(bin << 8) + i];
+    // guide classes that reach this bin, and the exclusive prefix of their sizes ("visits" of the bin)
+    uint32_t carry = 0;
+    for (int j0 = 0; j0 < bp.n_hi; j0 += kBinThreads) {
+      const int j = j0 + tid;
+      uint32_t cnt = 0;
+      if (j < bp.n_hi) {
+        const uint32_t t = bin ^ (bp.himasks[j] & 0xFFFFFFu);
+        const int a0 = bp.cls_off[t];
+        cnt = (uint32_t)(bp.cls_off[t + 1] - a0);
+        sh.start[j] = (uint32_t)a0;
+      }
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) sh.wtot[warp] = incl;
+      __syncthreads();
+      uint32_t before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kBinWarps; ++w) {
+        const uint32_t v = sh.wtot[w];
+        if (w < warp) before += v;
+        total += v;
+      }
+      if (j < bp.n_hi) sh.pre[j] = carry + before + incl - cnt;
+      carry += total;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      sh.pre[bp.n_hi] = carry;
+      sh.b0 = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {  // visits and pairs by bin distance
+      uint32_t pb = 0, prev = 0;
+      sh.PB[0] = 0; sh.R[0] = 0;
+      for (int d = 0; d <= bp.hA; ++d) {
+        const uint32_t r = sh.pre[bp.cum_hi[d]];
+        pb += (r - prev) * (uint32_t)bp.nm[d];
+        sh.R[d + 1] = r; sh.PB[d + 1] = pb;
+        prev = r;
+      }
+    }
+    // the bin's buckets in one pass when its slice fits the staging buffer, else in runs of buckets; a single bucket
+    // larger than the buffer is streamed from global memory
+    for (;;) {
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t b0 = sh.b0, e0 = sh.off[b0];
+        const uint32_t gs = (e0 >> 5) & ~1u;  // even group: 16-byte aligned source for any stride that is a multiple of 2 words
+        auto groups = [&](uint32_t e1) { return e1 > e0 ? ((e1 - 1u) >> 5) - gs + 1u : 0u; };
+        uint32_t b1 = 256;
+        if (groups(sh.off[256]) > (uint32_t)kSliceGroups) {
+          b1 = b0 + 1;
+          while (b1 < 256 && groups(sh.off[b1 + 1]) <= (uint32_t)kSliceGroups) ++b1;
+        }
+        const uint32_t ng = groups(sh.off[b1]);
+        sh.b1 = b1; sh.g_base = gs;
+        sh.glob = ng > (uint32_t)kSliceGroups ? 1u : 0u;
+        const uint32_t bytes = sh.glob ? 0u : ((ng * STRIDE * 4u + 15u) & ~15u);
+        sh.bytes = bytes;
+        if (bytes) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&sh.mbar)), "r"(bytes) : "memory");
+          const uint8_t *src = reinterpret_cast<const uint8_t *>(bp.planes + (size_t)gs * STRIDE);
+          for (uint32_t o = 0; o < bytes; o += 32768u) {
+            const uint32_t nb = min(32768u, bytes - o);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr(smem_raw + o)), "l"(src + o), "r"(nb), "r"(smem_addr(&sh.mbar)) : "memory");
+          }
+        }
+      }
+      __syncthreads();
+      const uint32_t b0 = sh.b0, b1 = sh.b1, g_base = sh.g_base;
+      const bool glob = sh.glob != 0;
+      if (sh.bytes) {  // wait for the slice
+        uint32_t done = 0;
+        while (!done) {
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                       : "=r"(done) : "r"(smem_addr(&sh.mbar)), "r"(phase) : "memory");
+        }
+        phase ^= 1u;
+      }
+      const uint32_t n_pairs = sh.PB[bp.hA + 1];
+      for (uint32_t p0 = (uint32_t)warp * 32u; p0 < n_pairs; p0 += kBinThreads) {
+        const uint32_t p = p0 + lane;
+        uint32_t lo = 0, hi = 0, gid = 0, probe = 0;
+        int budget = -1;
+        if (p < n_pairs) {
+          int d = 0;
+          while (p >= sh.PB[d + 1]) ++d;
+          const uint32_t qd = p - sh.PB[d], nmd = (uint32_t)bp.nm[d];
+          const uint32_t vq = qd / nmd, s = qd - vq * nmd;
+          const uint32_t v = sh.R[d] + vq;
+          int jl = d ? bp.cum_hi[d - 1] : 0, jh = bp.cum_hi[d];
+          while (jh - jl > 1) {
+            const int mid = (jl + jh) >> 1;
+            if (sh.pre[mid] <= v) jl = mid; else jh = mid;
+          }
+          const uint2 rec = bp.sg[sh.start[jl] + (v - sh.pre[jl])];
+          const uint32_t lm = sh.lom[s];
+          const uint32_t bl = (rec.x >> 24) ^ (lm & 0xFFu);
+          if (bl >= b0 && bl < b1) {
+            lo = sh.off[bl]; hi = sh.off[bl + 1];
+            budget = bp.k - d - (int)(lm >> 8);
+            gid = rec.y; probe = rec.x & 0xFFFFFFu;
+          }
+        }
+        compares += hi - lo;
+        LaneProbe<NB> lp;
+        lp.set(probe, budget);
+        if (glob) stream_groups<NB, STRIDE, false, false>(bp.planes + (size_t)g_base * STRIDE, g_base, lo, hi, lp, gid, probe, bp.hs, q, qn, lane, bp.canon, nullptr, -1);
+        else stream_groups<NB, STRIDE, false, true>(slice, g_base, lo, hi, lp, gid, probe, bp.hs, q, qn, lane, bp.canon, nullptr, -1);
+      }
+      if (b1 >= 256) break;
+      __syncthreads();
+      if (tid == 0) sh.b0 = b1;
+    }
+  }
+  drain_queue<false>(bp.hs, q, qn, lane, bp.canon, nullptr, -1);
+  for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
+  if (lane == 0 && compares) atomicAdd(bp.n_compares, compares);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// part two: (guide, seed) pairs of index B, counting-sorted by bucket
+struct PairParams {
+  const uint32_t *planes, *off, *other, *canon;
+  const uint4 *recs;   // x = bucket, y = probe | budget << 24, z = guide index
+  long long n_pairs;
+  int lo_d;
+  HitSink hs;
+  unsigned long long *n_compares;
+  unsigned long long *next_item;
+};
+
+// one thread per (guide, seed): the bucket the pair lands in
+__device__ __forceinline__ void b_pair(const uint64_t *guides, const uint32_t *masks, int n_seeds, int proto_shift, uint64_t proto_mask, int b_bits,
+                                       int k, long long idx, uint32_t *kk, uint32_t *pb, uint32_t *gid) {
+  const long long g = idx / n_seeds;
+  const int j = (int)(idx - g * n_seeds);
+  const uint64_t proto = (guides[g] >> proto_shift) & proto_mask;
+  const uint32_t m = masks[j];
+  *kk = (uint32_t)(proto & ((1ull << b_bits) - 1ull)) ^ (m & 0xFFFFFFu);
+  *pb = (uint32_t)(proto >> b_bits) | ((uint32_t)(k - (int)(m >> 24)) << 24);
+  *gid = (uint32_t)g;
+}
+
+__global__ void k_bpairs_hist(const uint64_t *__restrict__ guides, long long n_pairs, const uint32_t *__restrict__ masks, int n_seeds,
+                              int proto_shift, uint64_t proto_mask, int b_bits, int k, unsigned int *__restrict__ cnt) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n_pairs) return;
+  uint32_t kk, pb, gid;
+  b_pair(guides, masks, n_seeds, proto_shift, proto_mask, b_bits, k, idx, &kk, &pb, &gid);
+  atomicAdd(cnt + kk, 1u);
+}
+
+__global__ void k_bpairs_scatter(const uint64_t *__restrict__ guides, long long n_pairs, const uint32_t *__restrict__ masks, int n_seeds,
+                                 int proto_shift, uint64_t proto_mask, int b_bits, int k, const unsigned int *__restrict__ start,
+                                 unsigned int *__restrict__ cursor, uint4 *__restrict__ recs) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n_pairs) return;
+  uint32_t kk, pb, gid;
+  b_pair(guides, masks, n_seeds, proto_shift, proto_mask, b_bits, k, idx, &kk, &pb, &gid);
+  recs[start[kk] + atomicAdd(cursor + kk, 1u)] = make_uint4(kk, pb, gid, 0u);
+}
+
+constexpr int kPairThreads = 256;
+constexpr int kPairWarps = kPairThreads / 32;
+
+template <int NB>
+__global__ void __launch_bounds__(kPairThreads, 3) k_pair_scan(PairParams pp) {
+  constexpr int STRIDE = (2 * NB + 3) & ~3;
+  __shared__ uint4 s_q[kPairWarps][kQCap];
+  __shared__ unsigned int s_qn[kPairWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4 *q = s_q[warp];
+  unsigned int *qn = &s_qn[warp];
+  if (lane == 0) *qn = 0;
+  __syncwarp();
+  unsigned long long compares = 0;
+  const long long n_items = (pp.n_pairs + 31) / 32;
+  for (;;) {  // items are claimed in bucket order: the whole grid walks the index front to back
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(pp.next_item, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if ((long long)item >= n_items) break;
+    const long long pi = (long long)item * 32 + lane;
+    uint32_t lo = 0, hi = 0, gid = 0, probe = 0;
+    int budget = -1;
+    if (pi < pp.n_pairs) {
+      const uint4 r = pp.recs[pi];
+      lo = pp.off[r.x]; hi = pp.off[r.x + 1];
+      probe = r.y & 0xFFFFFFu; budget = (int)(r.y >> 24); gid = r.z;
+    }
+    compares += hi - lo;
+    LaneProbe<NB> lp;
+    lp.set(probe, budget);
+    stream_groups<NB, STRIDE, true, false>(pp.planes, 0u, lo, hi, lp, gid, probe, pp.hs, q, qn, lane, pp.canon, pp.other, pp.lo_d);
+  }
+  drain_queue<true>(pp.hs, q, qn, lane, pp.canon, pp.other, pp.lo_d);
+  for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
+  if (lane == 0 && compares) atomicAdd(pp.n_compares, compares);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-call set-up: guides listed by the bin of their key (part one), pairs sorted by bucket (part two)
+__global__ void k_bin_guide_hist(const uint64_t *__restrict__ guides, int64_t n, int proto_shift, uint64_t proto_mask, int b_bits,
+                                 unsigned int *__restrict__ cnt) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const uint64_t proto = (guides[g] >> proto_shift) & proto_mask;
+  atomicAdd(cnt + ((uint32_t)(proto >> b_bits) >> 8), 1u);
+}
+
+__global__ void k_bin_guide_scatter(const uint64_t *__restrict__ guides, int64_t n, int proto_shift, uint64_t proto_mask, int b_bits,
+                                    const int *__restrict__ cls_off, unsigned int *__restrict__ cursor, uint2 *__restrict__ sg) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const uint64_t proto = (guides[g] >> proto_shift) & proto_mask;
+  const uint32_t ka = (uint32_t)(proto >> b_bits), kb = (uint32_t)(proto & ((1ull << b_bits) - 1ull));
+  const uint32_t cls = ka >> 8;
+  sg[(uint32_t)cls_off[cls] + atomicAdd(cursor + cls, 1u)] = make_uint2(kb | ((ka & 0xFFu) << 24), (uint32_t)g);
+}
+
+struct BinScanPlan {
+  BinParams bp;
+  PairParams pp;
+  bool part_two;
+  int nb_a, nb_b;  // other bases of the two halves
+  size_t smem_a;
+};
+
+static bool bin_scan_supported(const Database &db, int hA, int64_t G) {
+  if (!db.A.d_planes || !db.B.d_planes || db.A.n_planes != 18) return false;
+  if (db.B.n_planes != 20 && db.B.n_planes != 22) return false;
+  if (hA > 3 || db.A.cum_hi[hA] > kNbrCap) return false;
+  return G < (1ll << 28);
+}
+
+// Launch the set-up kernels (no host synchronisation) and fill the plan.
+static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, BinScanPlan *pl, int *launches) {
+  Database &db = ctx->db;
+  cudaStream_t st = ctx->stream;
+  const int64_t G = sp.n_guides;
+  const uint32_t n_bins = 1u << (2 * (db.A.key_bases - 4));
+  const uint32_t n_keys_b = 1u << (2 * db.B.key_bases);
+  const long long n_pairs = (long long)G * nB;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_cls_cnt = 0;                                        // u32[n_bins + 1]  (zeroed)
+  const size_t o_cls_cur = o_cls_cnt + up(((size_t)n_bins + 1) * 4);  // u32[n_bins]      (zeroed)
+  const size_t o_b_cnt = o_cls_cur + up((size_t)n_bins * 4);         // u32[n_keys_b + 1] (zeroed)
+  const size_t o_b_cur = o_b_cnt + up(((size_t)n_keys_b + 1) * 4);    // u32[n_keys_b]     (zeroed)
+  const size_t o_ctr = o_b_cur + up((size_t)n_keys_b * 4);           // counters          (zeroed)
+  const size_t zero_bytes = o_ctr + 256;
+  const size_t o_cls_off = zero_bytes;                               // int[n_bins + 1]
+  const size_t o_b_start = o_cls_off + up(((size_t)n_bins + 1) * 4);  // u32[n_keys_b + 1]
+  const size_t o_sg = o_b_start + up(((size_t)n_keys_b + 1) * 4);     // uint2[G]
+  const size_t o_recs = o_sg + up((size_t)(G > 0 ? G : 1) * 8);       // uint4[n_pairs]
+  const size_t total = o_recs + up((size_t)(n_pairs > 0 ? n_pairs : 1) * 16);
+  FF_TRY(ctx->cell_ws.reserve(total));
+  uint8_t *w = ctx->cell_ws.as<uint8_t>();
+  FF_CUDA(cudaMemsetAsync(w, 0, zero_bytes, st));
+  unsigned int *cls_cnt = (unsigned int *)(w + o_cls_cnt), *cls_cur = (unsigned int *)(w + o_cls_cur);
+  unsigned int *b_cnt = (unsigned int *)(w + o_b_cnt), *b_cur = (unsigned int *)(w + o_b_cur);
+  int *cls_off = (int *)(w + o_cls_off);
+  unsigned int *b_start = (unsigned int *)(w + o_b_start);
+  uint2 *sg = (uint2 *)(w + o_sg);
+  uint4 *recs = (uint4 *)(w + o_recs);
+
+  size_t tmp = 0, tmp2 = 0;
+  FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cls_cnt, cls_off, (int)(n_bins + 1), st));
+  FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, b_cnt, b_start, (int)(n_keys_b + 1), st));
+  FF_TRY(ctx->cub_tmp.reserve(std::max(tmp, tmp2)));
+  if (G > 0) {
+    k_bin_guide_hist<<<blocks_for(G, 256), 256, 0, st>>>(sp.guides, G, sp.proto_shift, sp.proto_mask, sp.b_bits, cls_cnt);
+    FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, cls_cnt, cls_off, (int)(n_bins + 1), st));
+    k_bin_guide_scatter<<<blocks_for(G, 256), 256, 0, st>>>(sp.guides, G, sp.proto_shift, sp.proto_mask, sp.b_bits, cls_off, cls_cur, sg);
+    *launches += 3;
+  }
+  if (n_pairs > 0) {
+    k_bpairs_hist<<<blocks_for(n_pairs, 256), 256, 0, st>>>(sp.guides, n_pairs, db.B.d_masks, nB, sp.proto_shift, sp.proto_mask, sp.b_bits, sp.k, b_cnt);
+    FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp2, b_cnt, b_start, (int)(n_keys_b + 1), st));
+    k_bpairs_scatter<<<blocks_for(n_pairs, 256), 256, 0, st>>>(sp.guides, n_pairs, db.B.d_masks, nB, sp.proto_shift, sp.proto_mask, sp.b_bits, sp.k,
+                                                               b_start, b_cur, recs);
+    *launches += 3;
+  }
+  FF_CUDA(cudaGetLastError());
+
+  BinParams &bp = pl->bp;
+  bp.planes = db.A.d_planes; bp.off = db.A.d_off; bp.canon = db.A.d_canon; bp.himasks = db.A.d_himasks; bp.lomasks = db.A.d_lomasks;
+  bp.n_hi = db.A.cum_hi[hA];
+  for (int d = 0; d < 5; ++d) bp.cum_hi[d] = db.A.cum_hi[std::min(d, hA)];
+  for (int d = 0; d < 4; ++d) bp.nm[d] = d <= hA ? db.A.cum_lo[std::min(hA - d, 4)] : 0;
+  bp.hA = hA; bp.k = sp.k; bp.n_bins = n_bins; bp.sg = sg; bp.cls_off = cls_off;
+  bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits};
+  bp.n_compares = sp.n_compares;
+  bp.next_bin = (unsigned int *)(w + o_ctr);
+  PairParams &pp = pl->pp;
+  pp.planes = db.B.d_planes; pp.off = db.B.d_off; pp.other = db.B.d_other; pp.canon = db.B.d_canon; pp.recs = recs;
+  pp.n_pairs = n_pairs; pp.lo_d = hA; pp.hs = bp.hs; pp.n_compares = sp.n_compares;
+  pp.next_item = (unsigned long long *)(w + o_ctr + 64);
+  pl->part_two = n_pairs > 0;
+  pl->nb_a = db.A.n_planes / 2; pl->nb_b = db.B.n_planes / 2;
+  pl->smem_a = (size_t)kSliceGroups * db.A.n_planes * 4 + sizeof(BinShared);
+  return FF_OK;
+}
+
+// (re)launch the two scan kernels of a prepared plan; hit buffer and counters come from `sp`
+static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, int *launches) {
+  cudaStream_t st = ctx->stream;
+  pl->bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits};
+  pl->pp.hs = pl->bp.hs;
+  FF_CUDA(cudaMemsetAsync(pl->bp.next_bin, 0, 128, st));
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    FF_CUDA(cudaFuncSetAttribute(k_bin_scan<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_a));
+    attr_set[ctx->device & 63] = true;
+  }
+  k_bin_scan<9><<<ctx->sm_count * 2, kBinThreads, pl->smem_a, st>>>(pl->bp);
+  (*launches)++;
+  if (pl->part_two) {
+    const int grid = ctx->sm_count * 3;
+    if (pl->nb_b == 11) k_pair_scan<11><<<grid, kPairThreads, 0, st>>>(pl->pp);
+    else k_pair_scan<10><<<grid, kPairThreads, 0, st>>>(pl->pp);
+    (*launches)++;
+  }
+  FF_CUDA(cudaGetLastError());
+  return FF_OK;
+}

@@ -70,6 +70,16 @@ struct SeedIndex {
   uint32_t *d_gmasks = nullptr;    // [4^w]
   int goff[kCells + 1] = {0};      // first mask of every group
   int gcum[kCells][16] = {{0}};    // gcum[g][h] = # masks of group g at distance <= h
+  // bit-sliced copy of `other` for the bin scan (ff_binscan.inl): entries in groups of 32, one 32-bit word per bit plane
+  // (bit e of plane word j = bit j of other[32 g + e]); plane_stride words per group
+  uint32_t *d_planes = nullptr;
+  int n_planes = 0, plane_stride = 0;
+  uint64_t n_groups = 0;
+  // masks over the first key_bases - 4 key bases (the "bin" of a key), sorted by distance; the masks over the last four
+  // key bases live in constant memory (the same 256 for every key width)
+  uint32_t *d_himasks = nullptr;   // [4^(key_bases-4)] mask | distance << 24
+  uint32_t *d_lomasks = nullptr;   // [256] mask | distance << 8
+  int cum_hi[16] = {0}, cum_lo[16] = {0};
   void release();
 };
 

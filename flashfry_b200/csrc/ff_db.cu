@@ -47,6 +47,7 @@ int pack_from_index(int idx, Pack *o) {
 
 void SeedIndex::release() {
   cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks); cudaFree(d_masks_w1); cudaFree(d_gmasks);
+  cudaFree(d_planes); cudaFree(d_himasks); cudaFree(d_lomasks);
   *this = SeedIndex();
 }
 
@@ -155,9 +156,24 @@ static const MaskTables &mask_tables(int key_bases) {
 
 static unsigned int nblk(uint64_t n) { return (unsigned int)((n + 255) / 256); }
 
+// Bit-slice `other`: one warp per group of 32 entries, plane word j = ballot of bit j.  Entries past n read the 0xFF
+// padding of d_other; the scan rejects them by their index.
+__global__ void k_slice_planes(const uint32_t *__restrict__ other, uint64_t n_groups, int n_planes, int stride, uint32_t *__restrict__ planes) {
+  const uint64_t g = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  const uint32_t v = other[g * 32 + lane];
+  uint32_t mine = 0;
+  for (int j = 0; j < n_planes; ++j) {
+    const uint32_t w = __ballot_sync(0xffffffffu, (v >> j) & 1u);
+    if (lane == j) mine = w;
+  }
+  if (lane < stride) planes[g * stride + lane] = lane < n_planes ? mine : 0u;
+}
+
 // Build one half of the seed index from per-target keys.  identity: entries stay in database order (keys must already be sorted).
-static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, const uint32_t *d_key, const uint32_t *d_other_src,
-                            const uint32_t *d_iota, uint64_t n, bool identity) {
+static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, int other_bases, bool wide_planes, const uint32_t *d_key,
+                            const uint32_t *d_other_src, const uint32_t *d_iota, uint64_t n, bool identity) {
   cudaStream_t st = ctx->stream;
   ix->key_bases = key_bases;
   const uint32_t n_keys = 1u << (2 * key_bases);
@@ -192,6 +208,25 @@ static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, const uin
   FF_CUDA(cudaMemcpyAsync(ix->d_masks_w1, masks_w1.data(), masks_w1.size() * 4, cudaMemcpyHostToDevice, st));
   FF_CUDA(cudaMalloc(&ix->d_gmasks, gmasks.size() * 4));
   FF_CUDA(cudaMemcpyAsync(ix->d_gmasks, gmasks.data(), gmasks.size() * 4, cudaMemcpyHostToDevice, st));
+  // bin scan (ff_binscan.inl): bit-sliced `other` + the masks of a key split into its bin (first key_bases - 4 bases)
+  // and its last four bases.  Built for the splits the compare circuits exist for (9, 10 or 11 other bases).
+  if (key_bases >= 6 && other_bases >= 9 && other_bases <= 11) {
+    ix->n_planes = 2 * other_bases;
+    ix->plane_stride = wide_planes ? (ix->n_planes + 3) & ~3 : ix->n_planes;
+    ix->n_groups = (n + 31) / 32 + 1;
+    FF_CUDA(cudaMalloc(&ix->d_planes, ix->n_groups * ix->plane_stride * 4 + 64));
+    k_slice_planes<<<nblk(ix->n_groups * 32), 256, 0, st>>>(ix->d_other, ix->n_groups, ix->n_planes, ix->plane_stride, ix->d_planes);
+    std::vector<uint32_t> hi, lo;
+    make_masks(key_bases - 4, &hi, ix->cum_hi);
+    make_masks(4, &lo, ix->cum_lo);
+    for (uint32_t &m : lo) m = (m & 0xFFu) | ((m >> 24) << 8);
+    FF_CUDA(cudaMalloc(&ix->d_himasks, hi.size() * 4));
+    FF_CUDA(cudaMemcpyAsync(ix->d_himasks, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMalloc(&ix->d_lomasks, lo.size() * 4));
+    FF_CUDA(cudaMemcpyAsync(ix->d_lomasks, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaStreamSynchronize(st));  // hi / lo go out of scope
+    ctx->db.device_bytes += ix->n_groups * ix->plane_stride * 4 + hi.size() * 4 + lo.size() * 4;
+  }
   FF_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_sorted);
   FF_CUDA(cudaGetLastError());
@@ -232,8 +267,8 @@ int db_build_index(ff_ctx *ctx) {
   FF_CUDA(cudaMalloc(&d_kb, (n + 1) * 4));
   FF_CUDA(cudaMalloc(&d_iota, (n + 1) * 4));
   if (n) k_split_proto<<<nblk(n), 256, 0, st>>>(db.d_targets, n, db.proto_shift, 2 * b, (1ull << (2 * P)) - 1ull, d_ka, d_kb, d_iota);
-  int rc = build_seed_index(ctx, &db.A, a, d_ka, d_kb, d_iota, n, /*identity=*/sorted_db);
-  if (rc == FF_OK) rc = build_seed_index(ctx, &db.B, b, d_kb, d_ka, d_iota, n, /*identity=*/false);
+  int rc = build_seed_index(ctx, &db.A, a, b, /*wide_planes=*/false, d_ka, d_kb, d_iota, n, /*identity=*/sorted_db);
+  if (rc == FF_OK) rc = build_seed_index(ctx, &db.B, b, a, /*wide_planes=*/true, d_kb, d_ka, d_iota, n, /*identity=*/false);
   cudaFree(d_ka); cudaFree(d_kb); cudaFree(d_iota);
   FF_TRY(rc);
 

@@ -487,6 +487,7 @@ static void plan_passes(const Database &db, int k, int *hA_out, int *nA, int *nB
 }
 
 #include "ff_cellscan.inl"
+#include "ff_binscan.inl"
 
 static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
                           bool want_positions, int slot, DeviceResult *res) {
@@ -562,8 +563,13 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     cell_major = reuse >= 1.0 && (double)db.n_targets * 8.0 > 96e6;  // measured: ahead from 12 500 guides on 3e8 targets
     if (const char *e = getenv("FF_CELL_SCAN")) cell_major = atoi(e) != 0 && G > 0;
   }
+  bool bin_major = cell_major && bin_scan_supported(db, hA, G);
+  if (const char *e = getenv("FF_CELL_SCAN")) bin_major = bin_major && atoi(e) != 1;
+  if (bin_major) cell_major = false;
   CellParams cp;
+  BinScanPlan bpl;
   if (cell_major) FF_TRY(cell_scan_prepare(ctx, sp, hA, k_eff - hA - 1, &cp, &launches));
+  if (bin_major) FF_TRY(bin_scan_prepare(ctx, sp, hA, nB, &bpl, &launches));
   FF_CUDA(cudaEventRecord(ctx->ev[1], st));
   for (;;) {
     FF_TRY(ctx->hit_keys.reserve(ctx->hit_cap * 8));
@@ -571,7 +577,10 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     sp.hits = ctx->hit_keys.as<uint64_t>(); sp.hit_cap = ctx->hit_cap;
     FF_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
     if (G > 0) {
-      if (cell_major) {
+      if (bin_major) {
+        FF_TRY(bin_scan_launch(ctx, &bpl, sp, &launches));
+        launches--;
+      } else if (cell_major) {
         cp.sp = sp;
         FF_CUDA(cudaMemsetAsync(cp.next_item, 0, 16, st));
         k_cell_scan<0><<<max_grid, kScanThreads, 0, st>>>(cp);
