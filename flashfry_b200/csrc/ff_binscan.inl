@@ -104,15 +104,20 @@ struct HitSink {
   int tbits;
 };
 
-constexpr int kQCap = 64;  // queue entries per warp; drained at >= 32, and an iteration adds at most 32
+// All shared memory of the two kernels is addressed as byte offsets into this one array: a generic pointer to shared
+// memory costs an S2R + LEA (the shared window base) at every use inside the group loop.
+extern __shared__ __align__(128) uint8_t ff_smem[];
 
-// entries: x = hit word (range-checked), y = group, z = guide index, w = probe (part two: for the exact d1 > hA test)
+constexpr int kQCap = 64;  // hit-queue entries per warp; drained at >= 32, and one iteration adds at most 32
+
+// Queue entries (uint4): x = hit word (already cut to the bucket's range), y = group, z = guide index, w = probe (part
+// two: for the exact d1 > hA test).  The number of queued entries lives in a warp-uniform register.
 template <bool PASS_B>
-__device__ __forceinline__ void drain_queue(const HitSink &hs, uint4 *q, unsigned int *qn, int lane, const uint32_t *__restrict__ canon,
+__device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, uint32_t n, int lane, const uint32_t *__restrict__ canon,
                                             const uint32_t *__restrict__ other, int lo_d) {
   __syncwarp();
-  const unsigned int n = *qn;
-  for (unsigned int i0 = 0; i0 < n; i0 += 32) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(ff_smem + q_off);
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
     uint4 e = make_uint4(0u, 0u, 0u, 0u);
     if (i0 + lane < n) e = q[i0 + lane];
     uint32_t vm = e.x;
@@ -147,61 +152,100 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint4 *q, unsigne
     }
   }
   __syncwarp();
-  if (lane == 0) *qn = 0;
-  __syncwarp();
 }
 
-// Stream the groups of this lane's bucket [lo, hi) (empty for idle lanes).  `base` points at group `g_base`; the loop
-// is warp-uniform (longest bucket of the warp), lanes past their own bucket re-read its last group and drop the result.
+// Stream the groups of this lane's bucket [lo, hi) (empty for idle lanes).  SMEM: group `g_base` sits at byte offset
+// `base_off` of ff_smem; else at gbase[0].  The loop is warp-uniform (longest bucket of the warp); lanes past their own
+// bucket load nothing and drop their result.
 template <int NB, int STRIDE, bool PASS_B, bool SMEM>
-__device__ __forceinline__ void stream_groups(const uint32_t *base, uint32_t g_base, uint32_t lo, uint32_t hi, const LaneProbe<NB> &lp,
-                                              uint32_t gid, uint32_t probe, const HitSink &hs, uint4 *q, unsigned int *qn, int lane,
-                                              const uint32_t *canon, const uint32_t *other, int lo_d) {
+__device__ __forceinline__ void stream_groups(uint32_t base_off, const uint32_t *gbase, uint32_t g_base, uint32_t lo, uint32_t hi,
+                                              const LaneProbe<NB> &lp, uint32_t gid, uint32_t probe, const HitSink &hs, uint32_t q_off,
+                                              uint32_t &qcount, int lane, const uint32_t *canon, const uint32_t *other, int lo_d) {
   const int n = hi > lo ? (int)(((hi - 1u) >> 5) - (lo >> 5)) : -1;  // index of the lane's last iteration
   const int T = __reduce_max_sync(0xffffffffu, n);
-  const uint32_t g0 = n >= 0 ? (lo >> 5) : g_base;
+  const uint32_t g0 = lo >> 5;
+  uint32_t soff = base_off + (g0 - g_base) * (uint32_t)(STRIDE * 4);
+  const uint32_t *pg = SMEM ? nullptr : gbase + (size_t)(n >= 0 ? g0 - g_base : 0u) * STRIDE;
+  uint32_t w[2 * NB];
+#pragma unroll
+  for (int j = 0; j < 2 * NB; ++j) w[j] = 0u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   for (int it = 0; it <= T; ++it) {
-    const uint32_t g = g0 + (uint32_t)min(it, max(n, 0));
-    const uint32_t *pg = base + (size_t)(g - g_base) * STRIDE;
-    uint32_t w[2 * NB];
-    if (STRIDE % 4 == 0) {
+    if (it <= n) {  // lanes past their bucket keep the old words: no loads, no bank conflicts
+      if (SMEM) {
+        if (STRIDE % 4 == 0) {
 #pragma unroll
-      for (int j = 0; j < (2 * NB + 3) / 4; ++j) {
-        const uint4 v = SMEM ? *reinterpret_cast<const uint4 *>(pg + 4 * j) : __ldg(reinterpret_cast<const uint4 *>(pg + 4 * j));
-        w[4 * j] = v.x; w[4 * j + 1] = v.y;
-        if (4 * j + 2 < 2 * NB) { w[4 * j + 2] = v.z; w[4 * j + 3] = v.w; }
-      }
-    } else {
+          for (int j = 0; j < (2 * NB + 3) / 4; ++j) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(ff_smem + soff + 16 * j);
+            w[4 * j] = v.x; w[4 * j + 1] = v.y;
+            if (4 * j + 2 < 2 * NB) { w[4 * j + 2] = v.z; w[4 * j + 3] = v.w; }
+          }
+        } else {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const uint2 v = SMEM ? *reinterpret_cast<const uint2 *>(pg + 2 * j) : __ldg(reinterpret_cast<const uint2 *>(pg + 2 * j));
-        w[2 * j] = v.x; w[2 * j + 1] = v.y;
+          for (int j = 0; j < NB; ++j) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(ff_smem + soff + 8 * j);
+            w[2 * j] = v.x; w[2 * j + 1] = v.y;
+          }
+        }
+        soff += STRIDE * 4;
+      } else {
+        if (it + 2 <= n) {  // long part-two buckets: pull the group after next towards the SM
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pg + 2 * STRIDE));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pg + 2 * STRIDE + STRIDE - 1));
+        }
+        if (STRIDE % 4 == 0) {
+#pragma unroll
+          for (int j = 0; j < (2 * NB + 3) / 4; ++j) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(pg + 4 * j));
+            w[4 * j] = v.x; w[4 * j + 1] = v.y;
+            if (4 * j + 2 < 2 * NB) { w[4 * j + 2] = v.z; w[4 * j + 3] = v.w; }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(pg + 2 * j));
+            w[2 * j] = v.x; w[2 * j + 1] = v.y;
+          }
+        }
+        pg += STRIDE;
       }
     }
     uint32_t hm = lp.match(w);
     if (it > n) hm = 0u;
     if (hm) {  // which of the group's entries belong to the bucket
-      if (g == (lo >> 5)) hm &= 0xFFFFFFFFu << (lo & 31u);
-      if (g == ((hi - 1u) >> 5)) hm &= 0xFFFFFFFFu >> (31u - ((hi - 1u) & 31u));
-      if (hm) q[atomicAdd(qn, 1u)] = make_uint4(hm, g, gid, probe);
+      if (it == 0) hm &= 0xFFFFFFFFu << (lo & 31u);
+      if (it == n) hm &= 0xFFFFFFFFu >> (31u - ((hi - 1u) & 31u));
     }
-    __syncwarp();
-    if (*qn >= 32u) drain_queue<PASS_B>(hs, q, qn, lane, canon, other, lo_d);
+    const uint32_t hb = __ballot_sync(0xffffffffu, hm != 0u);
+    if (hb) {
+      if (hm) *reinterpret_cast<uint4 *>(ff_smem + q_off + 16u * (qcount + (uint32_t)__popc(hb & lt_mask))) = make_uint4(hm, g0 + (uint32_t)it, gid, probe);
+      qcount += (uint32_t)__popc(hb);
+      if (qcount >= 32u) {
+        drain_queue<PASS_B>(hs, q_off, qcount, lane, canon, other, lo_d);
+        qcount = 0;
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // part one: bins of index A through shared memory
-constexpr int kBinThreads = 384;
+#ifndef FF_BIN_THREADS
+#define FF_BIN_THREADS 384
+#endif
+constexpr int kBinThreads = FF_BIN_THREADS;
 constexpr int kBinWarps = kBinThreads / 32;
 constexpr int kNbrCap = 1160;       // bin-part masks within the seed budget (7 bases, distance <= 3: 1156)
-constexpr int kSliceGroups = 832;   // groups of 32 entries a CTA can stage (x 72 B = 58.5 KB; a human-sized bin is ~572)
+constexpr int kSliceGroups = 736;   // groups of 32 entries a CTA can stage (x 72 B = 52 KB; a human-sized bin is ~572)
+constexpr int kPairCap = 1920;      // pairs sorted by bucket at a time (a human-sized bin with 100 000 guides has ~3200)
+constexpr int kVisitCap = 2048;     // (class, guide) visits of a bin listed in shared memory (~1300); more: binary search
 
 struct BinParams {
   const uint32_t *planes, *off, *canon, *himasks, *lomasks;
   int n_hi;            // bin-part masks within the budget
   int cum_hi[5];       // cum_hi[d] = # bin-part masks at distance <= d (d <= hA <= 3)
   int nm[4];           // nm[d] = # last-four-bases masks a guide reached at bin distance d contributes
+  uint32_t rcp[4];     // floor(2^32 / nm[d])
   int hA, k;
   uint32_t n_bins;
   const uint2 *sg;     // guides listed by the bin of their own key: x = probe | (last four key bases) << 24, y = guide index
@@ -215,34 +259,36 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)
 
 struct BinShared {
   unsigned long long mbar;
-  uint32_t bin, b0, b1, glob, g_base, bytes;
+  uint32_t bin, b0, b1, glob, g_base, bytes, use_vis, next_slice;
   uint32_t R[6], PB[6];
   uint32_t wtot[kBinWarps];
-  unsigned int qn[kBinWarps];
   uint32_t off[260];
   uint32_t lom[256];
   uint32_t pre[kNbrCap + 4];
   uint32_t start[kNbrCap + 4];
+  uint32_t vis[kVisitCap];
   uint4 q[kBinWarps][kQCap];
+  // the chunk of pairs being processed, counting-sorted by bucket so that neighbouring lanes stream the same groups
+  uint32_t cnt[256], bstart[260];
+  uint2 rec[kPairCap];      // x = probe | bucket << 24, y = guide index | budget << 28
+  uint16_t rank[kPairCap], perm[kPairCap];
 };
 
 template <int NB>
 __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
   constexpr int STRIDE = 2 * NB;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint32_t *slice = reinterpret_cast<uint32_t *>(smem_raw);
-  BinShared &sh = *reinterpret_cast<BinShared *>(smem_raw + (size_t)kSliceGroups * STRIDE * 4);
+  constexpr uint32_t kShOff = (uint32_t)kSliceGroups * STRIDE * 4;
+  BinShared &sh = *reinterpret_cast<BinShared *>(ff_smem + kShOff);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sh.mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 256) sh.lom[tid] = bp.lomasks[tid];
-  if (lane == 0) sh.qn[warp] = 0;
   uint32_t phase = 0;
   unsigned long long compares = 0;
-  uint4 *q = sh.q[warp];
-  unsigned int *qn = &sh.qn[warp];
+  const uint32_t q_off = kShOff + (uint32_t)offsetof(BinShared, q) + (uint32_t)warp * kQCap * 16u;
+  uint32_t qcount = 0;
   for (;;) {
     __syncthreads();  // the previous bin is finished: its slice and tables may be overwritten
     if (tid == 0) sh.bin = atomicAdd(bp.next_bin, 1u);
@@ -280,12 +326,10 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
       carry += total;
       __syncthreads();
     }
-    if (tid == 0) {
+    if (tid == 0) {  // visits and pairs by bin distance
       sh.pre[bp.n_hi] = carry;
       sh.b0 = 0;
-    }
-    __syncthreads();
-    if (tid == 0) {  // visits and pairs by bin distance
+      sh.use_vis = carry <= (uint32_t)kVisitCap ? 1u : 0u;
       uint32_t pb = 0, prev = 0;
       sh.PB[0] = 0; sh.R[0] = 0;
       for (int d = 0; d <= bp.hA; ++d) {
@@ -295,6 +339,13 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
         prev = r;
       }
     }
+    __syncthreads();
+    const bool use_vis = sh.use_vis != 0;
+    if (use_vis)  // list the visits: the guide (position in sg) of every (class, guide) combination, in class order
+      for (int j = tid; j < bp.n_hi; j += kBinThreads) {
+        const uint32_t p0 = sh.pre[j], c = sh.pre[j + 1] - p0, a0 = sh.start[j];
+        for (uint32_t i = 0; i < c; ++i) sh.vis[p0 + i] = a0 + i;
+      }
     // the bin's buckets in one pass when its slice fits the staging buffer, else in runs of buckets; a single bucket
     // larger than the buffer is streamed from global memory
     for (;;) {
@@ -319,14 +370,106 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
           for (uint32_t o = 0; o < bytes; o += 32768u) {
             const uint32_t nb = min(32768u, bytes - o);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_addr(smem_raw + o)), "l"(src + o), "r"(nb), "r"(smem_addr(&sh.mbar)) : "memory");
+                         ::"r"(smem_addr(ff_smem + o)), "l"(src + o), "r"(nb), "r"(smem_addr(&sh.mbar)) : "memory");
           }
         }
       }
       __syncthreads();
       const uint32_t b0 = sh.b0, b1 = sh.b1, g_base = sh.g_base;
       const bool glob = sh.glob != 0;
-      if (sh.bytes) {  // wait for the slice
+      bool waited = sh.bytes == 0;
+      const uint32_t n_pairs = sh.PB[bp.hA + 1];
+      for (uint32_t c0 = 0; c0 < n_pairs; c0 += kPairCap) {
+        const uint32_t cn = min((uint32_t)kPairCap, n_pairs - c0);
+        if (tid < 256) sh.cnt[tid] = 0;
+        __syncthreads();
+        if (tid == 0) sh.next_slice = 0;  // (every warp has left the previous chunk's claim loop)
+        // enumerate the chunk's pairs; rank every pair inside its bucket
+        for (uint32_t i = tid; i < cn; i += kBinThreads) {
+          const uint32_t p = c0 + i;
+          int d = 0;
+          while (p >= sh.PB[d + 1]) ++d;
+          const uint32_t qd = p - sh.PB[d], nmd = (uint32_t)bp.nm[d];
+          uint32_t vq = __umulhi(qd, bp.rcp[d]), s = qd - vq * nmd;  // rcp rounds down: the quotient is exact or one short
+          if (s >= nmd) { ++vq; s -= nmd; }
+          const uint32_t v = sh.R[d] + vq;
+          uint32_t sidx;
+          if (use_vis) {
+            sidx = sh.vis[v];
+          } else {
+            int jl = d ? bp.cum_hi[d - 1] : 0, jh = bp.cum_hi[d];
+            while (jh - jl > 1) {
+              const int mid = (jl + jh) >> 1;
+              if (sh.pre[mid] <= v) jl = mid; else jh = mid;
+            }
+            sidx = sh.start[jl] + (v - sh.pre[jl]);
+          }
+          const uint2 rec = bp.sg[sidx];
+          const uint32_t lm = sh.lom[s];
+          const uint32_t bl = (rec.x >> 24) ^ (lm & 0xFFu);
+          uint16_t rk = 0xFFFFu;
+          if (bl >= b0 && bl < b1 && sh.off[bl + 1] > sh.off[bl]) {
+            rk = (uint16_t)atomicAdd(&sh.cnt[bl], 1u);
+            const int budget = min(bp.k - d - (int)(lm >> 8), 15);
+            sh.rec[i] = make_uint2((rec.x & 0xFFFFFFu) | (bl << 24), rec.y | ((uint32_t)budget << 28));
+          }
+          sh.rank[i] = rk;
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive prefix over the 256 bucket counts
+          uint32_t c[8], sum = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { c[j] = sh.cnt[lane * 8 + j]; sum += c[j]; }
+          uint32_t incl = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          uint32_t acc = incl - sum;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { sh.bstart[lane * 8 + j] = acc; acc += c[j]; }
+          if (lane == 31) sh.bstart[256] = acc;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < cn; i += kBinThreads) {
+          const uint32_t rk = sh.rank[i];
+          if (rk != 0xFFFFu) sh.perm[sh.bstart[sh.rec[i].x >> 24] + rk] = (uint16_t)i;
+        }
+        if (!waited) {  // the slice has had the whole enumeration to arrive
+          uint32_t done = 0;
+          while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_addr(&sh.mbar)), "r"(phase) : "memory");
+          }
+          phase ^= 1u;
+          waited = true;
+        }
+        __syncthreads();
+        const uint32_t nv = sh.bstart[256];
+        for (;;) {  // warps take 32 sorted pairs at a time
+          uint32_t j0 = 0;
+          if (lane == 0) j0 = atomicAdd(&sh.next_slice, 32u);
+          j0 = __shfl_sync(0xffffffffu, j0, 0);
+          if (j0 >= nv) break;
+          const uint32_t j = j0 + lane;
+          uint32_t lo = 0, hi = 0, gid = 0, probe = 0;
+          int budget = -1;
+          if (j < nv) {
+            const uint2 r = sh.rec[sh.perm[j]];
+            const uint32_t bl = r.x >> 24;
+            lo = sh.off[bl]; hi = sh.off[bl + 1];
+            probe = r.x & 0xFFFFFFu; gid = r.y & 0x0FFFFFFFu; budget = (int)(r.y >> 28);
+          }
+          compares += hi - lo;
+          LaneProbe<NB> lp;
+          lp.set(probe, budget);
+          if (j >= nv) lo = hi = g_base << 5;  // idle lanes: an empty bucket inside the slice
+          if (glob) stream_groups<NB, STRIDE, false, false>(0u, bp.planes + (size_t)g_base * STRIDE, g_base, lo, hi, lp, gid, probe, bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
+          else stream_groups<NB, STRIDE, false, true>(0u, nullptr, g_base, lo, hi, lp, gid, probe, bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
+        }
+      }
+      if (!waited) {  // no pairs at all: still consume the copy before the buffer is reused
         uint32_t done = 0;
         while (!done) {
           asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
@@ -334,43 +477,12 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
         }
         phase ^= 1u;
       }
-      const uint32_t n_pairs = sh.PB[bp.hA + 1];
-      for (uint32_t p0 = (uint32_t)warp * 32u; p0 < n_pairs; p0 += kBinThreads) {
-        const uint32_t p = p0 + lane;
-        uint32_t lo = 0, hi = 0, gid = 0, probe = 0;
-        int budget = -1;
-        if (p < n_pairs) {
-          int d = 0;
-          while (p >= sh.PB[d + 1]) ++d;
-          const uint32_t qd = p - sh.PB[d], nmd = (uint32_t)bp.nm[d];
-          const uint32_t vq = qd / nmd, s = qd - vq * nmd;
-          const uint32_t v = sh.R[d] + vq;
-          int jl = d ? bp.cum_hi[d - 1] : 0, jh = bp.cum_hi[d];
-          while (jh - jl > 1) {
-            const int mid = (jl + jh) >> 1;
-            if (sh.pre[mid] <= v) jl = mid; else jh = mid;
-          }
-          const uint2 rec = bp.sg[sh.start[jl] + (v - sh.pre[jl])];
-          const uint32_t lm = sh.lom[s];
-          const uint32_t bl = (rec.x >> 24) ^ (lm & 0xFFu);
-          if (bl >= b0 && bl < b1) {
-            lo = sh.off[bl]; hi = sh.off[bl + 1];
-            budget = bp.k - d - (int)(lm >> 8);
-            gid = rec.y; probe = rec.x & 0xFFFFFFu;
-          }
-        }
-        compares += hi - lo;
-        LaneProbe<NB> lp;
-        lp.set(probe, budget);
-        if (glob) stream_groups<NB, STRIDE, false, false>(bp.planes + (size_t)g_base * STRIDE, g_base, lo, hi, lp, gid, probe, bp.hs, q, qn, lane, bp.canon, nullptr, -1);
-        else stream_groups<NB, STRIDE, false, true>(slice, g_base, lo, hi, lp, gid, probe, bp.hs, q, qn, lane, bp.canon, nullptr, -1);
-      }
       if (b1 >= 256) break;
       __syncthreads();
       if (tid == 0) sh.b0 = b1;
     }
   }
-  drain_queue<false>(bp.hs, q, qn, lane, bp.canon, nullptr, -1);
+  drain_queue<false>(bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
   for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
   if (lane == 0 && compares) atomicAdd(bp.n_compares, compares);
 }
@@ -424,13 +536,9 @@ constexpr int kPairWarps = kPairThreads / 32;
 template <int NB>
 __global__ void __launch_bounds__(kPairThreads, 3) k_pair_scan(PairParams pp) {
   constexpr int STRIDE = (2 * NB + 3) & ~3;
-  __shared__ uint4 s_q[kPairWarps][kQCap];
-  __shared__ unsigned int s_qn[kPairWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint4 *q = s_q[warp];
-  unsigned int *qn = &s_qn[warp];
-  if (lane == 0) *qn = 0;
-  __syncwarp();
+  const uint32_t q_off = (uint32_t)warp * kQCap * 16u;  // dynamic shared memory: one hit queue per warp
+  uint32_t qcount = 0;
   unsigned long long compares = 0;
   const long long n_items = (pp.n_pairs + 31) / 32;
   for (;;) {  // items are claimed in bucket order: the whole grid walks the index front to back
@@ -449,9 +557,9 @@ __global__ void __launch_bounds__(kPairThreads, 3) k_pair_scan(PairParams pp) {
     compares += hi - lo;
     LaneProbe<NB> lp;
     lp.set(probe, budget);
-    stream_groups<NB, STRIDE, true, false>(pp.planes, 0u, lo, hi, lp, gid, probe, pp.hs, q, qn, lane, pp.canon, pp.other, pp.lo_d);
+    stream_groups<NB, STRIDE, true, false>(0u, pp.planes, 0u, lo, hi, lp, gid, probe, pp.hs, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
   }
-  drain_queue<true>(pp.hs, q, qn, lane, pp.canon, pp.other, pp.lo_d);
+  drain_queue<true>(pp.hs, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
   for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
   if (lane == 0 && compares) atomicAdd(pp.n_compares, compares);
 }
@@ -544,7 +652,10 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, B
   bp.planes = db.A.d_planes; bp.off = db.A.d_off; bp.canon = db.A.d_canon; bp.himasks = db.A.d_himasks; bp.lomasks = db.A.d_lomasks;
   bp.n_hi = db.A.cum_hi[hA];
   for (int d = 0; d < 5; ++d) bp.cum_hi[d] = db.A.cum_hi[std::min(d, hA)];
-  for (int d = 0; d < 4; ++d) bp.nm[d] = d <= hA ? db.A.cum_lo[std::min(hA - d, 4)] : 0;
+  for (int d = 0; d < 4; ++d) {
+    bp.nm[d] = d <= hA ? db.A.cum_lo[std::min(hA - d, 4)] : 1;
+    bp.rcp[d] = bp.nm[d] > 1 ? (uint32_t)(0x100000000ull / (uint64_t)bp.nm[d]) : 0xFFFFFFFFu;
+  }
   bp.hA = hA; bp.k = sp.k; bp.n_bins = n_bins; bp.sg = sg; bp.cls_off = cls_off;
   bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits};
   bp.n_compares = sp.n_compares;
@@ -574,8 +685,9 @@ static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, i
   (*launches)++;
   if (pl->part_two) {
     const int grid = ctx->sm_count * 3;
-    if (pl->nb_b == 11) k_pair_scan<11><<<grid, kPairThreads, 0, st>>>(pl->pp);
-    else k_pair_scan<10><<<grid, kPairThreads, 0, st>>>(pl->pp);
+    const size_t qsm = (size_t)kPairWarps * kQCap * 16;
+    if (pl->nb_b == 11) k_pair_scan<11><<<grid, kPairThreads, qsm, st>>>(pl->pp);
+    else k_pair_scan<10><<<grid, kPairThreads, qsm, st>>>(pl->pp);
     (*launches)++;
   }
   FF_CUDA(cudaGetLastError());
