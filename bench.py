@@ -281,14 +281,14 @@ def run_native(args):
                "hits_per_step": n_hits, "candidate_hits_per_step": cand, "scan_launches_last_step": scan_launches,
                "baseline_note": "vs_baseline = value / 53.7 guides/s (published single-core JVM, 100k guides, hg38, k<=4; BASELINE.md)"}
         # the two scan kernels (guide-major k_seed_scan / cell-major k_cell_scan) must agree on the whole timed batch
-        def _totals(env):
-            os.environ["FF_CELL_SCAN"] = env
+        def _totals(kernel):
+            ctx.set_option("scan_kernel", kernel)
             rr = ctx.discover_device(d_guides.data_ptr(), G, args.k, args.max_ot, 0)
             t = torch.as_tensor(_DevView(rr.d_total_count, G), device=dev).clone()
-            os.environ.pop("FF_CELL_SCAN", None)
+            ctx.set_option("scan_kernel", 0)
             return int(rr.n_hits), t
-        h0, t0_ = _totals("0")
-        h1, t1_ = _totals("1")
+        h0, t0_ = _totals(1)
+        h1, t1_ = _totals(2)
         out["scan_kernels_agree_on_full_batch"] = bool(h0 == h1 == n_hits and torch.equal(t0_, t1_))
         # BASELINE.json configs[4] flavour on the same batch: discover + CFD + Hsu2013 fused on the device
         fs = []
@@ -367,12 +367,12 @@ def cpu_baseline(ctx, guides, args, threads, budget_guides):
     dt = time.perf_counter() - t0
     # the sample doubles as a parity check of the timed GPU path
     ok = True
-    for env in ("0", "1"):  # both scan kernels against the oracle, at the full index size
-        os.environ["FF_CELL_SCAN"] = env
+    for kernel in (1, 2):  # both scan kernels against the oracle, at the full index size
+        ctx.set_option("scan_kernel", kernel)
         got = ctx.discover(sample, args.k, args.max_ot)
         ok = ok and bool((got.row_ptr == ref.row_ptr).all() and (got.targets == ref.targets).all() and (got.mismatches == ref.mismatches).all()
                          and (got.overflowed == ref.overflowed).all())
-    os.environ.pop("FF_CELL_SCAN", None)
+    ctx.set_option("scan_kernel", 0)
     _h, cmax, cspec, hsu = ctx.discover_score(sample[:64], args.k, args.max_ot)
     score_ok = True
     for g in range(min(64, len(sample))):

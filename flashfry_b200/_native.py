@@ -54,7 +54,7 @@ class FFTimings(C.Structure):
 
 
 # every symbol include/flashfry_b200.h declares (tests/test_abi.py checks the list against the header)
-SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_load_database",
+SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_set_option", "ff_load_database",
            "ff_save_image", "ff_load_image", "ff_load_database_arrays", "ff_synth_database", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
            "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_score", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
 
@@ -75,6 +75,7 @@ def lib():
     L.ff_destroy.restype = None
     L.ff_last_error.restype = C.c_char_p
     L.ff_set_stream.argtypes = [vp, vp]
+    L.ff_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     L.ff_load_database.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.ff_save_image.argtypes = [vp, C.c_char_p]
     L.ff_load_image.argtypes = [vp, C.c_char_p]

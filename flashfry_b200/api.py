@@ -89,6 +89,26 @@ class Context:
     def set_stream(self, cuda_stream: int):
         N.check(N.lib().ff_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def set_option(self, key: str, value: int):
+        """ff_set_option: tuning / test knobs of this context (see include/flashfry_b200.h)."""
+        N.check(N.lib().ff_set_option(self._h, key.encode(), int(value)))
+
+    def options(self, **kw):
+        """Context manager: set options for a block, restore the defaults afterwards."""
+        ctx = self
+        defaults = {"scan_kernel": 0, "force_general": 0, "window_cells": 0, "subbatch_min": 20000, "subbatch_c1": 65,
+                    "subbatch_c2": 90, "group_sort": 1, "b_spi": 0, "split_a": 0, "compact_hits": 0}
+
+        class _O:
+            def __enter__(self_o):
+                for k, v in kw.items():
+                    ctx.set_option(k, v)
+
+            def __exit__(self_o, *a):
+                for k in kw:
+                    ctx.set_option(k, defaults[k])
+        return _O()
+
     def load_database(self, db_path: str, header_path: Optional[str] = None):
         N.check(N.lib().ff_load_database(self._h, db_path.encode(), header_path.encode() if header_path else None))
 

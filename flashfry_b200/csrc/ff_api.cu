@@ -125,13 +125,11 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
 
   // Sub-batches of DECREASING size (65 / 25 / 10 %): the D2H of a sub-batch hides behind the scan of the next one, so
   // only the last -- smallest -- copy is exposed, while the large first batches keep the scan's bucket reuse high.
-  int64_t min_batch = 20000;
-  if (const char *e = getenv("FF_SUBBATCH_MIN")) min_batch = std::max<long long>(1, atoll(e));
+  const int64_t min_batch = std::max(1, c->opt.subbatch_min);
   const int nb = want_positions ? 1 : (int)std::min<int64_t>(3, std::max<int64_t>(1, n_guides / min_batch));
   int kCut[4][4] = {{0, 0, 0, 0}, {0, 100, 100, 100}, {0, 60, 100, 100}, {0, 65, 90, 100}};  // cumulative % (A/B on the GPU: 7.5 ms per 100 000 guides; 50/30/20: 7.8 ms)
-  if (const char *e = getenv("FF_SUBBATCH_CUTS")) {  // experiments: "c1,c2" = cumulative % of the first two of three sub-batches
-    int c1 = 0, c2 = 0;
-    if (sscanf(e, "%d,%d", &c1, &c2) == 2 && c1 > 0 && c1 < c2 && c2 < 100) { kCut[3][1] = c1; kCut[3][2] = c2; }
+  if (c->opt.subbatch_c1 > 0 && c->opt.subbatch_c1 < c->opt.subbatch_c2 && c->opt.subbatch_c2 < 100) {
+    kCut[3][1] = c->opt.subbatch_c1; kCut[3][2] = c->opt.subbatch_c2;
   }
 
   HitsOwner *o = owner_get();
@@ -282,6 +280,25 @@ int ff_set_stream(ff_ctx *c, void *cuda_stream) {
   FF_CUDA(cudaStreamSynchronize(c->stream));
   c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
   return FF_OK;
+}
+
+int ff_set_option(ff_ctx *c, const char *key, long long value) {
+  if (!c || !key) { set_error("null argument"); return FF_EINVAL; }
+  struct { const char *name; int *field; long long lo, hi; } table[] = {
+      {"scan_kernel", &c->opt.scan_kernel, 0, 2},       {"force_general", &c->opt.force_general, 0, 1},
+      {"window_cells", &c->opt.window_cells, 0, 64},    {"subbatch_min", &c->opt.subbatch_min, 1, 1 << 30},
+      {"subbatch_c1", &c->opt.subbatch_c1, 1, 98},      {"subbatch_c2", &c->opt.subbatch_c2, 2, 99},
+      {"group_sort", &c->opt.group_sort, 0, 1},         {"b_spi", &c->opt.b_spi, 0, 32},
+      {"split_a", &c->opt.split_a, 0, 12},              {"compact_hits", &c->opt.compact_hits, 0, 1},
+  };
+  for (auto &t : table)
+    if (strcmp(key, t.name) == 0) {
+      if (value < t.lo || value > t.hi) { set_error("option %s: value %lld out of range [%lld, %lld]", key, value, t.lo, t.hi); return FF_EINVAL; }
+      *t.field = (int)value;
+      return FF_OK;
+    }
+  set_error("unknown option %s", key);
+  return FF_EINVAL;
 }
 
 int ff_load_database(ff_ctx *c, const char *db_path, const char *header_path) {

@@ -65,11 +65,6 @@ struct SeedIndex {
   int cum[16] = {0};            // cum[h] = # masks at distance <= h (h = 0..w)
   uint32_t *d_masks_w1 = nullptr;  // the same table over w-1 bases (bulge patterns: one key base is a wildcard)
   int cum_w1[16] = {0};
-  // cell-major scan: the same masks grouped by the value of their first three bases (64 groups = the 64 database-order
-  // cells a seed can land in relative to the guide's own cell), inside a group sorted by distance
-  uint32_t *d_gmasks = nullptr;    // [4^w]
-  int goff[kCells + 1] = {0};      // first mask of every group
-  int gcum[kCells][16] = {{0}};    // gcum[g][h] = # masks of group g at distance <= h
   // bit-sliced copy of `other` for the bin scan (ff_binscan.inl): entries in groups of 32, one 32-bit word per bit plane
   // (bit e of plane word j = bit j of other[32 g + e]); plane_stride words per group
   uint32_t *d_planes = nullptr;
@@ -106,6 +101,19 @@ struct Database {
 
 struct Hits;  // host-side result owner (ff_api.cu)
 
+// Tuning and test knobs, set through ff_set_option (no environment variables are read by the library).
+struct Options {
+  int scan_kernel = 0;     // 0 = choose by batch and database size, 1 = guide-major k_seed_scan, 2 = bin-major k_bin_scan / k_pair_scan
+  int force_general = 0;   // 1 = take the windowed general path even for the mismatch-only search
+  int window_cells = 0;    // > 0: fixed window size (cells) of the general path
+  int subbatch_min = 20000;           // ff_discover cuts a guide set into up to three sub-batches of at least this size
+  int subbatch_c1 = 65, subbatch_c2 = 90;  // cumulative % of the first two of three sub-batches
+  int group_sort = 1;      // 0 = always order hits with the radix sort
+  int b_spi = 0;           // > 0: seeds per work item of the part-two pass of k_seed_scan / k_pattern_scan
+  int split_a = 0;         // > 0: bases in the part-one key of the next database build
+  int compact_hits = 0;    // ff_discover: 1 = ship database indices instead of target longs (ff_hits.target_index)
+};
+
 }  // namespace ff
 
 struct ff_ctx {
@@ -113,6 +121,7 @@ struct ff_ctx {
   int sm_count = 148;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   ff::Database db;
+  ff::Options opt;
 
   // ---- per-call workspaces (grow-only) ----
   ff::DevBuf cub_tmp;
@@ -123,7 +132,7 @@ struct ff_ctx {
   ff::DevBuf scratch_guides;  // H2D staging target for ff_discover
   // windowed / bulge discover: per-guide running totals, the active guide list (two copies), kept keys, scratch
   ff::DevBuf running, active, active2, act_flags, seg_end, kept_keys, kept_sorted, n_sel;
-  ff::DevBuf cell_ws;  // cell-major scan: guide classes, class-ordered guide lists, segment table
+  ff::DevBuf cell_ws;  // bin scan: guides listed by bin, (guide, seed) pairs sorted by bucket, counters
   // results of a discover call; two sets so that the D2H of one guide sub-batch overlaps the scan of the next
   struct OutSlot {
     ff::DevBuf row_ptr, total_count, overflowed, out_targets, out_mm, out_bulge, cfd_max, cfd_spec, hsu;

@@ -46,7 +46,7 @@ int pack_from_index(int idx, Pack *o) {
 }
 
 void SeedIndex::release() {
-  cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks); cudaFree(d_masks_w1); cudaFree(d_gmasks);
+  cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks); cudaFree(d_masks_w1);
   cudaFree(d_planes); cudaFree(d_himasks); cudaFree(d_lomasks);
   *this = SeedIndex();
 }
@@ -119,12 +119,10 @@ static void make_masks(int bases, std::vector<uint32_t> *out, int *cum) {
   }
 }
 
-// Mask tables of one key width: all masks by distance, the same over width - 1 bases (bulge wildcards), and grouped by
-// the first three bases ((group, distance, value) order: `masks` is already in (distance, value) order, so a stable
-// counting sort by group keeps the distance order inside every group).
+// Mask tables of one key width: all masks by distance, and the same over width - 1 bases (bulge wildcards).
 struct MaskTables {
-  std::vector<uint32_t> masks, masks_w1, gmasks;
-  int cum[16], cum_w1[16], goff[kCells + 1], gcum[kCells][16];
+  std::vector<uint32_t> masks, masks_w1;
+  int cum[16], cum_w1[16];
 };
 
 static const MaskTables &mask_tables(int key_bases) {
@@ -136,21 +134,6 @@ static const MaskTables &mask_tables(int key_bases) {
   MaskTables &t = cache[key_bases];
   make_masks(key_bases, &t.masks, t.cum);
   make_masks(key_bases - 1, &t.masks_w1, t.cum_w1);
-  t.gmasks.resize(t.masks.size());
-  const int gshift = 2 * key_bases - 6;
-  std::vector<int> cnt(kCells + 1, 0);
-  for (uint32_t m : t.masks) cnt[((m & 0xFFFFFFu) >> gshift) + 1]++;
-  for (int g = 0; g < kCells; ++g) cnt[g + 1] += cnt[g];
-  for (int g = 0; g <= kCells; ++g) t.goff[g] = cnt[g];
-  std::vector<int> cur(cnt.begin(), cnt.end() - 1);
-  memset(t.gcum, 0, sizeof t.gcum);
-  for (uint32_t m : t.masks) {
-    const int g = (int)((m & 0xFFFFFFu) >> gshift);
-    t.gmasks[cur[g]++] = m;
-    t.gcum[g][std::min(15, (int)(m >> 24))]++;
-  }
-  for (int g = 0; g < kCells; ++g)
-    for (int h = 1; h < 16; ++h) t.gcum[g][h] += t.gcum[g][h - 1];
   return t;
 }
 
@@ -197,17 +180,13 @@ static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, int other
   k_key_offsets<<<nblk((uint64_t)n_keys + 1), 256, 0, st>>>(sorted_keys, n, n_keys, ix->d_off);
   // the mask tables depend on the key width only: built once per process, re-uploaded per database
   const MaskTables &mt = mask_tables(key_bases);
-  const std::vector<uint32_t> &masks = mt.masks, &masks_w1 = mt.masks_w1, &gmasks = mt.gmasks;
+  const std::vector<uint32_t> &masks = mt.masks, &masks_w1 = mt.masks_w1;
   memcpy(ix->cum, mt.cum, sizeof ix->cum);
   memcpy(ix->cum_w1, mt.cum_w1, sizeof ix->cum_w1);
-  memcpy(ix->goff, mt.goff, sizeof ix->goff);
-  memcpy(ix->gcum, mt.gcum, sizeof ix->gcum);
   FF_CUDA(cudaMalloc(&ix->d_masks, masks.size() * 4));
   FF_CUDA(cudaMemcpyAsync(ix->d_masks, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice, st));
   FF_CUDA(cudaMalloc(&ix->d_masks_w1, masks_w1.size() * 4));
   FF_CUDA(cudaMemcpyAsync(ix->d_masks_w1, masks_w1.data(), masks_w1.size() * 4, cudaMemcpyHostToDevice, st));
-  FF_CUDA(cudaMalloc(&ix->d_gmasks, gmasks.size() * 4));
-  FF_CUDA(cudaMemcpyAsync(ix->d_gmasks, gmasks.data(), gmasks.size() * 4, cudaMemcpyHostToDevice, st));
   // bin scan (ff_binscan.inl): bit-sliced `other` + the masks of a key split into its bin (first key_bases - 4 bases)
   // and its last four bases.  Built for the splits the compare circuits exist for (9, 10 or 11 other bases).
   if (key_bases >= 6 && other_bases >= 9 && other_bases <= 11) {
@@ -230,7 +209,7 @@ static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, int other
   FF_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_sorted);
   FF_CUDA(cudaGetLastError());
-  ctx->db.device_bytes += ((size_t)n_keys + 1) * 4 + (n + 64) * 4 + (identity ? 0 : (n + 1) * 4) + 2 * masks.size() * 4 + masks_w1.size() * 4;
+  ctx->db.device_bytes += ((size_t)n_keys + 1) * 4 + (n + 64) * 4 + (identity ? 0 : (n + 1) * 4) + masks.size() * 4 + masks_w1.size() * 4;
   return FF_OK;
 }
 
@@ -258,7 +237,7 @@ int db_build_index(ff_ctx *ctx) {
   db.proto_shift = __builtin_ctzll(db.pack.cmp_mask);
   const int P = db.proto_bases;
   int a = (P + 2) / 2;  // 11 | 9 for the 20-mers, 10 | 9 for the 19-mers
-  if (const char *e = getenv("FF_SPLIT_A")) { const int v = atoi(e); if (v >= 4 && v <= 12 && P - v >= 4 && P - v <= 12) a = v; }
+  { const int v = ctx->opt.split_a; if (v >= 4 && v <= 12 && P - v >= 4 && P - v <= 12) a = v; }
   const int b = P - a;
   db.device_bytes = n * 8;
 

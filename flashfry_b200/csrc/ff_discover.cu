@@ -486,7 +486,6 @@ static void plan_passes(const Database &db, int k, int *hA_out, int *nA, int *nB
   }
 }
 
-#include "ff_cellscan.inl"
 #include "ff_binscan.inl"
 
 static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
@@ -524,7 +523,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   {  // part-two buckets are 4^(a-b) times longer: hand them out in smaller batches
     const double bucket_b = (double)db.n_targets / (double)(1ull << (2 * db.B.key_bases));
     int spi = bucket_b > 2048 ? 1 : bucket_b > 512 ? 4 : bucket_b > 128 ? 8 : 32;
-    if (const char *e = getenv("FF_B_SPI")) spi = std::max(1, atoi(e));
+    if (ctx->opt.b_spi > 0) spi = ctx->opt.b_spi;
     sp.B.seeds_per_item = spi; sp.B.items = (nB + spi - 1) / spi;
   }
   sp.items_per_guide = sp.A.items + sp.B.items;
@@ -556,19 +555,16 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   const long long n_items = G * (long long)sp.items_per_guide;
   const int max_grid = ctx->sm_count * 8;  // 8 CTAs of 8 warps per SM
   const int grid = (int)std::max<long long>(1, std::min<long long>(max_grid, (n_items + kScanWarps - 1) / kScanWarps));
-  // Guide-major or cell-major?  Cell-major pays when buckets are re-read (many guides) and the index does not fit in L2.
-  bool cell_major = false;
+  // Guide-major or bin-major?  Bin-major pays when buckets are re-read (many guides) and the index does not fit in L2.
+  bool bin_major = false;
   {
     const double reuse = (double)G * (double)nA / (double)(1ull << (2 * db.A.key_bases));
-    cell_major = reuse >= 1.0 && (double)db.n_targets * 8.0 > 96e6;  // measured: ahead from 12 500 guides on 3e8 targets
-    if (const char *e = getenv("FF_CELL_SCAN")) cell_major = atoi(e) != 0 && G > 0;
+    bin_major = reuse >= 1.0 && (double)db.n_targets * 8.0 > 96e6;  // measured: ahead from 12 500 guides on 3e8 targets
+    if (ctx->opt.scan_kernel == 1) bin_major = false;
+    if (ctx->opt.scan_kernel == 2) bin_major = G > 0;
+    bin_major = bin_major && bin_scan_supported(db, hA, G);
   }
-  bool bin_major = cell_major && bin_scan_supported(db, hA, G);
-  if (const char *e = getenv("FF_CELL_SCAN")) bin_major = bin_major && atoi(e) != 1;
-  if (bin_major) cell_major = false;
-  CellParams cp;
   BinScanPlan bpl;
-  if (cell_major) FF_TRY(cell_scan_prepare(ctx, sp, hA, k_eff - hA - 1, &cp, &launches));
   if (bin_major) FF_TRY(bin_scan_prepare(ctx, sp, hA, nB, &bpl, &launches));
   FF_CUDA(cudaEventRecord(ctx->ev[1], st));
   for (;;) {
@@ -580,11 +576,6 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
       if (bin_major) {
         FF_TRY(bin_scan_launch(ctx, &bpl, sp, &launches));
         launches--;
-      } else if (cell_major) {
-        cp.sp = sp;
-        FF_CUDA(cudaMemsetAsync(cp.next_item, 0, 16, st));
-        k_cell_scan<0><<<max_grid, kScanThreads, 0, st>>>(cp);
-        if (nB > 0) { k_cell_scan<1><<<max_grid, kScanThreads, 0, st>>>(cp); launches++; }
       } else {
         k_seed_scan<<<grid, kScanThreads, 0, st>>>(sp);
       }
@@ -607,7 +598,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   const uint64_t *sorted = ctx->hit_keys.as<uint64_t>();
   bool grouped = false;  // seg_start already known (counting sort by guide + per-guide warp sorts)
   bool try_grouped = n_cand > 0 && n_cand <= 160 * G;  // short segments on average
-  if (const char *e = getenv("FF_GROUP_SORT")) try_grouped = try_grouped && atoi(e) != 0;
+  try_grouped = try_grouped && ctx->opt.group_sort != 0;
   if (try_grouped) {
     FF_TRY(ctx->running.reserve((Gp + 1) * 8 * 2));  // per-guide counts [G+1] and cursors [G]
     unsigned long long *cnt = ctx->running.as<unsigned long long>(), *cursor = cnt + (Gp + 1);

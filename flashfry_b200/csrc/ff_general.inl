@@ -306,7 +306,7 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
   auto plan_items = [&](int cells) {
     const double run = (double)db.n_targets / (double)(1ull << (2 * b)) * (double)cells / (double)kCells;
     int spi = run > 2048 ? 1 : run > 512 ? 4 : run > 128 ? 8 : 32;
-    if (const char *e = getenv("FF_B_SPI")) spi = std::max(1, atoi(e));
+    if (ctx->opt.b_spi > 0) spi = ctx->opt.b_spi;
     for (int cls = 0; cls < 3; ++cls) { pl.c[cls].spiB = spi; pl.c[cls].itemsB = (pl.c[cls].nB + spi - 1) / spi; }
     pl.item0[0] = 0;
     for (int i = 0; i < pl.n_patterns; ++i) pl.item0[i + 1] = pl.item0[i] + pl.c[pl.cls[i]].itemsA + pl.c[pl.cls[i]].itemsB;
@@ -338,7 +338,7 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
   if (can_window && max_ot > 0 && exp_occ > 0.75 * (double)max_ot)
     cells_per_window = std::max(1, std::min(kCells, (int)std::ceil((double)kCells * 1.25 * (double)max_ot / exp_occ)));
   bool fixed_window = false;
-  if (const char *e = getenv("FF_WINDOW_CELLS")) { const int v = atoi(e); if (v >= 1 && can_window) { cells_per_window = std::min(v, kCells); fixed_window = true; } }
+  { const int v = ctx->opt.window_cells; if (v >= 1 && can_window) { cells_per_window = std::min(v, kCells); fixed_window = true; } }
   const bool windowed = cells_per_window < kCells;
   if (windowed) FF_TRY(db_build_cell_offsets(ctx));
   gp.cell_off = windowed ? db.d_cell_off : nullptr;
@@ -549,7 +549,7 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
     const double exp_occ = (double)db.n_targets * ball_probability(db.proto_bases, std::min(max_mm, db.proto_bases)) * 1.3;
     general = exp_occ > 2.0 * (double)max_ot;
   }
-  if (const char *e = getenv("FF_FORCE_GENERAL")) general = general || atoi(e) != 0;
+  general = general || ctx->opt.force_general != 0;
   if (general) return discover_general(ctx, d_guides, n_guides, max_mm, max_ot, want_positions, bulge_flags, slot, res);
   return discover_plain(ctx, d_guides, n_guides, max_mm, max_ot, want_positions, slot, res);
 }

@@ -56,6 +56,20 @@ int ff_abi_version(void);
  * stream).  Lets a host runtime (torch, JCuda ...) order/time the library's kernels with its own events. */
 int ff_set_stream(ff_ctx *ctx, void *cuda_stream);
 
+/* Tuning and test knobs of one context (the library reads no environment variables).  Keys:
+ *   scan_kernel   0 = chosen from batch and database size (default), 1 = guide-major k_seed_scan, 2 = bin-major
+ *                 k_bin_scan + k_pair_scan (falls back to 1 where the bin scan does not apply)
+ *   force_general 1 = run the mismatch-only search through the windowed general path (early termination of full guides)
+ *   window_cells  > 0 = fixed window size, in 1/64ths of the database, of the general path
+ *   subbatch_min, subbatch_c1, subbatch_c2   how ff_discover cuts a guide set into sub-batches (D2H overlap)
+ *   group_sort    0 = always order candidate hits with the radix sort
+ *   b_spi         > 0 = seeds per work item of the part-two pass of the guide-major kernels
+ *   split_a       > 0 = bases in the part-one key, applied by the next database load
+ *   compact_hits  1 = ff_discover ships database indices (ff_hits.target_index) and leaves ff_hits.targets NULL until
+ *                 ff_hits_resolve fills it from the host mirror of the target array
+ * Unknown key or out-of-range value: FF_EINVAL. */
+int ff_set_option(ff_ctx *ctx, const char *key, long long value);
+
 /* ---- database (replaces BinaryHeader.readHeader + the BGZF seek/inflate of SeekTraverser.fillBlock) ------ */
 /* Reads FlashFry's own on-disk format unchanged: BGZF body (reference/binary/DatabaseWriter.scala:78-97, both
  * block types of reference/binary/blocks/BlockManager.scala:362-442) + text side-car

@@ -37,25 +37,6 @@ def family_ctx(ff, family_db):
     ctx.close()
 
 
-def _env(**kw):
-    class _E:
-        def __enter__(self):
-            self.old = {k: os.environ.get(k) for k in kw}
-            for k, v in kw.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = str(v)
-
-        def __exit__(self, *a):
-            for k, v in self.old.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
-    return _E()
-
-
 def assert_bulge_equal(got, ref):
     helpers.assert_hits_equal(got, ref)
     assert got.bulge is not None and (np.asarray(got.bulge) == np.asarray(ref.bulge)).all(), "bulge codes differ"
@@ -98,9 +79,9 @@ def test_bulge_windows_equal_whole_database_scan(family_ctx, family_db, oracle, 
     targets, seeds = family_db
     pack = oracle.PACK_BY_INDEX[3]
     guides = np.concatenate([seeds[:24], helpers.planted_guides(pack, targets, 9, 24, max_subs=2)])
-    with _env(FF_WINDOW_CELLS=64):
+    with family_ctx.options(window_cells=64):
         whole = family_ctx.discover_bulge(guides, 3, 150, 3)
-    with _env(FF_WINDOW_CELLS=cells):
+    with family_ctx.options(window_cells=cells):
         win = family_ctx.discover_bulge(guides, 3, 150, 3)
     assert_bulge_equal(win, whole)
     ref = oracle.discover_bulge(pack, targets, guides, 3, 150, 3, n_threads=os.cpu_count() or 1)
@@ -116,7 +97,7 @@ def test_windowed_mismatch_search_equals_plain(family_ctx, family_db, oracle, ce
     pack = oracle.PACK_BY_INDEX[3]
     guides = np.concatenate([seeds, helpers.planted_guides(pack, targets, 3, 64, max_subs=4), helpers.random_guides(oracle, pack, 8, 32)])
     plain = family_ctx.discover(guides, 4, max_ot)
-    with _env(FF_FORCE_GENERAL=1, FF_WINDOW_CELLS=cells):
+    with family_ctx.options(force_general=1, window_cells=cells):
         gen = family_ctx.discover(guides, 4, max_ot)
     helpers.assert_hits_equal(gen, plain)
     ref = oracle.discover_soa(pack, 7, targets, oracle.bin_offsets_from_sorted(pack, 7, targets), guides, 4, max_ot)
@@ -173,7 +154,7 @@ def test_bulge_properties_on_a_large_synthetic_index(ff, oracle):
         targets = ctx.copy_targets()
         guides = np.concatenate([helpers.random_guides(oracle, pack, 21, 200), helpers.planted_guides(pack, targets, 22, 56, max_subs=3)])
         got = ctx.discover_bulge(guides, 5, 300, 3)
-        with _env(FF_WINDOW_CELLS=64):
+        with ctx.options(window_cells=64):
             whole = ctx.discover_bulge(guides, 5, 300, 3)
     assert_bulge_equal(got, whole)
     assert np.asarray(got.overflowed).mean() > 0.5  # ~2000 expected hits per guide: windows and early exit are exercised
@@ -199,16 +180,16 @@ def test_bulge_properties_on_a_large_synthetic_index(ff, oracle):
         assert (got.targets[lo:hi] == ref.targets[rlo:rhi]).all() and (got.bulge[lo:hi] == ref.bulge[rlo:rhi]).all()
 
 
-def test_bulge_sub_batches_equal_single_batch(family_ctx, family_db, oracle, monkeypatch):
+def test_bulge_sub_batches_equal_single_batch(family_ctx, family_db, oracle):
     """The host entry point pipelines guide sub-batches (D2H of one behind the scan of the next) in bulge mode too."""
     targets, seeds = family_db
     pack = oracle.PACK_BY_INDEX[3]
     guides = np.concatenate([seeds, helpers.planted_guides(pack, targets, 31, 50, max_subs=3)])
-    monkeypatch.setenv("FF_SUBBATCH_MIN", "1000000")
-    one = family_ctx.discover_bulge(guides, 3, 400, 3)
-    for min_batch in ("40", "20"):
-        monkeypatch.setenv("FF_SUBBATCH_MIN", min_batch)
-        many = family_ctx.discover_bulge(guides, 3, 400, 3)
+    with family_ctx.options(subbatch_min=1000000):
+        one = family_ctx.discover_bulge(guides, 3, 400, 3)
+    for min_batch in (40, 20):
+        with family_ctx.options(subbatch_min=min_batch):
+            many = family_ctx.discover_bulge(guides, 3, 400, 3)
         assert_bulge_equal(many, one)
 
 

@@ -188,13 +188,9 @@ def test_chr22_1000_guides_config(ff, oracle, chr22_db_path):
         assert ref.overflowed.sum() >= 1 or int(ref.total_count.max()) > 100
         # the same batch through the cell-major kernel and through the windowed general path: a real genome's skewed
         # buckets (repeats, poly-N runs of the seed keys) instead of the uniform synthetic index
-        for env in ({"FF_CELL_SCAN": "1"}, {"FF_FORCE_GENERAL": "1", "FF_WINDOW_CELLS": "3"}):
-            os.environ.update(env)
-            try:
+        for opts in ({"scan_kernel": 2}, {"force_general": 1, "window_cells": 3}):
+            with ctx.options(**opts):
                 helpers.assert_hits_equal(ctx.discover(guides, 4, 2000), ref)
-            finally:
-                for k in env:
-                    os.environ.pop(k, None)
         planted = helpers.planted_guides(db.pack, targets, 1003, 300, max_subs=2)
         ref_b = oracle.discover_bulge(db.pack, targets, planted[:6], 3, 2000, 3, n_threads=os.cpu_count() or 1)
         got_b = ctx.discover_bulge(planted, 3, 2000, 3)
@@ -454,7 +450,7 @@ def test_randomised_small_configurations(ff, oracle):
             raise AssertionError("trial %d enzyme %d n %d g %d k %d maxOT %d: %s" % (trial, enzyme, len(targets), g, k, max_ot, e))
 
 
-def test_pipelined_sub_batches_equal_single_batch(ff, oracle, small_db, monkeypatch):
+def test_pipelined_sub_batches_equal_single_batch(ff, oracle, small_db):
     """ff_discover cuts large guide sets into sub-batches whose D2H overlaps the next scan; the stitched CSR (row
     pointers, per-guide totals, fused scores) must equal the single-batch result and the oracle's."""
     _, db, _ = small_db
@@ -463,10 +459,10 @@ def test_pipelined_sub_batches_equal_single_batch(ff, oracle, small_db, monkeypa
     ref = oracle.discover_blocks(db, guides, 4, 2000)
     with ff.Context(0) as ctx:
         ctx.load_database(small_db[0])
-        monkeypatch.setenv("FF_SUBBATCH_MIN", "1000000")
+        ctx.set_option("subbatch_min", 1000000)
         one, c1, s1, h1 = ctx.discover_score(guides, 4, 2000)
-        for min_batch in ("200", "100", "7"):  # 2 sub-batches (60 / 40 %), 3 sub-batches (65 / 25 / 10 %)
-            monkeypatch.setenv("FF_SUBBATCH_MIN", min_batch)
+        for min_batch in (200, 100, 7):  # 2 sub-batches (60 / 40 %), 3 sub-batches (65 / 25 / 10 %)
+            ctx.set_option("subbatch_min", min_batch)
             many, c4, s4, h4 = ctx.discover_score(guides, 4, 2000)
             helpers.assert_hits_equal(many, ref)
             helpers.assert_hits_equal(many, one)
@@ -521,25 +517,22 @@ def test_hit_aggregates_minot_and_in_genome(ff, oracle):
 
 
 @pytest.mark.parametrize("k", [0, 1, 3, 4, 5, 6])
-def test_cell_major_scan_equals_guide_major_and_oracle(small_ctx, small_db, oracle, k, monkeypatch):
-    """The cell-major kernel (k_cell_scan: the same (guide, seed) pairs visited cell by cell for L2 reuse) is selected
-    for large batches on large indexes; forced here on the small FlashFry-format database."""
+def test_bin_major_scan_equals_guide_major_and_oracle(small_ctx, small_db, oracle, k):
+    """The bin-major kernels (k_bin_scan + k_pair_scan: bit-sliced compare, bins staged in shared memory, part-two pairs
+    sorted by bucket) are selected for large batches on large indexes; forced here on the small FlashFry-format database."""
     _, db, _ = small_db
     targets = db.soa()[0]
     guides = np.concatenate([helpers.random_guides(oracle, db.pack, 17 + k, 333),
                              helpers.planted_guides(db.pack, targets, 71 + k, 400, max_subs=5)])
     ref = oracle.discover_blocks(db, guides, k, 2000)
-    monkeypatch.setenv("FF_CELL_SCAN", "1")
-    for ppi in ("4", "32"):
-        monkeypatch.setenv("FF_CELL_PPI_B", ppi)
+    with small_ctx.options(scan_kernel=2):
         got = small_ctx.discover(guides, k, 2000, positions=True)
         helpers.assert_hits_equal(got, ref, check_positions=True)
-    monkeypatch.setenv("FF_CELL_SCAN", "0")
-    helpers.assert_hits_equal(small_ctx.discover(guides, k, 2000, positions=True), ref, check_positions=True)
+    with small_ctx.options(scan_kernel=1):
+        helpers.assert_hits_equal(small_ctx.discover(guides, k, 2000, positions=True), ref, check_positions=True)
 
 
-def test_cell_major_scan_other_enzymes_and_edge_cases(ff, oracle, tmp_path, monkeypatch):
-    monkeypatch.setenv("FF_CELL_SCAN", "1")
+def test_bin_major_scan_other_enzymes_and_edge_cases(ff, oracle, tmp_path):
     contigs = helpers.random_genome(78, 250_000, repeat_unit=70, n_repeats=150)
     fa = str(tmp_path / "g.fa")
     helpers.write_fasta(fa, contigs)
@@ -550,6 +543,7 @@ def test_cell_major_scan_other_enzymes_and_edge_cases(ff, oracle, tmp_path, monk
         targets = db.soa()[0]
         guides = helpers.planted_guides(db.pack, targets, 5, 300, max_subs=4)
         with ff.Context(0) as ctx:
+            ctx.set_option("scan_kernel", 2)
             ctx.load_database(dbp)
             for k, max_ot in ((4, 2000), (3, 2), (0, 2000)):
                 ref = oracle.discover_blocks(db, guides, k, max_ot)
@@ -559,14 +553,15 @@ def test_cell_major_scan_other_enzymes_and_edge_cases(ff, oracle, tmp_path, monk
             assert ctx.discover(guides[:0], 4, 2000).n_guides == 0
 
 
-def test_cell_major_scan_skewed_batches(ff, oracle, monkeypatch):
-    """Guide batches that break the cell-major kernel's balance assumptions: thousands of copies of one guide (one guide
-    class, one hot bucket per seed, hit buffer regrown and the scan repeated), all guides in two classes, one guide."""
-    monkeypatch.setenv("FF_CELL_SCAN", "1")
+def test_bin_major_scan_skewed_batches(ff, oracle):
+    """Guide batches that break the bin-major kernel's balance assumptions: thousands of copies of one guide (one guide
+    class, one hot bucket per seed, more visits than the shared-memory list holds, hit buffer regrown and the scan
+    repeated), all guides in two classes, one guide."""
     pack = oracle.PACK_BY_INDEX[3]
     targets, seeds = helpers.family_database(oracle, seed=19, n_seeds=24, variants_per_seed=900)
     bin_off = oracle.bin_offsets_from_sorted(pack, 7, targets)
     with ff.Context(0) as ctx:
+        ctx.set_option("scan_kernel", 2)
         ctx.load_database_arrays(3, targets)
         same = np.repeat(seeds[:1], 3000)
         two = np.concatenate([np.repeat(seeds[1:2], 500), helpers.planted_guides(pack, targets[:2000], 3, 500, max_subs=2)])
@@ -611,3 +606,32 @@ def test_database_image_round_trip(ff, oracle, small_db, tmp_path):
         with pytest.raises(ff.FlashFryError) as e:
             ctx.load_image(bad)
         assert e.value.code == -5
+
+
+def test_bin_major_scan_oversized_bins_and_buckets(ff, oracle):
+    """k_bin_scan stages a bin's slice of the bit-sliced index in shared memory (736 groups = 23 552 entries).  A bin
+    that is larger is processed in runs of buckets, a single bucket that is larger is streamed from global memory:
+    30 000 targets sharing their first 11 bases, 40 000 sharing their first 7, on a random background."""
+    pack = oracle.PACK_BY_INDEX[3]
+    rng = np.random.default_rng(77)
+
+    def block(n_fixed, n):  # n distinct targets whose first n_fixed protospacer bases are one random value
+        fixed = int(rng.integers(0, 1 << (2 * n_fixed)))
+        free = 2 * (21 - n_fixed)  # remaining protospacer bases + N
+        tail = np.unique(rng.integers(0, 1 << free, size=int(n * 1.3), dtype=np.uint64))[:n]
+        return ((np.uint64(fixed) << np.uint64(free)) | tail) << np.uint64(4) | np.uint64(0xA)
+
+    seqs = np.unique(np.concatenate([block(11, 30_000), block(7, 40_000), block(0, 50_000)]))
+    counts = rng.integers(1, 4, len(seqs)).astype(np.uint64)
+    targets = seqs | (counts << np.uint64(48))
+    bin_off = oracle.bin_offsets_from_sorted(pack, 7, targets)
+    guides = np.concatenate([helpers.planted_guides(pack, targets, 5, 160, max_subs=4), helpers.random_guides(oracle, pack, 6, 40)])
+    with ff.Context(0) as ctx:
+        ctx.load_database_arrays(3, targets)
+        for max_ot in (2000, 10 ** 7):
+            ref = oracle.discover_soa(pack, 7, targets, bin_off, guides, 4, max_ot, n_threads=os.cpu_count() or 1)
+            with ctx.options(scan_kernel=2):
+                helpers.assert_hits_equal(ctx.discover(guides, 4, max_ot), ref)
+            with ctx.options(scan_kernel=1):
+                helpers.assert_hits_equal(ctx.discover(guides, 4, max_ot), ref)
+        assert int(ref.row_ptr[-1]) > 10_000  # the planted guides really sit in the big bucket / bin

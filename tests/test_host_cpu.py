@@ -241,6 +241,9 @@ def test_library_carries_sm_100a_code_for_every_hot_kernel(built):
     archs = set(re.findall(r"sm_\d+a?", elfs))
     assert archs == {"sm_100a"}, archs
     syms = subprocess.run([cuobjdump, "-symbols", built], capture_output=True, text=True).stdout
-    for kernel in ("k_cell_scan", "k_seed_scan", "k_pattern_scan", "k_overflow_cut", "k_cut_window", "k_sort_segments", "k_gather",
+    for kernel in ("k_bin_scan", "k_pair_scan", "k_slice_planes", "k_seed_scan", "k_pattern_scan", "k_overflow_cut", "k_cut_window", "k_sort_segments", "k_gather",
                    "k_score", "k_hit_aggregates", "k_cell_offsets"):
         assert kernel in syms, "kernel missing from the library: " + kernel
+    # the bin scan stages its bins with TMA bulk copies (cp.async.bulk -> UBLKCP in SASS) completing on an mbarrier
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN2ff10k_bin_scanILi9EEEvNS_9BinParamsE", built], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass, "k_bin_scan lost its TMA bulk copy / mbarrier"

@@ -9,7 +9,7 @@ g = make_guides(100000, 3002)
 pinned = torch.from_numpy(g.view(np.int64)).pin_memory(); gh = pinned.numpy().view(np.uint64)
 gp = gh.ctypes.data_as(C.POINTER(C.c_uint64)); hp = C.POINTER(N.FFHits)()
 for cuts, mb in (("50,80", "20000"), ("60,85", "20000"), ("65,90", "20000"), ("55,85", "20000"), ("70,90","20000"), ("50,80", "45000")):
-    os.environ["FF_SUBBATCH_CUTS"] = cuts; os.environ["FF_SUBBATCH_MIN"] = mb
+    c1, c2 = cuts.split(","); ctx.set_option("subbatch_c1", int(c1)); ctx.set_option("subbatch_c2", int(c2)); ctx.set_option("subbatch_min", int(mb))
     for _ in range(3):
         N.check(N.lib().ff_discover(ctx._h, gp, len(g), 4, 2000, 0, C.byref(hp))); N.lib().ff_hits_free(hp)
     torch.cuda.synchronize(); t0 = time.perf_counter()

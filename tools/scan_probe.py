@@ -17,7 +17,7 @@ import flashfry_b200.api as ff  # noqa: E402
 n_t = int(float(sys.argv[1])) if len(sys.argv) > 1 else 300_000_000
 G = int(float(sys.argv[2])) if len(sys.argv) > 2 else 100_000
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 4
-modes = sys.argv[4].split(",") if len(sys.argv) > 4 else ["0", "1", "2"]
+modes = sys.argv[4].split(",") if len(sys.argv) > 4 else ["1", "2"]
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 
 ctx = ff.Context(0)
@@ -32,7 +32,7 @@ d_g = torch.from_numpy(guides.view(np.int64)).cuda()
 
 ref = None
 for m in modes:
-    os.environ["FF_CELL_SCAN"] = m
+    ctx.set_option("scan_kernel", int(m))
     best = None
     for r in range(reps):
         res = ctx.discover_device(d_g.data_ptr(), len(guides), k, 2000)
