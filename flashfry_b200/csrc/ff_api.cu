@@ -261,8 +261,9 @@ void ff_destroy(ff_ctx *c) {
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys, &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->out_tidx, &c->pos_cnt,
                     &c->pos_ptr, &c->out_positions, &c->cfd_per_ot, &c->hsu_per_ot, &c->scratch_guides, &c->running, &c->active, &c->active2,
-                    &c->act_flags, &c->seg_end, &c->kept_keys, &c->kept_sorted, &c->n_sel, &c->cell_ws};
+                    &c->act_flags, &c->seg_end, &c->kept_keys, &c->kept_sorted, &c->n_sel, &c->cell_ws, &c->idx32, &c->st_targets, &c->st_mm};
   for (DevBuf *b : bufs) b->release();
+  c->h_status.release();
   for (auto &os : c->out) {
     DevBuf *ob[] = {&os.row_ptr, &os.total_count, &os.overflowed, &os.out_targets, &os.out_mm, &os.out_bulge, &os.cfd_max, &os.cfd_spec, &os.hsu};
     for (DevBuf *b : ob) b->release();

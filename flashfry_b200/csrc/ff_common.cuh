@@ -127,6 +127,8 @@ struct ff_ctx {
   ff::DevBuf cub_tmp;
   ff::DevBuf hit_keys, hit_keys_sorted, counters;
   ff::DevBuf seg_start, n_keep, out_tidx;
+  ff::DevBuf idx32, st_targets, st_mm;  // per-guide ordering: scattered database indices, rows staged at their segment
+  ff::HostBuf h_status;                 // pinned mirror of the device status words (one D2H + one sync per call)
   ff::DevBuf pos_cnt, pos_ptr, out_positions;
   ff::DevBuf cfd_per_ot, hsu_per_ot;
   ff::DevBuf scratch_guides;  // H2D staging target for ff_discover

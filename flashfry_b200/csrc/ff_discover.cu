@@ -379,56 +379,172 @@ __global__ void k_gather_positions(const uint32_t *__restrict__ out_tidx, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// ------------------------------------------------------------------------------------------------------------
-// Ordering the candidate hits without a full radix sort.  A typical guide has ~10^2 hits, so the keys are first
-// grouped by guide with a counting sort (histogram, prefix sum, scatter: two passes over the keys) and every guide's
-// short segment is then sorted by database index inside one warp (bitonic network in shared memory).  Six onesweep
-// passes over 46-bit keys cost 0.8 ms for 1.2e7 keys; this costs about a third of that.  A segment longer than
-// kSegSortMax (a guide sitting in a repeat family) raises a flag and the call falls back to the radix sort.
+// Ordering the candidate hits without a full radix sort, and without the host in the loop.  A typical guide has ~10^2
+// hits, so the keys are grouped by guide with a counting sort (per-guide counts, prefix sum, scatter of the 32-bit
+// database indices) and every guide's short segment is sorted, cut by the overflow rule and gathered inside ONE warp
+// (k_sort_cut: bitonic network in shared memory, then the walk of k_overflow_cut, then the row itself written at the
+// segment's position).  Segments of 257..16 384 candidates (a guide inside a repeat family) are sorted beforehand by one
+// CTA each (k_sort_long); only a longer segment, or more than kLongCap long ones, sends the call to the radix sort.
+// Every kernel reads the number of candidates from device memory: the host synchronises once, at the end.
 constexpr int kSegSortMax = 256;
+constexpr int kLongMax = 16384;   // longest segment k_sort_long takes (64 KB of shared memory)
+constexpr int kLongCap = 1024;    // long segments per call
 
-__global__ void k_guide_hist(const uint64_t *__restrict__ keys, int64_t n, int tbits, unsigned long long *__restrict__ cnt) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(cnt + (keys[i] >> tbits), 1ull);
+// status words the pipeline leaves for the host (mirrored into pinned memory with one copy)
+struct PlainStatus {
+  unsigned long long n_cand, n_compares;
+  long long n_hits;
+  unsigned int flag, n_long;
+};
+
+__global__ void k_guide_hist(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ n_ptr, unsigned long long cap, int tbits,
+                             unsigned int *__restrict__ cnt) {
+  const unsigned long long n = min(*n_ptr, cap);
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+    atomicAdd(cnt + (keys[i] >> tbits), 1u);
 }
 
-__global__ void k_guide_scatter(const uint64_t *__restrict__ keys, int64_t n, int tbits, const int64_t *__restrict__ seg_start,
-                                unsigned long long *__restrict__ cursor, uint64_t *__restrict__ out) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t key = keys[i];
-  const uint64_t g = key >> tbits;
-  out[seg_start[g] + (int64_t)atomicAdd(cursor + g, 1ull)] = key;
+__global__ void k_guide_scatter(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ n_ptr, unsigned long long cap, int tbits,
+                                const int64_t *__restrict__ seg_start, unsigned int *__restrict__ cursor, uint32_t *__restrict__ out) {
+  const unsigned long long n = min(*n_ptr, cap);
+  const uint64_t low = (1ull << tbits) - 1ull;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    const uint64_t g = key >> tbits;
+    out[seg_start[g] + (int64_t)atomicAdd(cursor + g, 1u)] = (uint32_t)(key & low);
+  }
 }
 
-// one warp per guide: sort its (<= kSegSortMax) keys in place
-__global__ void __launch_bounds__(256) k_sort_segments(uint64_t *__restrict__ keys, const int64_t *__restrict__ seg_start, int64_t n_guides,
-                                                       unsigned int *__restrict__ too_long) {
-  __shared__ uint64_t s_keys[8][kSegSortMax];
+__global__ void k_widen_counts(const unsigned int *__restrict__ cnt, int64_t n, int64_t *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int64_t)cnt[i];
+  if (i == n) out[i] = 0;
+}
+
+__global__ void k_mark_long(const int64_t *__restrict__ seg_start, int64_t n_guides, uint32_t *__restrict__ long_list, PlainStatus *__restrict__ stt) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= n_guides) return;
+  const int64_t n = seg_start[g + 1] - seg_start[g];
+  if (n <= kSegSortMax) return;
+  if (n > kLongMax) { atomicOr(&stt->flag, 1u); return; }
+  const unsigned int pos = atomicAdd(&stt->n_long, 1u);
+  if (pos < (unsigned int)kLongCap) long_list[pos] = (uint32_t)g; else atomicOr(&stt->flag, 1u);
+}
+
+// one CTA per long segment: bitonic sort of up to kLongMax 32-bit indices in shared memory
+__global__ void __launch_bounds__(512) k_sort_long(uint32_t *__restrict__ idx, const int64_t *__restrict__ seg_start,
+                                                   const uint32_t *__restrict__ long_list, const PlainStatus *__restrict__ stt) {
+  extern __shared__ uint32_t s_long[];
+  if (blockIdx.x >= min(stt->n_long, (unsigned int)kLongCap)) return;
+  const uint32_t g = long_list[blockIdx.x];
+  const int64_t s0 = seg_start[g];
+  const int n = (int)(seg_start[g + 1] - s0);
+  int np = 512;
+  while (np < n) np <<= 1;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s_long[i] = i < n ? idx[s0 + i] : 0xFFFFFFFFu;
+  __syncthreads();
+  for (int k = 2; k <= np; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        const int x = i ^ j;
+        if (x > i) {
+          const uint32_t a = s_long[i], b = s_long[x];
+          if ((a > b) == ((i & k) == 0)) { s_long[i] = b; s_long[x] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) idx[s0 + i] = s_long[i];
+}
+
+// One warp per guide: sort its candidates by database index (short segments: here; long ones arrive sorted), walk them
+// in database order keeping the shortest prefix whose summed occurrence count reaches max_ot
+// (ResultsAggregator.scala:61-69 / CRISPRSiteOT.scala:39-46: append while currentTotal < overflow), and write the kept
+// row -- target long, mismatch count, database index -- at the segment's own position (k_compact_rows closes the gaps).
+__global__ void __launch_bounds__(256) k_sort_cut(uint32_t *__restrict__ idx, const int64_t *__restrict__ seg_start, int64_t n_guides,
+                                                  const uint64_t *__restrict__ targets, const uint64_t *__restrict__ guides, uint64_t cmp_mask,
+                                                  int max_ot, uint64_t *__restrict__ st_targets, uint8_t *__restrict__ st_mm,
+                                                  int64_t *__restrict__ n_keep, int32_t *__restrict__ total_count, uint8_t *__restrict__ overflowed) {
+  __shared__ uint32_t s_keys[8][kSegSortMax];
   const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (g >= n_guides) return;
   const int64_t s0 = seg_start[g];
   const int64_t n = seg_start[g + 1] - s0;
-  if (n <= 1) return;
-  if (n > kSegSortMax) { if (lane == 0) atomicOr(too_long, 1u); return; }
-  int np = 2;
-  while (np < (int)n) np <<= 1;
-  uint64_t *s = s_keys[warp];
-  for (int i = lane; i < np; i += 32) s[i] = i < (int)n ? keys[s0 + i] : ~0ull;
-  __syncwarp();
-  for (int k = 2; k <= np; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < np; i += 32) {
-        const int x = i ^ j;
-        if (x > i) {
-          const uint64_t a = s[i], b = s[x];
-          if ((a > b) == ((i & k) == 0)) { s[i] = b; s[x] = a; }
+  const bool in_smem = n <= kSegSortMax;
+  uint32_t *s = s_keys[warp];
+  if (in_smem && n > 0) {
+    int np = 32;
+    while (np < (int)n) np <<= 1;
+    for (int i = lane; i < np; i += 32) s[i] = i < (int)n ? idx[s0 + i] : 0xFFFFFFFFu;
+    __syncwarp();
+    if (n > 1) {
+      for (int k = 2; k <= np; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < np; i += 32) {
+            const int x = i ^ j;
+            if (x > i) {
+              const uint32_t a = s[i], b = s[x];
+              if ((a > b) == ((i & k) == 0)) { s[i] = b; s[x] = a; }
+            }
+          }
+          __syncwarp();
         }
-      }
-      __syncwarp();
     }
-  for (int i = lane; i < (int)n; i += 32) keys[s0 + i] = s[i];
+  }
+  const uint64_t guide = guides[g];
+  long long running = 0;
+  int64_t kept = 0;
+  for (int64_t base = 0; base < n && running < max_ot; base += 32) {
+    const int64_t i = base + lane;
+    uint32_t t = 0;
+    uint64_t tl = 0;
+    if (i < n) {
+      t = in_smem ? s[i] : idx[s0 + i];
+      tl = targets[t];
+    }
+    const long long c = (long long)(tl >> 48);
+    long long incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const bool keep = (i < n) && (running + incl - c < max_ot);
+    const unsigned int km = __ballot_sync(0xffffffffu, keep);
+    const int nk = __popc(km);  // kept hits form a prefix of the chunk
+    if (keep) {
+      st_targets[s0 + i] = tl;
+      st_mm[s0 + i] = (uint8_t)mismatches64(guide, tl, cmp_mask);
+      if (in_smem) idx[s0 + i] = t;
+    }
+    kept += nk;
+    const long long chunk_total = __shfl_sync(0xffffffffu, incl, nk > 0 ? nk - 1 : 0);
+    if (nk > 0) running += chunk_total;
+    if (nk < 32) break;
+  }
+  if (lane == 0) {
+    n_keep[g] = kept;
+    total_count[g] = (int32_t)running;
+    overflowed[g] = running >= max_ot ? 1 : 0;
+  }
+}
+
+// one warp per guide: move the kept row from its segment to its place in the CSR
+__global__ void k_compact_rows(const int64_t *__restrict__ seg_start, const int64_t *__restrict__ row_ptr, int64_t n_guides,
+                               const uint64_t *__restrict__ st_targets, const uint8_t *__restrict__ st_mm, const uint32_t *__restrict__ idx,
+                               uint64_t *__restrict__ out_targets, uint8_t *__restrict__ out_mm, uint32_t *__restrict__ out_tidx,
+                               PlainStatus *__restrict__ stt) {
+  const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_guides) return;
+  const int64_t s0 = seg_start[g], r0 = row_ptr[g], n = row_ptr[g + 1] - r0;
+  for (int64_t i = lane; i < n; i += 32) {
+    out_targets[r0 + i] = st_targets[s0 + i];
+    out_mm[r0 + i] = st_mm[s0 + i];
+    out_tidx[r0 + i] = idx[s0 + i];
+  }
+  if (g == n_guides - 1 && lane == 0) stt->n_hits = row_ptr[n_guides];
 }
 
 static inline unsigned int blocks_for(int64_t n, int threads) { return (unsigned int)((n + threads - 1) / threads); }
@@ -488,6 +604,10 @@ static void plan_passes(const Database &db, int k, int *hA_out, int *nA, int *nB
 
 #include "ff_binscan.inl"
 
+struct U32ToI64 {
+  __host__ __device__ int64_t operator()(unsigned int v) const { return (int64_t)v; }
+};
+
 static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
                           bool want_positions, int slot, DeviceResult *res) {
   Database &db = ctx->db;
@@ -501,7 +621,8 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
 
   const int64_t G = n_guides;
   const int64_t Gp = G > 0 ? G : 1;
-  FF_TRY(ctx->counters.reserve(64));
+  FF_TRY(ctx->counters.reserve(256));
+  FF_TRY(ctx->h_status.reserve(256));
   FF_TRY(ctx->seg_start.reserve((Gp + 1) * 8));
   FF_TRY(ctx->n_keep.reserve((Gp + 1) * 8));
   FF_TRY(os.row_ptr.reserve((Gp + 1) * 8));
@@ -533,24 +654,26 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   while ((1ull << tbits) < db.n_targets + 1) tbits++;
   sp.tbits = tbits;
 
-  // ---- scan (repeated once with a larger buffer if the hit buffer overflowed)
+  // ---- candidate buffer: expected candidates per random guide = N x P(a random P-mer is within k) (116 at k = 4 on a
+  // human-sized index); start with 1.4x that (+ slack), never more than 2^28 keys up front -- the call is repeated with
+  // a larger buffer if it was not enough
   if (ctx->hit_cap == 0) ctx->hit_cap = 1u << 22;
+  double expected_per_guide = 0.0;
   {
-    // expected candidates per random guide = N x P(a random P-mer is within k) (116 at k = 4 on a human-sized index);
-    // start with 1.4x that (+ slack), never more than 2^28 keys up front -- the scan is repeated if it was not enough
     double prob = 0.0, term = 1.0;  // term = C(P, i) 3^i
     for (int i = 0; i <= k_eff; ++i) {
       prob += term;
       term = term * 3.0 * (double)(db.proto_bases - i) / (double)(i + 1);
     }
     prob /= std::pow(4.0, (double)db.proto_bases);
-    const double per_guide = (double)db.n_targets * prob * 1.4 + 64.0;
+    expected_per_guide = (double)db.n_targets * prob;
+    const double per_guide = expected_per_guide * 1.4 + 64.0;
     size_t want = (size_t)std::min((double)G * per_guide, 268435456.0);
     if (want > ctx->hit_cap) ctx->hit_cap = want;
   }
-  unsigned long long *d_cnt = ctx->counters.as<unsigned long long>();  // [0] hits [1] compares
-  sp.hit_count = d_cnt; sp.n_compares = d_cnt + 1;
-  unsigned long long h_cnt[2] = {0, 0};
+  PlainStatus *d_stt = ctx->counters.as<PlainStatus>();
+  PlainStatus *h_stt = ctx->h_status.as<PlainStatus>();
+  sp.hit_count = &d_stt->n_cand; sp.n_compares = &d_stt->n_compares;
   int scan_launches = 0;
   const long long n_items = G * (long long)sp.items_per_guide;
   const int max_grid = ctx->sm_count * 8;  // 8 CTAs of 8 warps per SM
@@ -566,98 +689,120 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   }
   BinScanPlan bpl;
   if (bin_major) FF_TRY(bin_scan_prepare(ctx, sp, hA, nB, &bpl, &launches));
+  // Order the candidates with the per-guide pipeline (no host round trip) when segments are expected to be short.
+  bool grouped = G > 0 && ctx->opt.group_sort != 0 && expected_per_guide <= 160.0;
+  static bool long_attr[64] = {false};
+  if (grouped && !long_attr[ctx->device & 63]) {
+    FF_CUDA(cudaFuncSetAttribute(k_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize, kLongMax * 4));
+    long_attr[ctx->device & 63] = true;
+  }
   FF_CUDA(cudaEventRecord(ctx->ev[1], st));
+  int64_t n_cand = 0, n_hits = 0;
+  const uint64_t *sorted = nullptr;
+  size_t tmp_bytes = 0;
   for (;;) {
-    FF_TRY(ctx->hit_keys.reserve(ctx->hit_cap * 8));
-    FF_TRY(ctx->hit_keys_sorted.reserve(ctx->hit_cap * 8));
-    sp.hits = ctx->hit_keys.as<uint64_t>(); sp.hit_cap = ctx->hit_cap;
-    FF_CUDA(cudaMemsetAsync(d_cnt, 0, 16, st));
+    const size_t cap = ctx->hit_cap;
+    FF_TRY(ctx->hit_keys.reserve(cap * 8));
+    FF_TRY(os.out_targets.reserve((cap + 1) * 8));
+    FF_TRY(os.out_mm.reserve(cap + 1));
+    FF_TRY(ctx->out_tidx.reserve((cap + 1) * 4));
+    sp.hits = ctx->hit_keys.as<uint64_t>(); sp.hit_cap = cap;
+    FF_CUDA(cudaMemsetAsync(d_stt, 0, sizeof(PlainStatus), st));
     if (G > 0) {
       if (bin_major) {
         FF_TRY(bin_scan_launch(ctx, &bpl, sp, &launches));
-        launches--;
       } else {
         k_seed_scan<<<grid, kScanThreads, 0, st>>>(sp);
+        launches++;
       }
-      launches++;
       scan_launches++;
     }
     FF_CUDA(cudaEventRecord(ctx->ev[2], st));
-    FF_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+    if (grouped) {
+      FF_TRY(ctx->idx32.reserve((cap + 1) * 4));
+      FF_TRY(ctx->st_targets.reserve((cap + 1) * 8));
+      FF_TRY(ctx->st_mm.reserve(cap + 1));
+      FF_TRY(ctx->running.reserve((size_t)(Gp + 1) * 4 * 2 + kLongCap * 4));  // per-guide counts [G+1], cursors [G], long segments
+      unsigned int *cnt = ctx->running.as<unsigned int>(), *cursor = cnt + (Gp + 1);
+      uint32_t *long_list = reinterpret_cast<uint32_t *>(cursor + Gp);
+      FF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(Gp + 1) * 4 * 2, st));
+      const int sgrid = ctx->sm_count * 16;
+      k_guide_hist<<<sgrid, 256, 0, st>>>(sp.hits, &d_stt->n_cand, cap, tbits, cnt);
+      cub::TransformInputIterator<int64_t, U32ToI64, unsigned int *> cnt64(cnt, U32ToI64());
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
+      FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
+      k_guide_scatter<<<sgrid, 256, 0, st>>>(sp.hits, &d_stt->n_cand, cap, tbits, ctx->seg_start.as<int64_t>(), cursor, ctx->idx32.as<uint32_t>());
+      k_mark_long<<<blocks_for(G, 256), 256, 0, st>>>(ctx->seg_start.as<int64_t>(), G, long_list, d_stt);
+      k_sort_long<<<kLongCap, 512, kLongMax * 4, st>>>(ctx->idx32.as<uint32_t>(), ctx->seg_start.as<int64_t>(), long_list, d_stt);
+      FF_CUDA(cudaEventRecord(ctx->ev[3], st));
+      k_sort_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->idx32.as<uint32_t>(), ctx->seg_start.as<int64_t>(), G, db.d_targets, d_guides,
+                                                         db.pack.cmp_mask, max_ot, ctx->st_targets.as<uint64_t>(), ctx->st_mm.as<uint8_t>(),
+                                                         ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>());
+      FF_CUDA(cudaMemsetAsync(ctx->n_keep.as<int64_t>() + G, 0, 8, st));
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
+      FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
+      k_compact_rows<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), G, ctx->st_targets.as<uint64_t>(),
+                                                             ctx->st_mm.as<uint8_t>(), ctx->idx32.as<uint32_t>(), os.out_targets.as<uint64_t>(),
+                                                             os.out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>(), d_stt);
+      launches += 9;
+      FF_CUDA(cudaEventRecord(ctx->ev[4], st));
+    }
+    FF_CUDA(cudaMemcpyAsync(h_stt, d_stt, sizeof(PlainStatus), cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaStreamSynchronize(st));
-    if (h_cnt[0] <= ctx->hit_cap) break;
-    ctx->hit_cap = (size_t)(h_cnt[0] + h_cnt[0] / 8 + 1024);
-    FF_CUDA(cudaEventRecord(ctx->ev[1], st));  // time only the run that counted
+    n_cand = (int64_t)h_stt->n_cand;
+    if ((size_t)n_cand > cap) {  // the buffer was too small: grow it and repeat the call
+      ctx->hit_cap = (size_t)(n_cand + n_cand / 8 + 1024);
+      FF_CUDA(cudaEventRecord(ctx->ev[1], st));  // time only the run that counted
+      continue;
+    }
+    if (grouped && h_stt->flag) grouped = false;  // a segment beyond k_sort_long: order these candidates with the radix sort
+    if (grouped) n_hits = h_stt->n_hits;
+    break;
   }
-  const int64_t n_cand = (int64_t)h_cnt[0];
-  size_t tmp_bytes = 0;
 
-  // ---- order hits by (guide, database index)
-  int gbits = 1;
-  while ((1ll << gbits) < Gp) gbits++;
-  const uint64_t *sorted = ctx->hit_keys.as<uint64_t>();
-  bool grouped = false;  // seg_start already known (counting sort by guide + per-guide warp sorts)
-  bool try_grouped = n_cand > 0 && n_cand <= 160 * G;  // short segments on average
-  try_grouped = try_grouped && ctx->opt.group_sort != 0;
-  if (try_grouped) {
-    FF_TRY(ctx->running.reserve((Gp + 1) * 8 * 2));  // per-guide counts [G+1] and cursors [G]
-    unsigned long long *cnt = ctx->running.as<unsigned long long>(), *cursor = cnt + (Gp + 1);
-    unsigned int *d_flag = reinterpret_cast<unsigned int *>(d_cnt + 2);
-    FF_CUDA(cudaMemsetAsync(cnt, 0, (Gp + 1) * 8 * 2, st));
-    FF_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
-    k_guide_hist<<<blocks_for(n_cand, 256), 256, 0, st>>>(ctx->hit_keys.as<uint64_t>(), n_cand, tbits, cnt);
-    FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, reinterpret_cast<int64_t *>(cnt), ctx->seg_start.as<int64_t>(), G + 1, st));
-    FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
-    FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, reinterpret_cast<int64_t *>(cnt), ctx->seg_start.as<int64_t>(), G + 1, st));
-    k_guide_scatter<<<blocks_for(n_cand, 256), 256, 0, st>>>(ctx->hit_keys.as<uint64_t>(), n_cand, tbits, ctx->seg_start.as<int64_t>(), cursor,
-                                                            ctx->hit_keys_sorted.as<uint64_t>());
-    k_sort_segments<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->hit_keys_sorted.as<uint64_t>(), ctx->seg_start.as<int64_t>(), G, d_flag);
-    launches += 5;
-    unsigned int h_flag = 0;
-    FF_CUDA(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
-    FF_CUDA(cudaStreamSynchronize(st));
-    if (!h_flag) { grouped = true; sorted = ctx->hit_keys_sorted.as<uint64_t>(); }
-  }
-  if (n_cand > 0 && !grouped) {
-    FF_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, ctx->hit_keys.as<uint64_t>(), ctx->hit_keys_sorted.as<uint64_t>(), n_cand, 0, tbits + gbits, st));
-    FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
-    FF_CUDA(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp_bytes, ctx->hit_keys.as<uint64_t>(), ctx->hit_keys_sorted.as<uint64_t>(), n_cand, 0, tbits + gbits, st));
-    sorted = ctx->hit_keys_sorted.as<uint64_t>();
-    launches += 2 + (tbits + gbits + 7) / 8;
-  }
-  FF_CUDA(cudaEventRecord(ctx->ev[3], st));
-
-  // ---- overflow cut in database order
   if (!grouped) {
+    // ---- order hits by (guide, database index) with a radix sort over the significant key bits
+    int gbits = 1;
+    while ((1ll << gbits) < Gp) gbits++;
+    sorted = ctx->hit_keys.as<uint64_t>();
+    if (n_cand > 0) {
+      FF_TRY(ctx->hit_keys_sorted.reserve(ctx->hit_cap * 8));
+      FF_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, ctx->hit_keys.as<uint64_t>(), ctx->hit_keys_sorted.as<uint64_t>(), n_cand, 0, tbits + gbits, st));
+      FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
+      FF_CUDA(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp_bytes, ctx->hit_keys.as<uint64_t>(), ctx->hit_keys_sorted.as<uint64_t>(), n_cand, 0, tbits + gbits, st));
+      sorted = ctx->hit_keys_sorted.as<uint64_t>();
+      launches += 2 + (tbits + gbits + 7) / 8;
+    }
+    FF_CUDA(cudaEventRecord(ctx->ev[3], st));
+    // ---- overflow cut in database order
     k_segments<<<blocks_for(G + 1, 256), 256, 0, st>>>(sorted, n_cand, G, tbits, ctx->seg_start.as<int64_t>());
     launches++;
-  }
-  if (G > 0) {
-    k_overflow_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), db.d_targets, G, max_ot, tbits,
-                                                           ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>());
-    launches++;
-  }
-  FF_CUDA(cudaMemsetAsync(ctx->n_keep.as<int64_t>() + G, 0, 8, st));
-  FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
-  FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
-  FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
-  launches += 2;
-  int64_t n_hits = 0;
-  FF_CUDA(cudaMemcpyAsync(&n_hits, os.row_ptr.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, st));
-  FF_CUDA(cudaStreamSynchronize(st));
-  const int64_t Hp = n_hits > 0 ? n_hits : 1;
-  FF_TRY(os.out_targets.reserve(Hp * 8));
-  FF_TRY(os.out_mm.reserve(Hp));
-  FF_TRY(ctx->out_tidx.reserve(Hp * 4));
-  if (G > 0 && n_hits > 0) {
-    k_gather<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), db.d_targets, d_guides,
-                                                     db.pack.cmp_mask, G, tbits, os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>());
-    launches++;
+    if (G > 0) {
+      k_overflow_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), db.d_targets, G, max_ot, tbits,
+                                                             ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>());
+      launches++;
+    }
+    FF_CUDA(cudaMemsetAsync(ctx->n_keep.as<int64_t>() + G, 0, 8, st));
+    FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
+    FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
+    FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
+    launches += 2;
+    FF_CUDA(cudaMemcpyAsync(&n_hits, os.row_ptr.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    if (G > 0 && n_hits > 0) {
+      k_gather<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), db.d_targets, d_guides,
+                                                       db.pack.cmp_mask, G, tbits, os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>());
+      launches++;
+    }
   }
   int64_t n_pos = 0;
   FF_TRY(gather_positions(ctx, os, want_positions, n_hits, res, &n_pos, &launches));
-  FF_CUDA(cudaEventRecord(ctx->ev[4], st));
-  FF_CUDA(cudaStreamSynchronize(st));
+  if (!grouped || want_positions) {
+    FF_CUDA(cudaEventRecord(ctx->ev[4], st));
+    FF_CUDA(cudaStreamSynchronize(st));
+  }
   FF_CUDA(cudaGetLastError());
 
   FF_CUDA(cudaEventElapsedTime(&tm.prep_ms, ctx->ev[0], ctx->ev[1]));
@@ -668,16 +813,18 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   tm.score_ms = 0.f;
   tm.scan_launches = scan_launches;
   tm.kernel_launches = launches;
-  // algorithmic bytes of the scan: per (guide, seed) the two index entries, per streamed entry
-  // its 4-byte complementary part, per guide its 8-byte long, per candidate hit one 8-byte key written
-  tm.scan_bytes_read = (uint64_t)G * (uint64_t)(nA + nB) * 8ull + h_cnt[1] * 4ull + (uint64_t)G * 8ull + (uint64_t)n_cand * 8ull;
+  // bytes the scan kernels request (NOT the roofline's algorithmic bytes, see bench.py): per (guide, seed) the two index
+  // entries, per streamed entry its bit-sliced planes (or its 4-byte word in the guide-major kernel), per guide its
+  // long, per candidate hit one 8-byte key
+  tm.scan_bytes_read = (uint64_t)G * (uint64_t)(nA + nB) * 8ull + h_stt->n_compares * 4ull + (uint64_t)G * 8ull + (uint64_t)n_cand * 8ull;
   ctx->last = tm;
 
   res->n_guides = G; res->n_hits = n_hits; res->n_positions = n_pos;
-  res->n_candidate_hits = (uint64_t)n_cand; res->n_compares = h_cnt[1];
+  res->n_candidate_hits = (uint64_t)n_cand; res->n_compares = h_stt->n_compares;
   res->d_row_ptr = os.row_ptr.as<int64_t>(); res->d_targets = os.out_targets.as<uint64_t>();
   res->d_mismatches = os.out_mm.as<uint8_t>(); res->d_total_count = os.total_count.as<int32_t>();
   res->d_overflowed = os.overflowed.as<uint8_t>(); res->d_bulge = nullptr;
+  res->d_tidx = ctx->out_tidx.as<uint32_t>();
   return FF_OK;
 }
 

@@ -25,6 +25,7 @@ struct DeviceResult {
   const uint64_t *d_targets = nullptr;
   const uint8_t *d_mismatches = nullptr;
   const uint8_t *d_bulge = nullptr;  // bulge mode only
+  const uint32_t *d_tidx = nullptr;  // database index of every emitted hit (plain path)
   const int32_t *d_total_count = nullptr;
   const uint8_t *d_overflowed = nullptr;
   const int64_t *d_pos_ptr = nullptr;
