@@ -102,6 +102,7 @@ struct HitSink {
   unsigned long long *hit_count;
   unsigned long long hit_cap;
   int tbits;
+  unsigned int *gcnt;  // per-guide candidate counts for the ordering that follows (nullptr: not wanted)
 };
 
 // All shared memory of the two kernels is addressed as byte offsets into this one array: a generic pointer to shared
@@ -130,6 +131,7 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
       }
     }
     const int c = __popc(vm);
+    if (c && hs.gcnt) atomicAdd(hs.gcnt + e.z, (unsigned int)c);
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -657,7 +659,7 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, B
     bp.rcp[d] = bp.nm[d] > 1 ? (uint32_t)(0x100000000ull / (uint64_t)bp.nm[d]) : 0xFFFFFFFFu;
   }
   bp.hA = hA; bp.k = sp.k; bp.n_bins = n_bins; bp.sg = sg; bp.cls_off = cls_off;
-  bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits};
+  bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits, nullptr};
   bp.n_compares = sp.n_compares;
   bp.next_bin = (unsigned int *)(w + o_ctr);
   PairParams &pp = pl->pp;
@@ -671,9 +673,9 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, B
 }
 
 // (re)launch the two scan kernels of a prepared plan; hit buffer and counters come from `sp`
-static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, int *launches) {
+static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, unsigned int *gcnt, int *launches) {
   cudaStream_t st = ctx->stream;
-  pl->bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits};
+  pl->bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits, gcnt};
   pl->pp.hs = pl->bp.hs;
   FF_CUDA(cudaMemsetAsync(pl->bp.next_bin, 0, 128, st));
   static bool attr_set[64] = {false};

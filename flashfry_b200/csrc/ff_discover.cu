@@ -406,7 +406,8 @@ __global__ void k_guide_hist(const uint64_t *__restrict__ keys, const unsigned l
 
 __global__ void k_guide_scatter(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ n_ptr, unsigned long long cap, int tbits,
                                 const int64_t *__restrict__ seg_start, unsigned int *__restrict__ cursor, uint32_t *__restrict__ out) {
-  const unsigned long long n = min(*n_ptr, cap);
+  if (*n_ptr > cap) return;  // the candidate buffer overflowed: the call is repeated with a larger one
+  const unsigned long long n = *n_ptr;
   const uint64_t low = (1ull << tbits) - 1ull;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
     const uint64_t key = keys[i];
@@ -435,7 +436,7 @@ __global__ void k_mark_long(const int64_t *__restrict__ seg_start, int64_t n_gui
 __global__ void __launch_bounds__(512) k_sort_long(uint32_t *__restrict__ idx, const int64_t *__restrict__ seg_start,
                                                    const uint32_t *__restrict__ long_list, const PlainStatus *__restrict__ stt) {
   extern __shared__ uint32_t s_long[];
-  if (blockIdx.x >= min(stt->n_long, (unsigned int)kLongCap)) return;
+  if (blockIdx.x >= min(stt->n_long, (unsigned int)kLongCap) || stt->flag) return;
   const uint32_t g = long_list[blockIdx.x];
   const int64_t s0 = seg_start[g];
   const int n = (int)(seg_start[g + 1] - s0);
@@ -457,76 +458,112 @@ __global__ void __launch_bounds__(512) k_sort_long(uint32_t *__restrict__ idx, c
   for (int i = threadIdx.x; i < n; i += blockDim.x) idx[s0 + i] = s_long[i];
 }
 
-// One warp per guide: sort its candidates by database index (short segments: here; long ones arrive sorted), walk them
-// in database order keeping the shortest prefix whose summed occurrence count reaches max_ot
-// (ResultsAggregator.scala:61-69 / CRISPRSiteOT.scala:39-46: append while currentTotal < overflow), and write the kept
-// row -- target long, mismatch count, database index -- at the segment's own position (k_compact_rows closes the gaps).
+// What the walk over a guide's candidates in database order carries from chunk to chunk.
+struct CutState {
+  long long running;
+  int64_t kept;
+  bool done;
+};
+
+// One chunk of 32 candidates (lane i holds database index t, valid when i < n): keep the prefix while the running sum of
+// occurrence counts is below max_ot (ResultsAggregator.scala:61-69 / CRISPRSiteOT.scala:39-46: append while
+// currentTotal < overflow) and write the kept rows -- target long, mismatch count, database index -- at the segment's
+// own position (k_compact_rows closes the gaps between segments).
+__device__ __forceinline__ void cut_chunk(CutState &cs, int64_t i, int64_t n, uint32_t t, int lane, const uint64_t *__restrict__ targets,
+                                          uint64_t guide, uint64_t cmp_mask, int max_ot, int64_t s0, uint64_t *__restrict__ st_targets,
+                                          uint8_t *__restrict__ st_mm, uint32_t *__restrict__ idx) {
+  const uint64_t tl = i < n ? targets[t] : 0ull;
+  const int c = (int)(tl >> 48);
+  int incl = c;  // a chunk sums to < 2^21
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const bool keep = (i < n) && (cs.running + (long long)(incl - c) < (long long)max_ot);
+  const unsigned int km = __ballot_sync(0xffffffffu, keep);
+  const int nk = __popc(km);  // kept hits form a prefix of the chunk
+  if (keep) {
+    st_targets[s0 + i] = tl;
+    st_mm[s0 + i] = (uint8_t)mismatches64(guide, tl, cmp_mask);
+    idx[s0 + i] = t;
+  }
+  cs.kept += nk;
+  const int chunk_total = __shfl_sync(0xffffffffu, incl, nk > 0 ? nk - 1 : 0);
+  if (nk > 0) cs.running += chunk_total;
+  if (nk < 32 || cs.running >= max_ot) cs.done = true;
+}
+
+// A segment of at most 32 E candidates: bitonic sort in registers (element e * 32 + lane lives in v[e] of the lane:
+// partners closer than 32 are reached with one shuffle, the others are in the same lane), then the walk.
+template <int E>
+__device__ __forceinline__ void sort_cut_regs(CutState &cs, int64_t n, int lane, int64_t s0, uint32_t *__restrict__ idx,
+                                              const uint64_t *__restrict__ targets, uint64_t guide, uint64_t cmp_mask, int max_ot,
+                                              uint64_t *__restrict__ st_targets, uint8_t *__restrict__ st_mm) {
+  uint32_t v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) v[e] = (e * 32 + lane < n) ? idx[s0 + e * 32 + lane] : 0xFFFFFFFFu;
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int je = j >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if ((e & je) == 0) {
+            const bool up = ((e * 32) & k) == 0;  // k >= 64 here: the direction depends on e only
+            const uint32_t a = v[e], b = v[e | je];
+            const uint32_t lo = min(a, b), hi = max(a, b);
+            v[e] = up ? lo : hi; v[e | je] = up ? hi : lo;
+          }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int i = e * 32 + lane;
+          const bool up = (i & k) == 0, lower = (lane & j) == 0;
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, v[e], j);
+          v[e] = (lower == up) ? min(v[e], o) : max(v[e], o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (!cs.done && e * 32 < n) cut_chunk(cs, e * 32 + lane, n, v[e], lane, targets, guide, cmp_mask, max_ot, s0, st_targets, st_mm, idx);
+}
+
+// One warp per guide: sort its candidates by database index (up to kSegSortMax: in registers; longer segments arrive
+// sorted from k_sort_long and are streamed), cut, and stage the kept row.
 __global__ void __launch_bounds__(256) k_sort_cut(uint32_t *__restrict__ idx, const int64_t *__restrict__ seg_start, int64_t n_guides,
                                                   const uint64_t *__restrict__ targets, const uint64_t *__restrict__ guides, uint64_t cmp_mask,
                                                   int max_ot, uint64_t *__restrict__ st_targets, uint8_t *__restrict__ st_mm,
-                                                  int64_t *__restrict__ n_keep, int32_t *__restrict__ total_count, uint8_t *__restrict__ overflowed) {
-  __shared__ uint32_t s_keys[8][kSegSortMax];
+                                                  int64_t *__restrict__ n_keep, int32_t *__restrict__ total_count, uint8_t *__restrict__ overflowed,
+                                                  const PlainStatus *__restrict__ stt, unsigned long long cap) {
   const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   if (g >= n_guides) return;
+  if (stt->n_cand > cap || stt->flag) {  // overflowed buffer / a segment for the radix sort: this attempt is void
+    if (lane == 0) n_keep[g] = 0;
+    return;
+  }
   const int64_t s0 = seg_start[g];
   const int64_t n = seg_start[g + 1] - s0;
-  const bool in_smem = n <= kSegSortMax;
-  uint32_t *s = s_keys[warp];
-  if (in_smem && n > 0) {
-    int np = 32;
-    while (np < (int)n) np <<= 1;
-    for (int i = lane; i < np; i += 32) s[i] = i < (int)n ? idx[s0 + i] : 0xFFFFFFFFu;
-    __syncwarp();
-    if (n > 1) {
-      for (int k = 2; k <= np; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = lane; i < np; i += 32) {
-            const int x = i ^ j;
-            if (x > i) {
-              const uint32_t a = s[i], b = s[x];
-              if ((a > b) == ((i & k) == 0)) { s[i] = b; s[x] = a; }
-            }
-          }
-          __syncwarp();
-        }
-    }
-  }
   const uint64_t guide = guides[g];
-  long long running = 0;
-  int64_t kept = 0;
-  for (int64_t base = 0; base < n && running < max_ot; base += 32) {
-    const int64_t i = base + lane;
-    uint32_t t = 0;
-    uint64_t tl = 0;
-    if (i < n) {
-      t = in_smem ? s[i] : idx[s0 + i];
-      tl = targets[t];
+  CutState cs{0, 0, max_ot <= 0 || n == 0};
+  if (n <= 32) sort_cut_regs<1>(cs, n, lane, s0, idx, targets, guide, cmp_mask, max_ot, st_targets, st_mm);
+  else if (n <= 64) sort_cut_regs<2>(cs, n, lane, s0, idx, targets, guide, cmp_mask, max_ot, st_targets, st_mm);
+  else if (n <= 128) sort_cut_regs<4>(cs, n, lane, s0, idx, targets, guide, cmp_mask, max_ot, st_targets, st_mm);
+  else if (n <= kSegSortMax) sort_cut_regs<8>(cs, n, lane, s0, idx, targets, guide, cmp_mask, max_ot, st_targets, st_mm);
+  else
+    for (int64_t base = 0; base < n && !cs.done; base += 32) {
+      const int64_t i = base + lane;
+      cut_chunk(cs, i, n, i < n ? idx[s0 + i] : 0u, lane, targets, guide, cmp_mask, max_ot, s0, st_targets, st_mm, idx);
     }
-    const long long c = (long long)(tl >> 48);
-    long long incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const bool keep = (i < n) && (running + incl - c < max_ot);
-    const unsigned int km = __ballot_sync(0xffffffffu, keep);
-    const int nk = __popc(km);  // kept hits form a prefix of the chunk
-    if (keep) {
-      st_targets[s0 + i] = tl;
-      st_mm[s0 + i] = (uint8_t)mismatches64(guide, tl, cmp_mask);
-      if (in_smem) idx[s0 + i] = t;
-    }
-    kept += nk;
-    const long long chunk_total = __shfl_sync(0xffffffffu, incl, nk > 0 ? nk - 1 : 0);
-    if (nk > 0) running += chunk_total;
-    if (nk < 32) break;
-  }
   if (lane == 0) {
-    n_keep[g] = kept;
-    total_count[g] = (int32_t)running;
-    overflowed[g] = running >= max_ot ? 1 : 0;
+    n_keep[g] = cs.kept;
+    total_count[g] = (int32_t)cs.running;
+    overflowed[g] = cs.running >= max_ot ? 1 : 0;
   }
 }
 
@@ -708,9 +745,15 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     FF_TRY(ctx->out_tidx.reserve((cap + 1) * 4));
     sp.hits = ctx->hit_keys.as<uint64_t>(); sp.hit_cap = cap;
     FF_CUDA(cudaMemsetAsync(d_stt, 0, sizeof(PlainStatus), st));
+    unsigned int *cnt = nullptr, *cursor = nullptr;
+    if (grouped) {  // per-guide candidate counts [G + 1], scatter cursors [G], list of long segments
+      FF_TRY(ctx->running.reserve((size_t)(Gp + 1) * 4 * 2 + kLongCap * 4));
+      cnt = ctx->running.as<unsigned int>(); cursor = cnt + (Gp + 1);
+      FF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(Gp + 1) * 4 * 2, st));
+    }
     if (G > 0) {
       if (bin_major) {
-        FF_TRY(bin_scan_launch(ctx, &bpl, sp, &launches));
+        FF_TRY(bin_scan_launch(ctx, &bpl, sp, cnt, &launches));  // (counts the candidates per guide as it emits them)
       } else {
         k_seed_scan<<<grid, kScanThreads, 0, st>>>(sp);
         launches++;
@@ -722,12 +765,9 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
       FF_TRY(ctx->idx32.reserve((cap + 1) * 4));
       FF_TRY(ctx->st_targets.reserve((cap + 1) * 8));
       FF_TRY(ctx->st_mm.reserve(cap + 1));
-      FF_TRY(ctx->running.reserve((size_t)(Gp + 1) * 4 * 2 + kLongCap * 4));  // per-guide counts [G+1], cursors [G], long segments
-      unsigned int *cnt = ctx->running.as<unsigned int>(), *cursor = cnt + (Gp + 1);
       uint32_t *long_list = reinterpret_cast<uint32_t *>(cursor + Gp);
-      FF_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(Gp + 1) * 4 * 2, st));
       const int sgrid = ctx->sm_count * 16;
-      k_guide_hist<<<sgrid, 256, 0, st>>>(sp.hits, &d_stt->n_cand, cap, tbits, cnt);
+      if (!bin_major) k_guide_hist<<<sgrid, 256, 0, st>>>(sp.hits, &d_stt->n_cand, cap, tbits, cnt);
       cub::TransformInputIterator<int64_t, U32ToI64, unsigned int *> cnt64(cnt, U32ToI64());
       FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
       FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
@@ -738,7 +778,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
       FF_CUDA(cudaEventRecord(ctx->ev[3], st));
       k_sort_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->idx32.as<uint32_t>(), ctx->seg_start.as<int64_t>(), G, db.d_targets, d_guides,
                                                          db.pack.cmp_mask, max_ot, ctx->st_targets.as<uint64_t>(), ctx->st_mm.as<uint8_t>(),
-                                                         ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>());
+                                                         ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>(), d_stt, cap);
       FF_CUDA(cudaMemsetAsync(ctx->n_keep.as<int64_t>() + G, 0, 8, st));
       FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
       FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
