@@ -29,7 +29,7 @@ class FFHits(C.Structure):
                 ("pos_ptr", C.POINTER(C.c_int64)), ("positions", C.POINTER(C.c_uint64)),
                 ("total_count", C.POINTER(C.c_int32)), ("overflowed", C.POINTER(C.c_uint8)),
                 ("n_compares", C.c_uint64), ("n_candidate_hits", C.c_uint64), ("opaque", C.c_void_p),
-                ("bulge", C.POINTER(C.c_uint8))]
+                ("bulge", C.POINTER(C.c_uint8)), ("target_index", C.POINTER(C.c_uint32))]
 
 
 class FFDbInfo(C.Structure):
@@ -56,7 +56,7 @@ class FFTimings(C.Structure):
 # every symbol include/flashfry_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_set_option", "ff_load_database",
            "ff_save_image", "ff_load_image", "ff_load_database_arrays", "ff_synth_database", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
-           "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_score", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
+           "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_db_host_targets", "ff_hits_resolve", "ff_score", "ff_score_enzyme", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
 
 _lib = None
 
@@ -91,7 +91,11 @@ def lib():
     L.ff_discover_bulge_device.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(FFDeviceResult)]
     L.ff_hits_free.argtypes = [C.POINTER(FFHits)]
     L.ff_hits_free.restype = None
+    L.ff_db_host_targets.argtypes = [vp]
+    L.ff_db_host_targets.restype = u64p
+    L.ff_hits_resolve.argtypes = [vp, C.POINTER(FFHits)]
     L.ff_score.argtypes = [vp, u64p, C.POINTER(FFHits), C.c_uint32, dp, dp, dp, dp]
+    L.ff_score_enzyme.argtypes = [vp, C.c_int, u64p, C.POINTER(FFHits), C.c_uint32, dp, dp, dp, dp]
     i32p = C.POINTER(C.c_int32)
     L.ff_hit_aggregates.argtypes = [vp, C.c_int, u64p, C.POINTER(FFHits), i32p, i32p, i32p, i32p]
     L.ff_discover_score.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint32,

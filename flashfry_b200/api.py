@@ -25,6 +25,7 @@ class Hits:
     n_compares: int
     n_candidate_hits: int
     bulge: Optional[np.ndarray] = None  # ff_discover_bulge only: 0 none, 0x40|q RNA bulge, 0x80|q DNA bulge
+    target_index: Optional[np.ndarray] = None  # option compact_hits: database index of every hit
 
     @property
     def n_guides(self) -> int:
@@ -53,6 +54,8 @@ def _take_hits(hp) -> Hits:
                _arr(h.overflowed, G, np.uint8), pos_ptr, positions, int(h.n_compares), int(h.n_candidate_hits))
     if h.bulge:
         out.bulge = _arr(h.bulge, H, np.uint8)
+    if h.target_index:
+        out.target_index = _arr(h.target_index, H, np.uint32)
     N.lib().ff_hits_free(hp)
     return out
 
@@ -146,11 +149,16 @@ class Context:
         return out
 
     # ---- discover / score
-    def discover(self, guides, max_mismatch: int = 4, maximum_off_targets: int = 2000, positions: bool = False) -> Hits:
+    def discover(self, guides, max_mismatch: int = 4, maximum_off_targets: int = 2000, positions: bool = False,
+                 resolve: bool = False) -> Hits:
+        """ff_discover.  With option compact_hits the hit list carries target_index instead of targets; resolve=True
+        then calls ff_hits_resolve (targets filled from the host mirror of the database)."""
         g = _u64(guides)
         hp = C.POINTER(N.FFHits)()
         N.check(N.lib().ff_discover(self._h, g.ctypes.data_as(C.POINTER(C.c_uint64)), len(g), max_mismatch,
                                     maximum_off_targets, int(positions), C.byref(hp)))
+        if resolve:
+            N.check(N.lib().ff_hits_resolve(self._h, hp))
         return _take_hits(hp)
 
     def discover_bulge(self, guides, max_mismatch: int = 4, maximum_off_targets: int = 2000,

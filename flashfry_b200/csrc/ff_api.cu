@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 
 #include "ff_common.cuh"
 #include "ff_kernels.cuh"
@@ -55,7 +56,7 @@ void HostBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 // discover calls do not pay cudaHostAlloc.
 struct HitsOwner {
   ff_hits pub;
-  HostBuf row_ptr, targets, mm, bulge, pos_ptr, positions, total, ovf;
+  HostBuf row_ptr, targets, mm, bulge, pos_ptr, positions, total, ovf, tidx;
 };
 static std::mutex g_pool_mu;
 static std::vector<HitsOwner *> g_pool;
@@ -69,7 +70,7 @@ static void owner_put(HitsOwner *o) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
   if (g_pool.size() < 4) { g_pool.push_back(o); return; }
   o->row_ptr.release(); o->targets.release(); o->mm.release(); o->bulge.release(); o->pos_ptr.release(); o->positions.release();
-  o->total.release(); o->ovf.release();
+  o->total.release(); o->ovf.release(); o->tidx.release();
   delete o;
 }
 
@@ -139,6 +140,7 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   const int64_t G = n_guides;
   if ((rc = o->row_ptr.reserve((G + 1) * 8)) || (rc = o->total.reserve((G + 1) * 4)) || (rc = o->ovf.reserve(G + 1))) return fail(rc);
   ff_timings acc = {};
+  const bool compact = c->opt.compact_hits != 0 && !bulge_api;  // ship database indices, not target longs
   uint64_t n_compares = 0, n_cand = 0;
   int64_t hit_off = 0, pos_total = 0;
   bool with_pos = false;
@@ -158,13 +160,17 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
     }
     n_compares += r.n_compares; n_cand += r.n_candidate_hits;
     const int64_t H = r.n_hits;
-    if ((rc = grow_pinned(c, o->targets, (size_t)hit_off * 8, (size_t)(hit_off + H + 1) * 8)) ||
+    if ((rc = compact ? grow_pinned(c, o->tidx, (size_t)hit_off * 4, (size_t)(hit_off + H + 1) * 4)
+                      : grow_pinned(c, o->targets, (size_t)hit_off * 8, (size_t)(hit_off + H + 1) * 8)) ||
         (rc = grow_pinned(c, o->mm, (size_t)hit_off, (size_t)(hit_off + H + 1))) ||
         (bulge_api && (rc = grow_pinned(c, o->bulge, (size_t)hit_off, (size_t)(hit_off + H + 1)))))
       return fail(rc);
     // the compute stream is idle here (discover_on_device synchronises), so the slot's contents are final
     cudaError_t e = cudaMemcpyAsync(o->row_ptr.as<int64_t>() + g0, r.d_row_ptr, (gn + 1) * 8, cudaMemcpyDeviceToHost, cs);
-    if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->targets.as<uint64_t>() + hit_off, r.d_targets, H * 8, cudaMemcpyDeviceToHost, cs);
+    if (compact && !r.d_tidx) { set_error("compact hit lists are not available on this path"); return fail(FF_EUNSUPPORTED); }
+    if (e == cudaSuccess && H > 0)
+      e = compact ? cudaMemcpyAsync(o->tidx.as<uint32_t>() + hit_off, r.d_tidx, H * 4, cudaMemcpyDeviceToHost, cs)
+                  : cudaMemcpyAsync(o->targets.as<uint64_t>() + hit_off, r.d_targets, H * 8, cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->mm.as<uint8_t>() + hit_off, r.d_mismatches, H, cudaMemcpyDeviceToHost, cs);
     if (e == cudaSuccess && bulge_api && H > 0) {
       if (r.d_bulge) e = cudaMemcpyAsync(o->bulge.as<uint8_t>() + hit_off, r.d_bulge, H, cudaMemcpyDeviceToHost, cs);
@@ -200,7 +206,8 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   c->last = acc;
   ff_hits &h = o->pub;
   h.n_guides = G; h.n_hits = hit_off;
-  h.row_ptr = rp; h.targets = o->targets.as<uint64_t>(); h.mismatches = o->mm.as<uint8_t>();
+  h.row_ptr = rp; h.targets = compact ? nullptr : o->targets.as<uint64_t>(); h.mismatches = o->mm.as<uint8_t>();
+  h.target_index = compact ? o->tidx.as<uint32_t>() : nullptr;
   h.pos_ptr = with_pos ? o->pos_ptr.as<int64_t>() : nullptr;
   h.positions = with_pos ? o->positions.as<uint64_t>() : nullptr;
   h.total_count = o->total.as<int32_t>(); h.overflowed = o->ovf.as<uint8_t>();
@@ -209,6 +216,34 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   h.opaque = o;
   *out = &h;
   return FF_OK;
+}
+
+// A caller-built CSR (ff_score / ff_hit_aggregates read row_ptr[G] targets): row_ptr must start at 0, be monotone and
+// end at n_hits.
+static int check_csr(const ff_hits *h) {
+  const int64_t G = h->n_guides;
+  if (G < 0 || h->n_hits < 0 || !h->row_ptr || (h->n_hits > 0 && !h->targets)) { set_error("malformed hit list"); return FF_EINVAL; }
+  if (h->row_ptr[0] != 0 || h->row_ptr[G] != h->n_hits) { set_error("hit list: row_ptr does not span [0, n_hits]"); return FF_EINVAL; }
+  for (int64_t g = 0; g < G; ++g)
+    if (h->row_ptr[g + 1] < h->row_ptr[g]) { set_error("hit list: row_ptr is not monotone at row %lld", (long long)g); return FF_EINVAL; }
+  return FF_OK;
+}
+
+// No exception crosses the C ABI: host allocations are sized from file contents and caller arguments.
+template <typename F>
+static int guarded(F &&f) noexcept {
+  try {
+    return f();
+  } catch (const std::bad_alloc &) {
+    set_error("out of host memory");
+    return FF_ENOMEM;
+  } catch (const std::exception &e) {
+    set_error("internal error: %s", e.what());
+    return FF_EIO;
+  } catch (...) {
+    set_error("internal error");
+    return FF_EIO;
+  }
 }
 
 }  // namespace ff
@@ -221,36 +256,38 @@ int ff_abi_version(void) { return 2; }
 const char *ff_last_error(void) { return g_err; }
 
 int ff_create(ff_ctx **out, int device_id) {
-  if (!out) { set_error("null out pointer"); return FF_EINVAL; }
-  *out = nullptr;
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n <= 0) {
-    set_error("no CUDA device available (%s); libflashfry_b200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    return FF_ENODEVICE;
-  }
-  if (device_id < 0 || device_id >= n) { set_error("device %d out of range (0..%d)", device_id, n - 1); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(device_id));
-  ff_ctx *c = new (std::nothrow) ff_ctx();
-  if (!c) { set_error("out of host memory"); return FF_ENOMEM; }
-  c->device = device_id;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-  e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
-  c->stream = c->own_stream;
-  e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
-  for (auto &ev : c->slot_copied) {
-    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
-  }
-  for (auto &ev : c->ev) {
-    e = cudaEventCreate(&ev);
-    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
-  }
-  *out = c;
-  return FF_OK;
+  return guarded([&]() -> int {
+    if (!out) { set_error("null out pointer"); return FF_EINVAL; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+      set_error("no CUDA device available (%s); libflashfry_b200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+      return FF_ENODEVICE;
+    }
+    if (device_id < 0 || device_id >= n) { set_error("device %d out of range (0..%d)", device_id, n - 1); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(device_id));
+    ff_ctx *c = new (std::nothrow) ff_ctx();
+    if (!c) { set_error("out of host memory"); return FF_ENOMEM; }
+    c->device = device_id;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    c->stream = c->own_stream;
+    e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    for (auto &ev : c->slot_copied) {
+      e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+    }
+    for (auto &ev : c->ev) {
+      e = cudaEventCreate(&ev);
+      if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+    }
+    *out = c;
+    return FF_OK;
+  });
 }
 
 void ff_destroy(ff_ctx *c) {
@@ -259,13 +296,14 @@ void ff_destroy(ff_ctx *c) {
   cudaStreamSynchronize(c->stream);
   c->db.release();
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-  DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys, &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->out_tidx, &c->pos_cnt,
+  DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys, &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->pos_cnt,
                     &c->pos_ptr, &c->out_positions, &c->cfd_per_ot, &c->hsu_per_ot, &c->scratch_guides, &c->running, &c->active, &c->active2,
                     &c->act_flags, &c->seg_end, &c->kept_keys, &c->kept_sorted, &c->n_sel, &c->cell_ws, &c->idx32, &c->st_targets, &c->st_mm};
   for (DevBuf *b : bufs) b->release();
   c->h_status.release();
+  c->host_targets.release();
   for (auto &os : c->out) {
-    DevBuf *ob[] = {&os.row_ptr, &os.total_count, &os.overflowed, &os.out_targets, &os.out_mm, &os.out_bulge, &os.cfd_max, &os.cfd_spec, &os.hsu};
+    DevBuf *ob[] = {&os.row_ptr, &os.total_count, &os.overflowed, &os.out_targets, &os.out_mm, &os.out_tidx, &os.out_bulge, &os.cfd_max, &os.cfd_spec, &os.hsu};
     for (DevBuf *b : ob) b->release();
   }
   for (auto &ev : c->slot_copied) if (ev) cudaEventDestroy(ev);
@@ -276,79 +314,95 @@ void ff_destroy(ff_ctx *c) {
 }
 
 int ff_set_stream(ff_ctx *c, void *cuda_stream) {
-  if (!c) { set_error("null context"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  FF_CUDA(cudaStreamSynchronize(c->stream));
-  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
-  return FF_OK;
+  return guarded([&]() -> int {
+    if (!c) { set_error("null context"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    FF_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return FF_OK;
+  });
 }
 
 int ff_set_option(ff_ctx *c, const char *key, long long value) {
-  if (!c || !key) { set_error("null argument"); return FF_EINVAL; }
-  struct { const char *name; int *field; long long lo, hi; } table[] = {
-      {"scan_kernel", &c->opt.scan_kernel, 0, 2},       {"force_general", &c->opt.force_general, 0, 1},
-      {"window_cells", &c->opt.window_cells, 0, 64},    {"subbatch_min", &c->opt.subbatch_min, 1, 1 << 30},
-      {"subbatch_c1", &c->opt.subbatch_c1, 1, 98},      {"subbatch_c2", &c->opt.subbatch_c2, 2, 99},
-      {"group_sort", &c->opt.group_sort, 0, 1},         {"b_spi", &c->opt.b_spi, 0, 32},
-      {"split_a", &c->opt.split_a, 0, 12},              {"compact_hits", &c->opt.compact_hits, 0, 1},
-  };
-  for (auto &t : table)
-    if (strcmp(key, t.name) == 0) {
-      if (value < t.lo || value > t.hi) { set_error("option %s: value %lld out of range [%lld, %lld]", key, value, t.lo, t.hi); return FF_EINVAL; }
-      *t.field = (int)value;
-      return FF_OK;
-    }
-  set_error("unknown option %s", key);
-  return FF_EINVAL;
+  return guarded([&]() -> int {
+    if (!c || !key) { set_error("null argument"); return FF_EINVAL; }
+    struct { const char *name; int *field; long long lo, hi; } table[] = {
+        {"scan_kernel", &c->opt.scan_kernel, 0, 2},       {"force_general", &c->opt.force_general, 0, 1},
+        {"window_cells", &c->opt.window_cells, 0, 64},    {"subbatch_min", &c->opt.subbatch_min, 1, 1 << 30},
+        {"subbatch_c1", &c->opt.subbatch_c1, 1, 98},      {"subbatch_c2", &c->opt.subbatch_c2, 2, 99},
+        {"group_sort", &c->opt.group_sort, 0, 1},         {"b_spi", &c->opt.b_spi, 0, 32},
+        {"split_a", &c->opt.split_a, 0, 12},              {"compact_hits", &c->opt.compact_hits, 0, 1},
+    };
+    for (auto &t : table)
+      if (strcmp(key, t.name) == 0) {
+        if (value < t.lo || value > t.hi) { set_error("option %s: value %lld out of range [%lld, %lld]", key, value, t.lo, t.hi); return FF_EINVAL; }
+        *t.field = (int)value;
+        return FF_OK;
+      }
+    set_error("unknown option %s", key);
+    return FF_EINVAL;
+  });
 }
 
 int ff_load_database(ff_ctx *c, const char *db_path, const char *header_path) {
-  if (!c || !db_path) { set_error("null argument"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  std::string hp = header_path ? header_path : std::string(db_path) + ".header";  // BinaryHeader.headerExtension
-  return db_load_files(c, db_path, hp.c_str());
+  return guarded([&]() -> int {
+    if (!c || !db_path) { set_error("null argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    std::string hp = header_path ? header_path : std::string(db_path) + ".header";  // BinaryHeader.headerExtension
+    return db_load_files(c, db_path, hp.c_str());
+  });
 }
 
 int ff_save_image(ff_ctx *c, const char *image_path) {
-  if (!c || !image_path) { set_error("null argument"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  FF_CUDA(cudaStreamSynchronize(c->stream));
-  return db_save_image(c, image_path);
+  return guarded([&]() -> int {
+    if (!c || !image_path) { set_error("null argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    FF_CUDA(cudaStreamSynchronize(c->stream));
+    return db_save_image(c, image_path);
+  });
 }
 
 int ff_load_image(ff_ctx *c, const char *image_path) {
-  if (!c || !image_path) { set_error("null argument"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  return db_load_image(c, image_path);
+  return guarded([&]() -> int {
+    if (!c || !image_path) { set_error("null argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    return db_load_image(c, image_path);
+  });
 }
 
 int ff_load_database_arrays(ff_ctx *c, int enzyme_index, int bin_width, const uint64_t *targets, uint64_t n_targets,
                             const uint64_t *positions, uint64_t n_positions, const char *const *contigs, int n_contigs) {
-  if (!c || (!targets && n_targets)) { set_error("null argument"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  Pack pack;
-  FF_TRY(pack_from_index(enzyme_index, &pack));
-  std::vector<std::string> names;
-  for (int i = 0; contigs && i < n_contigs; ++i) names.push_back(contigs[i] ? contigs[i] : "");
-  return db_from_host_arrays(c, pack, bin_width, targets, n_targets, positions, n_positions, names);
+  return guarded([&]() -> int {
+    if (!c || (!targets && n_targets)) { set_error("null argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    Pack pack;
+    FF_TRY(pack_from_index(enzyme_index, &pack));
+    std::vector<std::string> names;
+    for (int i = 0; contigs && i < n_contigs; ++i) names.push_back(contigs[i] ? contigs[i] : "");
+    return db_from_host_arrays(c, pack, bin_width, targets, n_targets, positions, n_positions, names);
+  });
 }
 
 int ff_synth_database(ff_ctx *c, int enzyme_index, uint64_t n_targets, uint64_t seed) {
-  if (!c) { set_error("null context"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  Pack pack;
-  FF_TRY(pack_from_index(enzyme_index, &pack));
-  return db_synth(c, pack, n_targets, seed);
+  return guarded([&]() -> int {
+    if (!c) { set_error("null context"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    Pack pack;
+    FF_TRY(pack_from_index(enzyme_index, &pack));
+    return db_synth(c, pack, n_targets, seed);
+  });
 }
 
 int ff_db_info(const ff_ctx *c, ff_db_info_t *o) {
-  if (!c || !o) { set_error("null argument"); return FF_EINVAL; }
-  if (!c->db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
-  const Database &d = c->db;
-  o->enzyme_index = d.pack.enzyme_index; o->bin_width = d.bin_width; o->scan_len = d.pack.scan_len; o->pam_len = d.pack.pam_len;
-  o->five_prime_pam = d.pack.five_prime; o->cmp_mask = d.pack.cmp_mask; o->n_targets = d.n_targets; o->n_positions = d.n_positions;
-  o->n_contigs = (int)d.contigs.size(); o->seed_split_a = d.A.key_bases; o->device_bytes = d.device_bytes;
-  return FF_OK;
+  return guarded([&]() -> int {
+    if (!c || !o) { set_error("null argument"); return FF_EINVAL; }
+    if (!c->db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
+    const Database &d = c->db;
+    o->enzyme_index = d.pack.enzyme_index; o->bin_width = d.bin_width; o->scan_len = d.pack.scan_len; o->pam_len = d.pack.pam_len;
+    o->five_prime_pam = d.pack.five_prime; o->cmp_mask = d.pack.cmp_mask; o->n_targets = d.n_targets; o->n_positions = d.n_positions;
+    o->n_contigs = (int)d.contigs.size(); o->seed_split_a = d.A.key_bases; o->device_bytes = d.device_bytes;
+    return FF_OK;
+  });
 }
 
 const char *ff_db_contig(const ff_ctx *c, int contig_id) {
@@ -357,27 +411,83 @@ const char *ff_db_contig(const ff_ctx *c, int contig_id) {
 }
 
 int ff_db_copy_targets(ff_ctx *c, uint64_t first, uint64_t n, uint64_t *out) {
-  if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
-  if (!c->db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
-  if (first + n > c->db.n_targets) { set_error("target range out of bounds"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  FF_CUDA(cudaMemcpy(out, c->db.d_targets + first, n * 8, cudaMemcpyDeviceToHost));
-  return FF_OK;
+  return guarded([&]() -> int {
+    if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+    if (!c->db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
+    if (first + n > c->db.n_targets) { set_error("target range out of bounds"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    FF_CUDA(cudaMemcpy(out, c->db.d_targets + first, n * 8, cudaMemcpyDeviceToHost));
+    return FF_OK;
+  });
 }
 
 int ff_discover(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions, ff_hits **out) {
-  return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, 0, out, nullptr, nullptr, nullptr);
+  return guarded([&]() -> int {
+    return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, 0, out, nullptr, nullptr, nullptr);
+  });
 }
 
 int ff_discover_score(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int want_positions,
                       uint32_t metrics, ff_hits **out, double *cfd_max, double *cfd_spec, double *hsu) {
-  return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, metrics, out, cfd_max, cfd_spec, hsu);
+  return guarded([&]() -> int {
+    return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, metrics, out, cfd_max, cfd_spec, hsu);
+  });
 }
 
 int ff_discover_bulge(ff_ctx *c, const uint64_t *guides, int64_t n_guides, int max_mm, int max_ot, int bulge_flags, int want_positions,
                       ff_hits **out) {
-  if (bulge_flags & ~(FF_BULGE_RNA | FF_BULGE_DNA)) { set_error("unknown bulge flag"); return FF_EINVAL; }
-  return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, 0, out, nullptr, nullptr, nullptr, bulge_flags, true);
+  return guarded([&]() -> int {
+    if (bulge_flags & ~(FF_BULGE_RNA | FF_BULGE_DNA)) { set_error("unknown bulge flag"); return FF_EINVAL; }
+    return discover_host(c, guides, n_guides, max_mm, max_ot, want_positions, 0, out, nullptr, nullptr, nullptr, bulge_flags, true);
+  });
+}
+
+const uint64_t *ff_db_host_targets(ff_ctx *c) {
+  if (!c || !c->db.resident) { set_error("no database resident in this context"); return nullptr; }
+  if (c->host_targets.p && c->host_targets_n == c->db.n_targets) return c->host_targets.as<uint64_t>();
+  if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+  if (c->host_targets.reserve((c->db.n_targets + 1) * 8) != FF_OK) return nullptr;
+  if (cudaMemcpy(c->host_targets.p, c->db.d_targets, c->db.n_targets * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("copy of the target array to the host failed");
+    return nullptr;
+  }
+  c->host_targets_n = c->db.n_targets;
+  return c->host_targets.as<uint64_t>();
+}
+
+int ff_hits_resolve(ff_ctx *c, ff_hits *h) {
+  return guarded([&]() -> int {
+    if (!c || !h || !h->opaque) { set_error("null argument"); return FF_EINVAL; }
+    if (h->targets || h->n_hits == 0) return FF_OK;
+    if (!h->target_index) { set_error("hit list carries neither targets nor indices"); return FF_EINVAL; }
+    const uint64_t *mirror = ff_db_host_targets(c);
+    if (!mirror) return FF_ENOMEM;
+    HitsOwner *o = static_cast<HitsOwner *>(h->opaque);
+    FF_TRY(o->targets.reserve((size_t)(h->n_hits + 1) * 8));
+    uint64_t *out = o->targets.as<uint64_t>();
+    const uint32_t *ix = h->target_index;
+    const int64_t H = h->n_hits;
+    const uint64_t n_t = c->host_targets_n;
+    unsigned nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (H < 200000) nth = 1;
+    std::vector<int> bad(nth, 0);
+    auto work = [&](unsigned w) {
+      const int64_t lo = H * w / nth, hi = H * (w + 1) / nth;
+      for (int64_t i = lo; i < hi; ++i) {
+        if (i + 16 < hi) __builtin_prefetch(mirror + ix[i + 16]);
+        if (ix[i] >= n_t) { bad[w] = 1; out[i] = 0; } else out[i] = mirror[ix[i]];
+      }
+    };
+    if (nth == 1) work(0);
+    else {
+      std::vector<std::thread> pool;
+      for (unsigned w = 0; w < nth; ++w) pool.emplace_back(work, w);
+      for (auto &t : pool) t.join();
+    }
+    for (int b : bad) if (b) { set_error("hit list holds a database index out of range"); return FF_EINVAL; }
+    h->targets = out;
+    return FF_OK;
+  });
 }
 
 void ff_hits_free(ff_hits *h) {
@@ -387,102 +497,126 @@ void ff_hits_free(ff_hits *h) {
 
 int ff_score(ff_ctx *c, const uint64_t *guides, const ff_hits *hits, uint32_t metrics, double *cfd_max, double *cfd_spec,
              double *hsu, double *per_ot_cfd) {
-  if (!c || !hits || (!guides && hits->n_guides > 0)) { set_error("null argument"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  const int64_t G = hits->n_guides;
-  if (G <= 0 || !metrics) return FF_OK;
-  const int64_t H = hits->row_ptr[G];
-  cudaStream_t st = c->stream;
-  FF_TRY(c->scratch_guides.reserve(G * 8));
-  ff_ctx::OutSlot &os = c->out[0];
-  FF_TRY(os.row_ptr.reserve((G + 1) * 8));
-  FF_TRY(os.out_targets.reserve((H + 1) * 8));
-  FF_TRY(os.cfd_max.reserve(G * 8));
-  FF_TRY(os.cfd_spec.reserve(G * 8));
-  FF_TRY(os.hsu.reserve(G * 8));
-  FF_TRY(c->cfd_per_ot.reserve((H + 1) * 8));
-  FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, G * 8, cudaMemcpyHostToDevice, st));
-  FF_CUDA(cudaMemcpyAsync(os.row_ptr.p, hits->row_ptr, (G + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (H > 0) FF_CUDA(cudaMemcpyAsync(os.out_targets.p, hits->targets, H * 8, cudaMemcpyHostToDevice, st));
-  FF_TRY(score_on_device(c, c->scratch_guides.as<uint64_t>(), G, os.row_ptr.as<int64_t>(), os.out_targets.as<uint64_t>(), H, metrics,
-                         os.cfd_max.as<double>(), os.cfd_spec.as<double>(), os.hsu.as<double>(), c->cfd_per_ot.as<double>()));
-  if (cfd_max && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_max, os.cfd_max.p, G * 8, cudaMemcpyDeviceToHost, st));
-  if (cfd_spec && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_spec, os.cfd_spec.p, G * 8, cudaMemcpyDeviceToHost, st));
-  if (hsu && (metrics & FF_METRIC_HSU2013)) FF_CUDA(cudaMemcpyAsync(hsu, os.hsu.p, G * 8, cudaMemcpyDeviceToHost, st));
-  if (per_ot_cfd && (metrics & FF_METRIC_CFD) && H > 0) FF_CUDA(cudaMemcpyAsync(per_ot_cfd, c->cfd_per_ot.p, H * 8, cudaMemcpyDeviceToHost, st));
-  FF_CUDA(cudaStreamSynchronize(st));
-  FF_CUDA(cudaGetLastError());
-  return FF_OK;
+  // the enzyme of the resident database; without one the caller vouches for 23-bp Cas9 longs (ff_score_enzyme says it)
+  return ff_score_enzyme(c, c && c->db.resident ? c->db.pack.enzyme_index : 3, guides, hits, metrics, cfd_max, cfd_spec, hsu, per_ot_cfd);
+}
+
+int ff_score_enzyme(ff_ctx *c, int enzyme_index, const uint64_t *guides, const ff_hits *hits, uint32_t metrics, double *cfd_max,
+                    double *cfd_spec, double *hsu, double *per_ot_cfd) {
+  return guarded([&]() -> int {
+    if (!c || !hits || (!guides && hits->n_guides > 0)) { set_error("null argument"); return FF_EINVAL; }
+    Pack pack;
+    FF_TRY(pack_from_index(enzyme_index, &pack));
+    if (!(pack.scan_len == 23 && !pack.five_prime)) {  // validOverEnzyme (Doench2016CFDScore.scala:96-98)
+      set_error("CFD / Hsu2013 are only valid for 23-bp Cas9 parameter packs");
+      return FF_EUNSUPPORTED;
+    }
+    FF_TRY(check_csr(hits));
+    FF_CUDA(cudaSetDevice(c->device));
+    const int64_t G = hits->n_guides;
+    if (G <= 0 || !metrics) return FF_OK;
+    const int64_t H = hits->row_ptr[G];
+    cudaStream_t st = c->stream;
+    FF_TRY(c->scratch_guides.reserve(G * 8));
+    ff_ctx::OutSlot &os = c->out[0];
+    FF_TRY(os.row_ptr.reserve((G + 1) * 8));
+    FF_TRY(os.out_targets.reserve((H + 1) * 8));
+    FF_TRY(os.cfd_max.reserve(G * 8));
+    FF_TRY(os.cfd_spec.reserve(G * 8));
+    FF_TRY(os.hsu.reserve(G * 8));
+    FF_TRY(c->cfd_per_ot.reserve((H + 1) * 8));
+    FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, G * 8, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(os.row_ptr.p, hits->row_ptr, (G + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (H > 0) FF_CUDA(cudaMemcpyAsync(os.out_targets.p, hits->targets, H * 8, cudaMemcpyHostToDevice, st));
+    FF_TRY(score_on_device(c, c->scratch_guides.as<uint64_t>(), G, os.row_ptr.as<int64_t>(), os.out_targets.as<uint64_t>(), H, metrics,
+                           os.cfd_max.as<double>(), os.cfd_spec.as<double>(), os.hsu.as<double>(), c->cfd_per_ot.as<double>()));
+    if (cfd_max && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_max, os.cfd_max.p, G * 8, cudaMemcpyDeviceToHost, st));
+    if (cfd_spec && (metrics & FF_METRIC_CFD)) FF_CUDA(cudaMemcpyAsync(cfd_spec, os.cfd_spec.p, G * 8, cudaMemcpyDeviceToHost, st));
+    if (hsu && (metrics & FF_METRIC_HSU2013)) FF_CUDA(cudaMemcpyAsync(hsu, os.hsu.p, G * 8, cudaMemcpyDeviceToHost, st));
+    if (per_ot_cfd && (metrics & FF_METRIC_CFD) && H > 0) FF_CUDA(cudaMemcpyAsync(per_ot_cfd, c->cfd_per_ot.p, H * 8, cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    FF_CUDA(cudaGetLastError());
+    return FF_OK;
+  });
 }
 
 int ff_hit_aggregates(ff_ctx *c, int enzyme_index, const uint64_t *guides, const ff_hits *hits, int32_t *closest,
                       int32_t *closest_count, int32_t *hist, int32_t *in_genome) {
-  if (!c || !hits || (!guides && hits->n_guides > 0)) { set_error("null argument"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  Pack pack;
-  FF_TRY(pack_from_index(enzyme_index, &pack));
-  const int64_t G = hits->n_guides;
-  if (G <= 0) return FF_OK;
-  const int64_t H = hits->row_ptr[G];
-  cudaStream_t st = c->stream;
-  ff_ctx::OutSlot &os = c->out[0];
-  FF_TRY(c->scratch_guides.reserve(G * 8));
-  FF_TRY(os.row_ptr.reserve((G + 1) * 8));
-  FF_TRY(os.out_targets.reserve((H + 1) * 8));
-  FF_TRY(os.total_count.reserve(G * 8 * 4));  // 8 int32 per guide
-  FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, G * 8, cudaMemcpyHostToDevice, st));
-  FF_CUDA(cudaMemcpyAsync(os.row_ptr.p, hits->row_ptr, (G + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (H > 0) FF_CUDA(cudaMemcpyAsync(os.out_targets.p, hits->targets, H * 8, cudaMemcpyHostToDevice, st));
-  FF_TRY(hit_aggregates_on_device(c, c->scratch_guides.as<uint64_t>(), G, os.row_ptr.as<int64_t>(), os.out_targets.as<uint64_t>(),
-                                  pack.cmp_mask, os.total_count.as<int32_t>()));
-  std::vector<int32_t> tmp((size_t)G * 8);
-  FF_CUDA(cudaMemcpyAsync(tmp.data(), os.total_count.p, (size_t)G * 8 * 4, cudaMemcpyDeviceToHost, st));
-  FF_CUDA(cudaStreamSynchronize(st));
-  for (int64_t g = 0; g < G; ++g) {
-    const int32_t *o = tmp.data() + g * 8;
-    if (closest) closest[g] = o[0];
-    if (closest_count) closest_count[g] = o[1];
-    if (hist) for (int m = 0; m < 5; ++m) hist[g * 5 + m] = o[2 + m];
-    if (in_genome) in_genome[g] = o[7];
-  }
-  return FF_OK;
+  return guarded([&]() -> int {
+    if (!c || !hits || (!guides && hits->n_guides > 0)) { set_error("null argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    Pack pack;
+    FF_TRY(pack_from_index(enzyme_index, &pack));
+    FF_TRY(check_csr(hits));
+    const int64_t G = hits->n_guides;
+    if (G <= 0) return FF_OK;
+    const int64_t H = hits->row_ptr[G];
+    cudaStream_t st = c->stream;
+    ff_ctx::OutSlot &os = c->out[0];
+    FF_TRY(c->scratch_guides.reserve(G * 8));
+    FF_TRY(os.row_ptr.reserve((G + 1) * 8));
+    FF_TRY(os.out_targets.reserve((H + 1) * 8));
+    FF_TRY(os.total_count.reserve(G * 8 * 4));  // 8 int32 per guide
+    FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, G * 8, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(os.row_ptr.p, hits->row_ptr, (G + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (H > 0) FF_CUDA(cudaMemcpyAsync(os.out_targets.p, hits->targets, H * 8, cudaMemcpyHostToDevice, st));
+    FF_TRY(hit_aggregates_on_device(c, c->scratch_guides.as<uint64_t>(), G, os.row_ptr.as<int64_t>(), os.out_targets.as<uint64_t>(),
+                                    pack.cmp_mask, os.total_count.as<int32_t>()));
+    std::vector<int32_t> tmp((size_t)G * 8);
+    FF_CUDA(cudaMemcpyAsync(tmp.data(), os.total_count.p, (size_t)G * 8 * 4, cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    for (int64_t g = 0; g < G; ++g) {
+      const int32_t *o = tmp.data() + g * 8;
+      if (closest) closest[g] = o[0];
+      if (closest_count) closest_count[g] = o[1];
+      if (hist) for (int m = 0; m < 5; ++m) hist[g * 5 + m] = o[2 + m];
+      if (in_genome) in_genome[g] = o[7];
+    }
+    return FF_OK;
+  });
 }
 
 int ff_discover_device(ff_ctx *c, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot, uint32_t metrics,
                        ff_device_result *out) {
-  if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  DeviceResult r;
-  FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, 0, 0, &r));
-  FF_TRY(score_slot(c, d_guides, r, metrics, 0));
-  out->d_bulge = nullptr;
-  out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
-  out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
-  out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
-  out->d_cfd_max = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_max.as<double>() : nullptr;
-  out->d_cfd_specificity = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_spec.as<double>() : nullptr;
-  out->d_hsu2013 = (metrics & FF_METRIC_HSU2013) ? c->out[0].hsu.as<double>() : nullptr;
-  return FF_OK;
+  return guarded([&]() -> int {
+    if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    DeviceResult r;
+    FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, 0, 0, &r));
+    FF_TRY(score_slot(c, d_guides, r, metrics, 0));
+    out->d_bulge = nullptr;
+    out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
+    out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
+    out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
+    out->d_cfd_max = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_max.as<double>() : nullptr;
+    out->d_cfd_specificity = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_spec.as<double>() : nullptr;
+    out->d_hsu2013 = (metrics & FF_METRIC_HSU2013) ? c->out[0].hsu.as<double>() : nullptr;
+    return FF_OK;
+  });
 }
 
 int ff_discover_bulge_device(ff_ctx *c, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot, int bulge_flags,
                              ff_device_result *out) {
-  if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
-  FF_CUDA(cudaSetDevice(c->device));
-  DeviceResult r;
-  FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, bulge_flags, 0, &r));
-  out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
-  out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
-  out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
-  out->d_cfd_max = out->d_cfd_specificity = out->d_hsu2013 = nullptr;
-  out->d_bulge = r.d_bulge;
-  return FF_OK;
+  return guarded([&]() -> int {
+    if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    DeviceResult r;
+    FF_TRY(discover_on_device(c, d_guides, n_guides, max_mm, max_ot, false, bulge_flags, 0, &r));
+    out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
+    out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
+    out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
+    out->d_cfd_max = out->d_cfd_specificity = out->d_hsu2013 = nullptr;
+    out->d_bulge = r.d_bulge;
+    return FF_OK;
+  });
 }
 
 int ff_last_timings(const ff_ctx *c, ff_timings *out) {
-  if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
-  *out = c->last;
-  return FF_OK;
+  return guarded([&]() -> int {
+    if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+    *out = c->last;
+    return FF_OK;
+  });
 }
 
 }  // extern "C"

@@ -126,8 +126,10 @@ struct ff_ctx {
   // ---- per-call workspaces (grow-only) ----
   ff::DevBuf cub_tmp;
   ff::DevBuf hit_keys, hit_keys_sorted, counters;
-  ff::DevBuf seg_start, n_keep, out_tidx;
+  ff::DevBuf seg_start, n_keep;
   ff::DevBuf idx32, st_targets, st_mm;  // per-guide ordering: scattered database indices, rows staged at their segment
+  ff::HostBuf host_targets;             // host mirror of db.d_targets (ff_db_host_targets), made on first use
+  uint64_t host_targets_n = 0;
   ff::HostBuf h_status;                 // pinned mirror of the device status words (one D2H + one sync per call)
   ff::DevBuf pos_cnt, pos_ptr, out_positions;
   ff::DevBuf cfd_per_ot, hsu_per_ot;
@@ -137,7 +139,7 @@ struct ff_ctx {
   ff::DevBuf cell_ws;  // bin scan: guides listed by bin, (guide, seed) pairs sorted by bucket, counters
   // results of a discover call; two sets so that the D2H of one guide sub-batch overlaps the scan of the next
   struct OutSlot {
-    ff::DevBuf row_ptr, total_count, overflowed, out_targets, out_mm, out_bulge, cfd_max, cfd_spec, hsu;
+    ff::DevBuf row_ptr, total_count, overflowed, out_targets, out_mm, out_tidx, out_bulge, cfd_max, cfd_spec, hsu;
   } out[2];
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t slot_copied[2] = {nullptr, nullptr};  // D2H of the slot's previous contents has finished

@@ -310,6 +310,7 @@ int db_build_cell_offsets(ff_ctx *ctx) {
 int db_from_host_arrays(ff_ctx *ctx, const Pack &pack, int bin_width, const uint64_t *targets, uint64_t n_targets,
                         const uint64_t *positions, uint64_t n_positions, const std::vector<std::string> &contigs) {
   ctx->db.release();
+  ctx->host_targets_n = 0;  // the host mirror of the previous database is stale
   Database &db = ctx->db;
   db.pack = pack; db.bin_width = bin_width; db.n_targets = n_targets; db.n_positions = positions ? n_positions : 0;
   db.contigs = contigs;
@@ -401,6 +402,7 @@ static int scan_members(const std::vector<uint8_t> &raw, std::vector<Member> *ms
       return FF_EFORMAT;
     }
     const size_t xlen = raw[off + 10] | (raw[off + 11] << 8);
+    if (off + 12 + xlen + 8 > raw.size()) { set_error("truncated BGZF member at byte %zu", off); return FF_EFORMAT; }
     size_t p = off + 12, end = off + 12 + xlen;
     long bsize = -1;
     while (p + 4 <= end) {
@@ -408,7 +410,7 @@ static int scan_members(const std::vector<uint8_t> &raw, std::vector<Member> *ms
       if (raw[p] == 'B' && raw[p + 1] == 'C' && slen == 2) bsize = raw[p + 4] | (raw[p + 5] << 8);
       p += 4 + slen;
     }
-    if (bsize < 0 || off + bsize + 1 > raw.size()) { set_error("BGZF member without a valid BC field at byte %zu", off); return FF_EFORMAT; }
+    if (bsize < 0 || off + bsize + 1 > raw.size() || (size_t)bsize + 1 < 12 + xlen + 8) { set_error("BGZF member without a valid BC field at byte %zu", off); return FF_EFORMAT; }
     Member m;
     m.off = off; m.len = (size_t)bsize + 1; m.hdr = 12 + xlen;
     const uint8_t *tail = raw.data() + off + m.len - 4;
@@ -591,7 +593,14 @@ int db_load_image(ff_ctx *ctx, const char *path) {
   }
   Pack pack;
   if (pack_from_index(h.enzyme_index, &pack) != FF_OK) { fclose(f); return FF_EFORMAT; }
-  if (h.contig_bytes > (1u << 28) || h.n_targets > 0xFFFF0000ull) { fclose(f); set_error("implausible sizes in image %s", path); return FF_EFORMAT; }
+  {  // sizes come from the file: check them against its length before allocating anything
+    fseek(f, 0, SEEK_END);
+    const unsigned long long flen = (unsigned long long)ftell(f);
+    fseek(f, (long)sizeof h, SEEK_SET);
+    const bool ok_sizes = h.contig_bytes <= (1u << 28) && h.n_targets <= 0xFFFF0000ull && h.n_positions <= h.n_targets * 32767ull &&
+                          sizeof h + h.contig_bytes + 8ull * h.n_targets + 8ull * h.n_positions <= flen;
+    if (!ok_sizes) { fclose(f); set_error("implausible sizes in image %s", path); return FF_EFORMAT; }
+  }
   std::string names(h.contig_bytes, '\0');
   std::vector<uint64_t> targets(h.n_targets + 1), positions(h.n_positions + 1);
   bool ok = h.contig_bytes == 0 || fread(&names[0], 1, h.contig_bytes, f) == h.contig_bytes;
@@ -645,6 +654,7 @@ int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed) {
   if (pack.five_prime) { set_error("synthetic databases are spCas9-family only"); return FF_EUNSUPPORTED; }
   if (n_targets == 0 || n_targets > 3000000000ull) { set_error("bad synthetic database size"); return FF_EINVAL; }
   ctx->db.release();
+  ctx->host_targets_n = 0;
   Database &db = ctx->db;
   cudaStream_t st = ctx->stream;
   const int random_bits = 2 * (pack.scan_len - 2);                     // protospacer + N

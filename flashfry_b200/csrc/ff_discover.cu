@@ -139,6 +139,9 @@ __device__ __forceinline__ void verify_chunk(const ScanParams &p, const WarpHits
 #ifndef FF_GROUP
 #define FF_GROUP 4
 #endif
+#ifndef FF_TAIL
+#define FF_TAIL 4
+#endif
 
 // One pass (A or B) of one work item: `n` (<= 32) seeds starting at `seed0`.  Lanes look the buckets up (one batched
 // index access per 32 seeds); the warp then streams the buckets FF_GROUP at a time: the first 128-entry chunk of every
@@ -235,8 +238,6 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
       const uint32_t jlo = __shfl_sync(0xffffffffu, lo, l0 + j), jhi = __shfl_sync(0xffffffffu, hi, l0 + j);
       if (jhi - (jlo & ~3u) <= 128u) continue;  // warp-uniform
       const int bud = __shfl_sync(0xffffffffu, budget, l0 + j);
-#ifndef FF_TAIL
-#define FF_TAIL 4
       for (uint32_t c2 = (jlo & ~3u) + lane4 + 128u; c2 < jhi; c2 += 128u * FF_TAIL) {
         uint4 w[FF_TAIL];
 #pragma unroll
@@ -250,7 +251,6 @@ __device__ __forceinline__ void scan_seeds(const ScanParams &p, const SeedSide &
       }
     }
   }
-#endif
   __syncwarp();
   if (*wh.count >= kHW / 2) flush_warp_hits(wh, lane);
 }
@@ -611,7 +611,7 @@ static int gather_positions(ff_ctx *ctx, ff_ctx::OutSlot &os, bool want_position
     FF_CUDA(cudaStreamSynchronize(st));
     FF_TRY(ctx->out_positions.reserve((n_pos > 0 ? n_pos : 1) * 8));
     if (n_hits > 0) {
-      k_gather_positions<<<blocks_for(n_hits * 32, 256), 256, 0, st>>>(ctx->out_tidx.as<uint32_t>(), ctx->pos_ptr.as<int64_t>(), db.d_pos_off,
+      k_gather_positions<<<blocks_for(n_hits * 32, 256), 256, 0, st>>>(os.out_tidx.as<uint32_t>(), ctx->pos_ptr.as<int64_t>(), db.d_pos_off,
                                                                       db.d_positions, n_hits, ctx->out_positions.as<uint64_t>());
       (*launches)++;
     }
@@ -742,7 +742,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     FF_TRY(ctx->hit_keys.reserve(cap * 8));
     FF_TRY(os.out_targets.reserve((cap + 1) * 8));
     FF_TRY(os.out_mm.reserve(cap + 1));
-    FF_TRY(ctx->out_tidx.reserve((cap + 1) * 4));
+    FF_TRY(os.out_tidx.reserve((cap + 1) * 4));
     sp.hits = ctx->hit_keys.as<uint64_t>(); sp.hit_cap = cap;
     FF_CUDA(cudaMemsetAsync(d_stt, 0, sizeof(PlainStatus), st));
     unsigned int *cnt = nullptr, *cursor = nullptr;
@@ -785,7 +785,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
       FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
       k_compact_rows<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), G, ctx->st_targets.as<uint64_t>(),
                                                              ctx->st_mm.as<uint8_t>(), ctx->idx32.as<uint32_t>(), os.out_targets.as<uint64_t>(),
-                                                             os.out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>(), d_stt);
+                                                             os.out_mm.as<uint8_t>(), os.out_tidx.as<uint32_t>(), d_stt);
       launches += 9;
       FF_CUDA(cudaEventRecord(ctx->ev[4], st));
     }
@@ -833,7 +833,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     FF_CUDA(cudaStreamSynchronize(st));
     if (G > 0 && n_hits > 0) {
       k_gather<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), db.d_targets, d_guides,
-                                                       db.pack.cmp_mask, G, tbits, os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), ctx->out_tidx.as<uint32_t>());
+                                                       db.pack.cmp_mask, G, tbits, os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), os.out_tidx.as<uint32_t>());
       launches++;
     }
   }
@@ -864,7 +864,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   res->d_row_ptr = os.row_ptr.as<int64_t>(); res->d_targets = os.out_targets.as<uint64_t>();
   res->d_mismatches = os.out_mm.as<uint8_t>(); res->d_total_count = os.total_count.as<int32_t>();
   res->d_overflowed = os.overflowed.as<uint8_t>(); res->d_bulge = nullptr;
-  res->d_tidx = ctx->out_tidx.as<uint32_t>();
+  res->d_tidx = os.out_tidx.as<uint32_t>();
   return FF_OK;
 }
 

@@ -504,11 +504,11 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
   FF_TRY(os.out_targets.reserve(Hp * 8));
   FF_TRY(os.out_mm.reserve(Hp));
   FF_TRY(os.out_bulge.reserve(Hp));
-  FF_TRY(ctx->out_tidx.reserve(Hp * 4));
+  FF_TRY(os.out_tidx.reserve(Hp * 4));
   if (G > 0 && n_hits > 0) {
     k_gather_general<<<blocks_for(G * 32, 256), 256, 0, st>>>(kept, os.row_ptr.as<int64_t>(), db.d_targets, d_guides, db.proto_shift, P, bulge_flags, G, tbits,
                                                              os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), os.out_bulge.as<uint8_t>(),
-                                                             ctx->out_tidx.as<uint32_t>());
+                                                             os.out_tidx.as<uint32_t>());
     launches++;
   }
   int64_t n_pos = 0;
@@ -533,6 +533,7 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
   res->d_row_ptr = os.row_ptr.as<int64_t>(); res->d_targets = os.out_targets.as<uint64_t>();
   res->d_mismatches = os.out_mm.as<uint8_t>(); res->d_bulge = os.out_bulge.as<uint8_t>();
   res->d_total_count = os.total_count.as<int32_t>(); res->d_overflowed = os.overflowed.as<uint8_t>();
+  res->d_tidx = os.out_tidx.as<uint32_t>();
   return FF_OK;
 }
 

@@ -129,7 +129,18 @@ typedef struct ff_hits {
   void *opaque;
   const uint8_t *bulge;        /* [n_hits], ff_discover_bulge only (else NULL): 0 = no bulge, 0x40|q = RNA bulge at guide
                                   base q, 0x80|q = DNA bulge at genomic base q; mismatches[] then counts the aligned pairs */
+  const uint32_t *target_index; /* [n_hits] with option compact_hits = 1 (else NULL): the hit's index in database order;
+                                  targets[i] == ff_db_host_targets(ctx)[target_index[i]].  targets stays NULL until
+                                  ff_hits_resolve fills it */
 } ff_hits;
+
+/* Compact hit lists (option compact_hits): a hit's target long is 8 bytes, its database index 4; the device-to-host copy
+ * of the hit list is the slowest part of a large discover call, so a host that can look the long up itself (the JVM glue
+ * does, when it builds a CRISPRHit) asks for indices.  ff_db_host_targets returns a host mirror of the resident target
+ * array (database order, made on first use, owned by the context; NULL on failure); ff_hits_resolve fills
+ * hits->targets from it on all host threads. */
+const uint64_t *ff_db_host_targets(ff_ctx *ctx);
+int ff_hits_resolve(ff_ctx *ctx, ff_hits *hits);
 
 /* guides: BitEncoding.bitEncodeString(bases, count = 1) longs in ResultsAggregator order (any order is accepted;
  * rows come back in the same order).  max_mismatch >= 0, max_off_targets >= 0. */
@@ -160,6 +171,11 @@ int ff_discover_bulge(ff_ctx *ctx, const uint64_t *guides, int64_t n_guides, int
  * host prints "NA" (scoring/ScoreModel.scala:125-128). */
 int ff_score(ff_ctx *ctx, const uint64_t *guides, const ff_hits *hits, uint32_t metrics, double *cfd_max,
              double *cfd_specificity, double *hsu2013, double *per_ot_cfd);
+
+/* The same with the enzyme stated by the caller (FlashFry's standalone `score` knows it from the --database header):
+ * ff_score uses the resident database's enzyme, or spCas9-NGG when no database is resident. */
+int ff_score_enzyme(ff_ctx *ctx, int enzyme_index, const uint64_t *guides, const ff_hits *hits, uint32_t metrics,
+                    double *cfd_max, double *cfd_specificity, double *hsu2013, double *per_ot_cfd);
 
 /* Integer aggregates over the same hit lists: scoring/ClosestHit.scala:43-76 ("minot": smallest non-zero mismatch
  * count, the summed occurrence count at that distance, the 0..4-mismatch occurrence histogram) and the in-genome count

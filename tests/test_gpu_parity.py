@@ -635,3 +635,35 @@ def test_bin_major_scan_oversized_bins_and_buckets(ff, oracle):
             with ctx.options(scan_kernel=1):
                 helpers.assert_hits_equal(ctx.discover(guides, 4, max_ot), ref)
         assert int(ref.row_ptr[-1]) > 10_000  # the planted guides really sit in the big bucket / bin
+
+
+def test_compact_hit_lists_resolve_to_the_same_rows(small_ctx, small_db, oracle):
+    """Option compact_hits: ff_discover ships 32-bit database indices instead of target longs (5 instead of 9 bytes per hit
+    over PCIe); ff_hits_resolve rebuilds the longs from the host mirror of the database.  Also across sub-batches."""
+    _, db, _ = small_db
+    targets = db.soa()[0]
+    guides = np.concatenate([helpers.random_guides(oracle, db.pack, 91, 200), helpers.planted_guides(db.pack, targets, 92, 300, max_subs=4)])
+    ref = oracle.discover_blocks(db, guides, 4, 2000)
+    for min_batch in (1_000_000, 100):
+        with small_ctx.options(compact_hits=1, subbatch_min=min_batch):
+            raw = small_ctx.discover(guides, 4, 2000)
+            full = small_ctx.discover(guides, 4, 2000, resolve=True)
+        assert raw.target_index is not None and len(raw.targets) == 0
+        assert (targets[raw.target_index] == ref.targets).all()
+        helpers.assert_hits_equal(full, ref)
+    helpers.assert_hits_equal(small_ctx.discover(guides, 4, 2000), ref)  # option off again: longs as before
+
+
+def test_score_rejects_malformed_hit_lists(ff, oracle):
+    """ff_score / ff_hit_aggregates read row_ptr[n_guides] targets from a caller-built CSR: a row_ptr that does not start at 0,
+    is not monotone or does not end at n_hits is refused (FF_EINVAL), as is an enzyme the scorers are not valid for."""
+    g = [oracle.encode("GAGTCCGAGCAGAAGAAGAAGGG")]
+    t = np.asarray([oracle.encode("GAGTCCGAGCAGAAGAAGAATGG")], np.uint64)
+    with ff.Context(0) as ctx:
+        ctx.score(g, [0, 1], t)
+        for bad in ([1, 1], [0, 2], [0, 0]):
+            with pytest.raises(ff.FlashFryError) as e:
+                ctx.score(g, bad, t)
+            assert e.value.code == -1
+        with pytest.raises(ff.FlashFryError):
+            ctx.score(g + g, [0, 1, 0], t)
