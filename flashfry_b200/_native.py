@@ -56,7 +56,9 @@ class FFTimings(C.Structure):
 # every symbol include/flashfry_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_set_option", "ff_load_database",
            "ff_save_image", "ff_load_image", "ff_load_database_arrays", "ff_synth_database", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
-           "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_db_host_targets", "ff_hits_resolve", "ff_score", "ff_score_enzyme", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings"]
+           "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_db_host_targets", "ff_hits_resolve", "ff_score", "ff_score_enzyme", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings",
+           "ff_multi_create", "ff_multi_destroy", "ff_multi_size", "ff_multi_ctx", "ff_multi_set_option", "ff_multi_load_database",
+           "ff_multi_synth_database", "ff_shard_range", "ff_multi_discover", "ff_multi_device_totals"]
 
 _lib = None
 
@@ -102,6 +104,20 @@ def lib():
                                     C.POINTER(C.POINTER(FFHits)), dp, dp, dp]
     L.ff_discover_device.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.POINTER(FFDeviceResult)]
     L.ff_last_timings.argtypes = [vp, C.POINTER(FFTimings)]
+    L.ff_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.ff_multi_destroy.argtypes = [vp]
+    L.ff_multi_destroy.restype = None
+    L.ff_multi_size.argtypes = [vp]
+    L.ff_multi_ctx.argtypes = [vp, C.c_int]
+    L.ff_multi_ctx.restype = vp
+    L.ff_multi_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    L.ff_multi_load_database.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.ff_multi_synth_database.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64]
+    L.ff_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, i64p, i64p]
+    L.ff_shard_range.restype = None
+    L.ff_multi_discover.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(FFHits)), i32p]
+    L.ff_multi_device_totals.argtypes = [vp, C.c_int]
+    L.ff_multi_device_totals.restype = vp
     _lib = L
     return L
 

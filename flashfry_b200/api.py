@@ -100,7 +100,7 @@ class Context:
         """Context manager: set options for a block, restore the defaults afterwards."""
         ctx = self
         defaults = {"scan_kernel": 0, "force_general": 0, "window_cells": 0, "subbatch_min": 20000, "subbatch_c1": 65,
-                    "subbatch_c2": 90, "group_sort": 1, "b_spi": 0, "split_a": 0, "compact_hits": 0}
+                    "subbatch_c2": 90, "group_sort": 1, "trace": 0, "b_spi": 0, "split_a": 0, "compact_hits": 0}
 
         class _O:
             def __enter__(self_o):
@@ -231,3 +231,64 @@ class Context:
         t = N.FFTimings()
         N.check(N.lib().ff_last_timings(self._h, C.byref(t)))
         return t
+
+
+def shard_range(n_guides: int, n_shards: int, shard: int):
+    """ff_shard_range: (first, count) of a shard of the guide array (pure function of the C ABI)."""
+    first, count = C.c_int64(), C.c_int64()
+    N.lib().ff_shard_range(n_guides, n_shards, shard, C.byref(first), C.byref(count))
+    return int(first.value), int(count.value)
+
+
+class MultiContext:
+    """Several GPUs behind one process (ff_multi): guide-sharded discover + one NCCL all-gather of the totals."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        N.check(N.lib().ff_multi_create(C.byref(self._h), arr, len(devices)))
+        self.n = len(devices)
+
+    def close(self):
+        if self._h:
+            N.lib().ff_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, key: str, value: int):
+        N.check(N.lib().ff_multi_set_option(self._h, key.encode(), int(value)))
+
+    def synth_database(self, enzyme_index: int, n_targets: int, seed: int):
+        N.check(N.lib().ff_multi_synth_database(self._h, enzyme_index, n_targets, seed))
+
+    def load_database(self, db_path: str, header_path: Optional[str] = None):
+        N.check(N.lib().ff_multi_load_database(self._h, db_path.encode(), header_path.encode() if header_path else None))
+
+    def rank_timings(self, rank: int) -> N.FFTimings:
+        t = N.FFTimings()
+        N.check(N.lib().ff_last_timings(N.lib().ff_multi_ctx(self._h, rank), C.byref(t)))
+        return t
+
+    def discover_raw(self, guides_ptr, n_guides: int, max_mismatch: int, maximum_off_targets: int, totals: np.ndarray):
+        """The bare call (bench timing): hit lists are freed immediately, totals land in `totals` (int32[n_guides])."""
+        hp = (C.POINTER(N.FFHits) * self.n)()
+        N.check(N.lib().ff_multi_discover(self._h, guides_ptr, n_guides, max_mismatch, maximum_off_targets, 0, hp,
+                                          totals.ctypes.data_as(C.POINTER(C.c_int32))))
+        hits = sum(int(hp[r].contents.n_hits) for r in range(self.n))
+        for r in range(self.n):
+            N.lib().ff_hits_free(hp[r])
+        return hits
+
+    def discover(self, guides, max_mismatch: int = 4, maximum_off_targets: int = 2000, positions: bool = False):
+        """-> (list of per-shard Hits, all-gathered total_count int32[n_guides])."""
+        g = _u64(guides)
+        hp = (C.POINTER(N.FFHits) * self.n)()
+        totals = np.zeros(max(len(g), 1), np.int32)
+        N.check(N.lib().ff_multi_discover(self._h, g.ctypes.data_as(C.POINTER(C.c_uint64)), len(g), max_mismatch, maximum_off_targets,
+                                          int(positions), hp, totals.ctypes.data_as(C.POINTER(C.c_int32))))
+        return [_take_hits(hp[r]) for r in range(self.n)], totals[:len(g)]

@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libflashfry_b200.so")
 CLI = os.path.join(HERE, "flashfry_b200_cli")
 SELFTEST = os.path.join(HERE, "host_selftest")
 
-CU_SOURCES = ["ff_api.cu", "ff_db.cu", "ff_discover.cu", "ff_score.cu"]
+CU_SOURCES = ["ff_api.cu", "ff_db.cu", "ff_discover.cu", "ff_score.cu", "ff_multi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr"]
 
@@ -73,7 +73,7 @@ def build_variant(name: str, defines) -> str:
     with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
         list(ex.map(lambda c: _run(c, False), jobs))
     lib = os.path.join(out_dir, "libflashfry_b200.so")
-    _run([cc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-lpthread",
+    _run([cc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-lpthread", "-ldl",
                                                "-Xcompiler", "-fPIC", "-cudart", "static"], False)
     for o in objs:
         os.remove(o)
@@ -95,7 +95,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(lambda c: _run(c, verbose), jobs))
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in CU_SOURCES]
     if force or _newer(objs, LIB):
-        _run([cc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-lpthread",
+        _run([cc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-lpthread", "-ldl",
                                                    "-Xcompiler", "-fPIC", "-cudart", "static"], verbose)
     cli_src = os.path.join(CSRC, "host", "flashfry_cli.cpp")
     if os.path.exists(cli_src) and (force or _newer([cli_src] + hdrs + [LIB], CLI)):

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <chrono>
 
 #include "ff_common.cuh"
 #include "ff_kernels.cuh"
@@ -133,6 +134,12 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
     kCut[3][1] = c->opt.subbatch_c1; kCut[3][2] = c->opt.subbatch_c2;
   }
 
+  const auto t_start = std::chrono::steady_clock::now();
+  auto trace = [&](const char *what, int b) {
+    if (!c->opt.trace) return;
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count();
+    fprintf(stderr, "[ff trace] %8.1f us  %s %d\n", us, what, b);
+  };
   HitsOwner *o = owner_get();
   if (!o) { set_error("out of host memory"); return FF_ENOMEM; }
   int rc = FF_OK;
@@ -152,7 +159,9 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
     batch_g0[b] = g0;
     if (b >= 2) { cudaError_t e = cudaEventSynchronize(c->slot_copied[slot]); if (e != cudaSuccess) return fail(cuda_fail(e, "event sync", __FILE__, __LINE__)); }
     DeviceResult r;
+    trace("sub-batch start", b);
     if ((rc = discover_on_device(c, d_guides + g0, gn, max_mm, max_ot, want_positions != 0, bulge_flags, slot, &r)) != FF_OK) return fail(rc);
+    trace("device done", b);
     add_timings(&acc, c->last);
     if (metrics) {
       if ((rc = score_slot(c, d_guides + g0, r, metrics, slot)) != FF_OK) return fail(rc);
@@ -192,12 +201,14 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
       if (e == cudaSuccess && pos_total > 0) e = cudaMemcpyAsync(o->positions.p, r.d_positions, pos_total * 8, cudaMemcpyDeviceToHost, cs);
     }
     if (e == cudaSuccess) e = cudaEventRecord(c->slot_copied[slot], cs);
+    trace("copies queued", b);
     if (e != cudaSuccess) return fail(cuda_fail(e, "D2H of discover results", __FILE__, __LINE__));
     batch_hit_off[b] = hit_off;
     hit_off += H;
   }
   batch_hit_off[nb] = hit_off; batch_g0[nb] = G;
   { cudaError_t e = cudaStreamSynchronize(cs); if (e != cudaSuccess) return fail(cuda_fail(e, "D2H of discover results", __FILE__, __LINE__)); }
+  trace("copies done", nb);
   // sub-batch row pointers are local: shift them by the batch's first hit
   int64_t *rp = o->row_ptr.as<int64_t>();
   for (int b = 1; b < nb; ++b)
@@ -285,6 +296,10 @@ int ff_create(ff_ctx **out, int device_id) {
       e = cudaEventCreate(&ev);
       if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
     }
+    e = cudaHostAlloc(&c->h_status, 256, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&c->h_status_dev, c->h_status, 0);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaHostAlloc(mapped status)", __FILE__, __LINE__); }
+    memset(c->h_status, 0, 256);
     *out = c;
     return FF_OK;
   });
@@ -300,7 +315,7 @@ void ff_destroy(ff_ctx *c) {
                     &c->pos_ptr, &c->out_positions, &c->cfd_per_ot, &c->hsu_per_ot, &c->scratch_guides, &c->running, &c->active, &c->active2,
                     &c->act_flags, &c->seg_end, &c->kept_keys, &c->kept_sorted, &c->n_sel, &c->cell_ws, &c->idx32, &c->st_targets, &c->st_mm};
   for (DevBuf *b : bufs) b->release();
-  c->h_status.release();
+  if (c->h_status) cudaFreeHost(c->h_status);
   c->host_targets.release();
   for (auto &os : c->out) {
     DevBuf *ob[] = {&os.row_ptr, &os.total_count, &os.overflowed, &os.out_targets, &os.out_mm, &os.out_tidx, &os.out_bulge, &os.cfd_max, &os.cfd_spec, &os.hsu};
@@ -331,7 +346,8 @@ int ff_set_option(ff_ctx *c, const char *key, long long value) {
         {"window_cells", &c->opt.window_cells, 0, 64},    {"subbatch_min", &c->opt.subbatch_min, 1, 1 << 30},
         {"subbatch_c1", &c->opt.subbatch_c1, 1, 98},      {"subbatch_c2", &c->opt.subbatch_c2, 2, 99},
         {"group_sort", &c->opt.group_sort, 0, 1},         {"b_spi", &c->opt.b_spi, 0, 32},
-        {"split_a", &c->opt.split_a, 0, 12},              {"compact_hits", &c->opt.compact_hits, 0, 1},
+        {"trace", &c->opt.trace, 0, 1},
+      {"split_a", &c->opt.split_a, 0, 12},              {"compact_hits", &c->opt.compact_hits, 0, 1},
     };
     for (auto &t : table)
       if (strcmp(key, t.name) == 0) {

@@ -111,6 +111,7 @@ struct Options {
   int group_sort = 1;      // 0 = always order hits with the radix sort
   int b_spi = 0;           // > 0: seeds per work item of the part-two pass of k_seed_scan / k_pattern_scan
   int split_a = 0;         // > 0: bases in the part-one key of the next database build
+  int trace = 0;           // 1 = ff_discover prints host-side timestamps of its sub-batches to stderr
   int compact_hits = 0;    // ff_discover: 1 = ship database indices instead of target longs (ff_hits.target_index)
 };
 
@@ -130,7 +131,9 @@ struct ff_ctx {
   ff::DevBuf idx32, st_targets, st_mm;  // per-guide ordering: scattered database indices, rows staged at their segment
   ff::HostBuf host_targets;             // host mirror of db.d_targets (ff_db_host_targets), made on first use
   uint64_t host_targets_n = 0;
-  ff::HostBuf h_status;                 // pinned mirror of the device status words (one D2H + one sync per call)
+  // Status words of a call (candidate count, flags, hit count), written by the last kernel straight into MAPPED pinned
+  // host memory: a cudaMemcpy of these few bytes would queue behind the previous sub-batch's hit-list D2H in the copy engine.
+  void *h_status = nullptr, *h_status_dev = nullptr;
   ff::DevBuf pos_cnt, pos_ptr, out_positions;
   ff::DevBuf cfd_per_ot, hsu_per_ot;
   ff::DevBuf scratch_guides;  // H2D staging target for ff_discover

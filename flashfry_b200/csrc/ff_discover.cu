@@ -567,6 +567,16 @@ __global__ void __launch_bounds__(256) k_sort_cut(uint32_t *__restrict__ idx, co
   }
 }
 
+// the status words, written into mapped host memory (no copy engine involved)
+__global__ void k_publish_status(const PlainStatus *__restrict__ stt, const int64_t *__restrict__ row_ptr_end, volatile PlainStatus *host) {
+  if (threadIdx.x == 0) {
+    host->n_cand = stt->n_cand; host->n_compares = stt->n_compares;
+    host->n_hits = row_ptr_end ? *row_ptr_end : stt->n_hits;
+    host->flag = stt->flag; host->n_long = stt->n_long;
+    __threadfence_system();
+  }
+}
+
 // one warp per guide: move the kept row from its segment to its place in the CSR
 __global__ void k_compact_rows(const int64_t *__restrict__ seg_start, const int64_t *__restrict__ row_ptr, int64_t n_guides,
                                const uint64_t *__restrict__ st_targets, const uint8_t *__restrict__ st_mm, const uint32_t *__restrict__ idx,
@@ -659,7 +669,6 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   const int64_t G = n_guides;
   const int64_t Gp = G > 0 ? G : 1;
   FF_TRY(ctx->counters.reserve(256));
-  FF_TRY(ctx->h_status.reserve(256));
   FF_TRY(ctx->seg_start.reserve((Gp + 1) * 8));
   FF_TRY(ctx->n_keep.reserve((Gp + 1) * 8));
   FF_TRY(os.row_ptr.reserve((Gp + 1) * 8));
@@ -709,7 +718,8 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     if (want > ctx->hit_cap) ctx->hit_cap = want;
   }
   PlainStatus *d_stt = ctx->counters.as<PlainStatus>();
-  PlainStatus *h_stt = ctx->h_status.as<PlainStatus>();
+  PlainStatus *h_stt = static_cast<PlainStatus *>(ctx->h_status);
+  PlainStatus *h_stt_dev = static_cast<PlainStatus *>(ctx->h_status_dev);
   sp.hit_count = &d_stt->n_cand; sp.n_compares = &d_stt->n_compares;
   int scan_launches = 0;
   const long long n_items = G * (long long)sp.items_per_guide;
@@ -789,7 +799,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
       launches += 9;
       FF_CUDA(cudaEventRecord(ctx->ev[4], st));
     }
-    FF_CUDA(cudaMemcpyAsync(h_stt, d_stt, sizeof(PlainStatus), cudaMemcpyDeviceToHost, st));
+    k_publish_status<<<1, 32, 0, st>>>(d_stt, nullptr, h_stt_dev);
     FF_CUDA(cudaStreamSynchronize(st));
     n_cand = (int64_t)h_stt->n_cand;
     if ((size_t)n_cand > cap) {  // the buffer was too small: grow it and repeat the call
@@ -829,8 +839,9 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
     FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
     launches += 2;
-    FF_CUDA(cudaMemcpyAsync(&n_hits, os.row_ptr.as<int64_t>() + G, 8, cudaMemcpyDeviceToHost, st));
+    k_publish_status<<<1, 32, 0, st>>>(d_stt, os.row_ptr.as<int64_t>() + G, h_stt_dev);
     FF_CUDA(cudaStreamSynchronize(st));
+    n_hits = h_stt->n_hits;
     if (G > 0 && n_hits > 0) {
       k_gather<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), db.d_targets, d_guides,
                                                        db.pack.cmp_mask, G, tbits, os.out_targets.as<uint64_t>(), os.out_mm.as<uint8_t>(), os.out_tidx.as<uint32_t>());

@@ -14,9 +14,9 @@ def shard_range(n_guides: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous, balanced (sizes differ by at most one) slice of rank `rank`."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError("bad rank/world: %d/%d" % (rank, world))
-    base, extra = divmod(n_guides, world)
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    from . import api  # the C ABI's ff_shard_range: one definition for the one-process-per-GPU ranks and for ff_multi
+    first, count = api.shard_range(n_guides, world, rank)
+    return first, first + count
 
 
 def all_gather_counts(local_counts, n_guides: int, group=None):

@@ -64,6 +64,7 @@ int ff_set_stream(ff_ctx *ctx, void *cuda_stream);
  *   subbatch_min, subbatch_c1, subbatch_c2   how ff_discover cuts a guide set into sub-batches (D2H overlap)
  *   group_sort    0 = always order candidate hits with the radix sort
  *   b_spi         > 0 = seeds per work item of the part-two pass of the guide-major kernels
+ *   trace         1 = ff_discover prints host-side timestamps of its sub-batches to stderr
  *   split_a       > 0 = bases in the part-one key, applied by the next database load
  *   compact_hits  1 = ff_discover ships database indices (ff_hits.target_index) and leaves ff_hits.targets NULL until
  *                 ff_hits_resolve fills it from the host mirror of the target array
@@ -210,6 +211,31 @@ int ff_discover_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
 /* The bulge extension on device-resident guides (no scoring: CFD / Hsu2013 are not defined for bulged alignments). */
 int ff_discover_bulge_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mismatch,
                              int max_off_targets, int bulge_flags, ff_device_result *out);
+
+/* ---- several GPUs behind one host process ------------------------------------------------------------------
+ * The reference is a single process (modules/OffTargetDiscovery.scala:117: "multithreaded (not supported currently)"); a
+ * JVM host reaches every GPU of a box through one ff_multi: one ff_ctx and one persistent host thread per device, every
+ * device holds a replica of the database, discover shards the guide array (rank r: ff_shard_range), and ONE
+ * ncclAllGather of the per-guide occurrence totals at the end leaves the global vector on every device and on the host.
+ * NCCL is loaded at run time (dlopen) only when n_devices > 1. */
+typedef struct ff_multi ff_multi;
+int ff_multi_create(ff_multi **out, const int *device_ids, int n_devices);
+void ff_multi_destroy(ff_multi *m);
+int ff_multi_size(const ff_multi *m);
+ff_ctx *ff_multi_ctx(ff_multi *m, int rank);  /* the rank's context: ff_db_info, ff_last_timings ... (not while a multi call runs) */
+int ff_multi_set_option(ff_multi *m, const char *key, long long value);
+/* FlashFry's files are read and inflated once; the decoded arrays reach the other devices with ncclBroadcast (NVLink). */
+int ff_multi_load_database(ff_multi *m, const char *db_path, const char *header_path);
+int ff_multi_synth_database(ff_multi *m, int enzyme_index, uint64_t n_targets, uint64_t seed);
+/* guides [first, first + count) belong to shard `shard` of n_shards: first = n_guides * shard / n_shards (pure function) */
+void ff_shard_range(int64_t n_guides, int n_shards, int shard, int64_t *first, int64_t *count);
+/* out: [n_devices] hit lists, out[r] = rows of shard r's guides (free each with ff_hits_free); total_count_all:
+ * [n_guides] (may be NULL) = the all-gathered CRISPRSiteOT.currentTotal of every guide, in guide order. */
+int ff_multi_discover(ff_multi *m, const uint64_t *guides, int64_t n_guides, int max_mismatch, int max_off_targets,
+                      int want_positions, ff_hits **out, int32_t *total_count_all);
+/* device pointer (on rank's GPU) to the gathered totals of the last ff_multi_discover: n_devices shards padded to
+ * ceil(n_guides / n_devices) int32 each; NULL for a single device */
+const int32_t *ff_multi_device_totals(ff_multi *m, int rank);
 
 /* Device-time of the kernels of the last discover call on this context, from CUDA events recorded on the
  * context's stream (ms).  scan = the bin-scan kernel (dominant), prep = guide sort/bucketing, order = hit sort,

@@ -16,25 +16,6 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
-def ff():
-    import flashfry_b200.api as api
-    return api
-
-
-@pytest.fixture(scope="module")
-def small_db(oracle, tmp_path_factory):
-    """A 400 kb random genome with a repeat family, indexed into FlashFry's own format by the oracle."""
-    d = tmp_path_factory.mktemp("smalldb")
-    contigs = helpers.random_genome(101, 200_000, repeat_unit=60, n_repeats=400, n_contigs=2)
-    fa = str(d / "genome.fa")
-    helpers.write_fasta(fa, contigs, lower_fraction=0.2)
-    dbp = str(d / "small_cas9ngg_database")
-    stats = oracle.build_database(fa, dbp, "spcas9ngg")
-    db = oracle.read_database(dbp)
-    return dbp, db, stats
-
-
-@pytest.fixture(scope="module")
 def small_ctx(ff, small_db):
     ctx = ff.Context(0)
     ctx.load_database(small_db[0])

@@ -241,9 +241,23 @@ def test_library_carries_sm_100a_code_for_every_hot_kernel(built):
     archs = set(re.findall(r"sm_\d+a?", elfs))
     assert archs == {"sm_100a"}, archs
     syms = subprocess.run([cuobjdump, "-symbols", built], capture_output=True, text=True).stdout
-    for kernel in ("k_bin_scan", "k_pair_scan", "k_slice_planes", "k_seed_scan", "k_pattern_scan", "k_overflow_cut", "k_cut_window", "k_sort_segments", "k_gather",
+    for kernel in ("k_bin_scan", "k_pair_scan", "k_slice_planes", "k_seed_scan", "k_pattern_scan", "k_overflow_cut", "k_cut_window", "k_sort_cut", "k_sort_long", "k_compact_rows", "k_gather",
                    "k_score", "k_hit_aggregates", "k_cell_offsets"):
         assert kernel in syms, "kernel missing from the library: " + kernel
     # the bin scan stages its bins with TMA bulk copies (cp.async.bulk -> UBLKCP in SASS) completing on an mbarrier
     sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN2ff10k_bin_scanILi9EEEvNS_9BinParamsE", built], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass, "k_bin_scan lost its TMA bulk copy / mbarrier"
+
+
+def test_c_abi_shard_range_is_the_one_definition_of_sharding(built):
+    """ff_shard_range (pure function of the C ABI, no GPU needed) is what ff_multi_discover shards with; the
+    one-process-per-GPU ranks (flashfry_b200.sharding) call the same symbol."""
+    import flashfry_b200.api as api
+    from flashfry_b200.sharding import shard_range
+    for n in (0, 1, 5, 100000, 100003):
+        for world in (1, 2, 8):
+            edges = [api.shard_range(n, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and sum(c for _, c in edges) == n
+            assert all(edges[r][0] + edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+            assert [shard_range(n, r, world) for r in range(world)] == [(f, f + c) for f, c in edges]
+    assert api.shard_range(10, 0, 0) == (0, 0) and api.shard_range(10, 2, 5) == (0, 0)
