@@ -62,6 +62,20 @@ def make_guides(n, seed, planted_from=None, planted_seed=0, planted_frac=0.10):
     return (g | (np.uint64(1) << np.uint64(48))).astype(np.uint64)
 
 
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def family_consensus(seed, f):
+    """The 21-base (protospacer + N) consensus of repeat family f of ff_synth_database_skewed (ff_db.cu k_synth_families)."""
+    with np.errstate(over="ignore"):
+        f = np.asarray(f, dtype=np.uint64)
+        return _splitmix64(np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0xFA111E5) + f) >> np.uint64(64 - 42)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -133,15 +147,28 @@ def ncu_traffic():
     return None
 
 
-def cell_major_expected(G, n_t):
-    """Mirror of the library's choice (ff_discover.cu discover_plain): cell-major when part-one buckets are re-read."""
-    return G * 529 / float(4 ** 11) >= 1.0 and n_t * 8.0 > 96e6
+BASELINE_JVM = {  # FlashFry JVM, one core, hg38 (paper/timing_data/bwa_flashfry), seconds per run
+    3: {1: 44.0, 100: 45.1, 1000: 48.4, 10000: 90.9, 100000: 514.6},
+    4: {1: 46.4, 100: 48.5, 1000: 63.6, 10000: 224.8, 100000: 1862.9},
+    5: {1: 50.6, 100: 57.7, 1000: 130.7, 10000: 835.7, 100000: 7918.5},
+}
+
+
+def _metric_name(workload, k):
+    if workload == "fused":
+        return "guides/sec, discover (<=%d mismatches) + CFD + Hsu2013 fused on the GPU, vs hg38-sized index" % k
+    if workload == "bulge":
+        return "guides/sec at <=5 mismatches + one 1-bp RNA/DNA bulge vs hg38-sized index (extension: no reference semantics)"
+    return "guides/sec at <=%d mismatches vs hg38-sized index" % k
 
 
 def run_native(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import flashfry_b200.api as ff
+    from flashfry_b200 import _native as N
+    from flashfry_b200.sharding import shard_range, all_gather_counts
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -152,6 +179,9 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    wl = args.workload
+    n_total = args.guides if args.guides else (50_000 if wl == "fused" else 100_000)
+    k = 5 if wl == "bulge" else args.k
 
     ctx = ff.Context(local)
     t0 = time.perf_counter()
@@ -160,27 +190,39 @@ def run_native(args):
     db_s = time.perf_counter() - t0
     info = ctx.info()
     n_t = int(info.n_targets)
-    # planted guides are drawn from a few slices of the resident database
+    # planted guides are drawn from a few slices of the resident database (identical replicas: identical on every rank)
     rng = np.random.default_rng(17)
-    slices = [ctx.copy_targets(int(s), 2048) for s in rng.integers(0, max(1, n_t - 2048), 16)]
-    pool = np.concatenate(slices)
-    guides = make_guides(args.guides, SEED_GUIDES + 1000 * rank, pool, SEED_PLANTED + rank)
+    pool = np.concatenate([ctx.copy_targets(int(s), 2048) for s in rng.integers(0, max(1, n_t - 2048), 16)])
+    if args.scaling == "strong":   # configs[2]: ONE guide set, sharded over the ranks
+        all_guides = make_guides(n_total, SEED_GUIDES, pool, SEED_PLANTED)
+        lo, hi = shard_range(len(all_guides), rank, world)
+        guides, G_job = all_guides[lo:hi], len(all_guides)
+    else:                          # weak: every rank its own batch of the full size
+        guides = make_guides(n_total, SEED_GUIDES + 1000 * rank, pool, SEED_PLANTED + rank)
+        G_job = world * len(guides)
     G = len(guides)
 
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
     d_guides = torch.from_numpy(guides.view(np.int64)).to(dev)
-    counts_all = torch.empty(world * G, dtype=torch.int32, device=dev) if world > 1 else None
 
     class _DevView:  # wrap a context-owned device pointer for torch without copying
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
+    counts_weak = torch.empty(world * G, dtype=torch.int32, device=dev) if (world > 1 and args.scaling == "weak") else None
+
     def step():
-        r = ctx.discover_device(d_guides.data_ptr(), G, args.k, args.max_ot, 0)
+        if wl == "bulge":
+            r = ctx.discover_bulge_device(d_guides.data_ptr(), G, k, args.max_ot, 3)
+        else:
+            r = ctx.discover_device(d_guides.data_ptr(), G, k, args.max_ot, 3 if wl == "fused" else 0)
         if world > 1:  # the one collective of the path: every rank learns every guide's total count
-            mine = torch.as_tensor(_DevView(r.d_total_count, G), device=dev)
-            dist.all_gather_into_tensor(counts_all, mine)
+            mine = torch.as_tensor(_DevView(r.d_total_count, G), device=dev) if G else torch.zeros(0, dtype=torch.int32, device=dev)
+            if args.scaling == "strong":
+                all_gather_counts(mine, G_job)
+            else:
+                dist.all_gather_into_tensor(counts_weak, mine)
         return r
 
     def sync_all():
@@ -197,15 +239,14 @@ def run_native(args):
     sync_all()
     t_region0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    scan_ms, launches, cand, compares, scan_bytes = [], 0, 0, 0, 0
+    tms, launches = [], 0
     sync_all()
     e0.record(stream)
     for _ in range(args.steps):
         r = step()
         tm = ctx.timings()
-        scan_ms.append(tm.scan_ms); launches += tm.kernel_launches + (1 if world > 1 else 0)
-        cand, compares, scan_bytes = int(r.n_candidate_hits), int(r.n_compares), int(tm.scan_bytes_read)
-        scan_launches = tm.scan_launches
+        tms.append((tm.scan_ms, tm.scan_part1_ms, tm.scan_part2_ms, tm.prep_ms, tm.order_ms, tm.cut_ms, tm.score_ms))
+        launches += tm.kernel_launches + (1 if world > 1 else 0)
     e1.record(stream)
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -214,144 +255,275 @@ def run_native(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax.item())
     ms_per_step = ms / args.steps
-    value = world * G / (ms_per_step / 1e3)
-    n_hits = int(r.n_hits)
+    value = G_job / (ms_per_step / 1e3)
+    n_hits, cand = int(r.n_hits), int(r.n_candidate_hits)
+    ent1, ent2, req_bytes, scan_launches = int(tm.entries_part1), int(tm.entries_part2), int(tm.scan_bytes_read), int(tm.scan_launches)
 
-    # ---- e2e through the C ABI with host buffers (H2D guides, D2H hit lists), same steps
+    # ---- e2e through the C ABI with HOST buffers (pinned guides in, hit lists out), same shard, same steps
     pinned = torch.from_numpy(guides.view(np.int64)).pin_memory()
     g_host = pinned.numpy().view(np.uint64)
-    import ctypes as C
-    from flashfry_b200 import _native as N
     hp = C.POINTER(N.FFHits)()
     gp = g_host.ctypes.data_as(C.POINTER(C.c_uint64))
+    sc = [np.zeros(max(G, 1)) for _ in range(3)]
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
 
     def e2e_step():
-        N.check(N.lib().ff_discover(ctx._h, gp, G, args.k, args.max_ot, 0, C.byref(hp)))
+        if wl == "fused":
+            N.check(N.lib().ff_discover_score(ctx._h, gp, G, k, args.max_ot, 0, 3, C.byref(hp), dp(sc[0]), dp(sc[1]), dp(sc[2])))
+        elif wl == "bulge":
+            N.check(N.lib().ff_discover_bulge(ctx._h, gp, G, k, args.max_ot, 3, 0, C.byref(hp)))
+        else:
+            N.check(N.lib().ff_discover(ctx._h, gp, G, k, args.max_ot, 0, C.byref(hp)))
         nh = int(hp.contents.n_hits)
         N.lib().ff_hits_free(hp)
         return nh
-    for _ in range(max(1, args.warmup // 2 + 1)):
-        nh = e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        nh = e2e_step()
-    sync_all()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+
+    def time_e2e(steps):
+        for _ in range(max(2, args.warmup // 2 + 1)):
+            nh = e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            nh = e2e_step()
+        sync_all()
+        s = (time.perf_counter() - t0) / steps
+        if world > 1:
+            tmax = torch.tensor([s], device=dev, dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            s = float(tmax.item())
+        return s, nh
+    e2e_steps = args.steps if wl != "bulge" else max(2, args.steps // 5)
+    e2e_s, nh = time_e2e(e2e_steps)
     clocks = sampler.stop(t_region0, sampler.mark()) if rank == 0 else None  # samples taken inside the two timed regions
-    if world > 1:
-        tmax = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_s = float(tmax.item())
-    e2e = {"value": world * G / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": 8 * G,
-           "d2h_bytes_per_step": (G + 1) * 8 + nh * 9 + G * 5, "ms_per_step": e2e_s * 1e3}
+    per_hit = 10 if wl == "bulge" else 9
+    e2e = {"value": G_job / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": 8 * G,
+           "d2h_bytes_per_step": (G + 1) * 8 + nh * per_hit + G * 5 + (24 * G if wl == "fused" else 0), "ms_per_step": e2e_s * 1e3,
+           "bytes_are": "per rank", "over_device_step": e2e_s * 1e3 / ms_per_step}
 
     out = None
     if rank == 0:
         peak, peak_src = measured_peak()
-        scan_avg_ms = float(np.mean(scan_ms))
-        achieved = scan_bytes / (scan_avg_ms / 1e3) / 1e9
-        scan_kernel = "k_cell_scan" if cell_major_expected(G, n_t) else "k_seed_scan"
-        roof = {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "alg_bytes_per_launch": scan_bytes, "kernel_ms": scan_avg_ms,
-                "kernel_share_of_step": scan_avg_ms / ms_per_step, "traffic": None,
-                "entries_streamed_per_launch": compares, "entries_per_guide": compares / max(G, 1),
-                # the second ceiling -- one 32-bit POPC per compared entry, 16 lanes/clk/SM x 148 SMs x 1.9 GHz
-                "compares_per_s": compares / (scan_avg_ms / 1e3), "compare_ceiling_per_s": 4.5e12,
-                "compare_frac": compares / (scan_avg_ms / 1e3) / 4.5e12}
+        a = np.asarray(tms, dtype=np.float64).mean(axis=0)
+        scan_ms, p1_ms, p2_ms = float(a[0]), float(a[1]), float(a[2])
+        bin_major = p2_ms > 0.0
+        # ALG_BYTES = 8 N_t (every target word once) + 8 G (guides) + 16 H (compact hit records)
+        alg_bytes = 8 * n_t + 8 * G + 16 * cand
+        achieved = alg_bytes / (scan_ms / 1e3) / 1e9
         tr = ncu_traffic()
-        if (tr and tr.get("targets") == n_t and tr.get("max_mismatch") == args.k and tr.get("kernel") == scan_kernel
-                and tr.get("guides_in_profiled_launch") == G):
-            # dram__bytes_read + dram__bytes_write of one launch of the same kernel on the same workload (ncu --set full)
-            roof["traffic"] = tr.get("dram_bytes_per_profiled_launch")
+        tr_ok = bool(tr and tr.get("targets") == n_t and tr.get("max_mismatch") == k and tr.get("guides_in_profiled_launch") == G
+                     and tr.get("kernel") == ("k_bin_scan+k_pair_scan" if bin_major else "k_seed_scan"))
+        traffic = tr.get("dram_bytes_per_profiled_launch") if tr_ok else None
+        roof = {"bound": (tr.get("bound") if tr_ok else None) or ("issue" if bin_major else "hbm"),
+                "kernel": "k_bin_scan + k_pair_scan (the bin-major scan: one launch per index half)" if bin_major else "k_seed_scan",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "alg_bytes_8d": alg_bytes, "alg_bytes_are": "SURVEY.md 8(d): 8*N_t + 8*G + 16*H per call",
+                "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / (float(a[[0, 3, 4, 5, 6]].sum())),
+                "traffic": traffic, "dram_frac": (traffic / (scan_ms / 1e3) / 1e9 / peak) if traffic else None,
+                "requested_bytes": req_bytes, "requested_bytes_are": "index lookups + bit-sliced planes streamed + guides + hit keys (L2 / shared-memory level, not HBM)",
+                "entries_compared_per_launch": ent1 + ent2, "entries_per_guide": (ent1 + ent2) / max(G, 1),
+                # SURVEY 8(d)'s second ceiling -- one 32-bit POPC per compared entry, 16 lanes/clk/SM x 148 SMs x 1.9 GHz.  The
+                # bit-sliced kernels do not use the POPC pipe (40 LOP3 per 32 entries), so this fraction may exceed 1.
+                "compares_per_s": (ent1 + ent2) / (scan_ms / 1e3), "compare_ceiling_per_s": 4.5e12,
+                "compare_frac": (ent1 + ent2) / (scan_ms / 1e3) / 4.5e12,
+                "launches": ([{"kernel": "k_bin_scan<9> (index A through shared memory, TMA-staged bins)", "ms": p1_ms, "entries": ent1,
+                               "compares_per_s": ent1 / (p1_ms / 1e3)},
+                              {"kernel": "k_pair_scan<11> (index B, pairs sorted by bucket)", "ms": p2_ms, "entries": ent2,
+                               "compares_per_s": ent2 / (p2_ms / 1e3)}] if bin_major else
+                             [{"kernel": "k_seed_scan", "ms": scan_ms, "entries": ent1 + ent2}]),
+                "step_breakdown_ms": {"prep": float(a[3]), "scan": scan_ms, "order": float(a[4]), "cut": float(a[5]), "score": float(a[6])}}
+        if tr_ok:
             roof["traffic_source"] = tr.get("source")
-            roof["note"] = ("algorithmic bytes = what the kernel requests per (guide, seed): index entries + streamed bucket entries; the "
-                            "cell-major order serves repeated bucket reads from L2, so HBM traffic is BELOW the algorithmic bytes")
-        out = {"metric": "guides/sec at <=4 mismatches vs hg38-sized index", "value": value, "unit": "guides/s", "n_gpus": world,
+            for key in ("issue_frac", "alu_pipe_frac", "per_launch"):
+                if key in tr:
+                    roof[key] = tr[key]
+        out = {"metric": _metric_name(wl, k), "value": value, "unit": "guides/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": value / 53.7, "dtype": "u64", "data": "synthetic",
-               "config": {"workload": "configs[2]: %d synthetic NGG guides per GPU (+10%% planted) vs synthetic %d-target spCas9-NGG index, "
-                                      "k<=%d, maxOT %d" % (G, n_t, args.k, args.max_ot),
-                          "guides_per_gpu": G, "targets": n_t, "max_mismatch": args.k, "maximum_off_targets": args.max_ot,
-                          "parallelism": "guide-sharded x%d, one index replica per GPU" % world,
+               "scaling": args.scaling, "vs_baseline": (value / 53.7) if wl == "discover" and k == 4 else None, "dtype": "u64", "data": "synthetic",
+               "config": {"workload": "%s: %d synthetic NGG guides (+10%% planted) %s vs synthetic %d-target spCas9-NGG index, k<=%d%s, maxOT %d" % (
+                              {"discover": "configs[2]", "fused": "configs[4] (discover + CFD + Hsu2013 fused)", "bulge": "configs[3] (1-bp bulge extension)"}[wl],
+                              G_job, "in total, guide-sharded over %d GPU(s)" % world if args.scaling == "strong" else "= %d per GPU" % G,
+                              n_t, k, " + one 1-bp RNA/DNA bulge" if wl == "bulge" else "", args.max_ot),
+                          "guides_total": G_job, "guides_per_gpu": G, "targets": n_t, "max_mismatch": k, "maximum_off_targets": args.max_ot,
+                          "parallelism": "guide-sharded x%d, one index replica per GPU, one NCCL all-gather of int32 totals per step" % world,
                           "l2": "index (%.1f GB) is larger than L2, re-streamed every step" % (info.device_bytes / 1e9),
                           "seed_split": "first %d | last %d protospacer bases" % (int(info.seed_split_a), 20 - int(info.seed_split_a)),
                           "db_build_s": db_s},
                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
                "hits_per_step": n_hits, "candidate_hits_per_step": cand, "scan_launches_last_step": scan_launches,
                "baseline_note": "vs_baseline = value / 53.7 guides/s (published single-core JVM, 100k guides, hg38, k<=4; BASELINE.md)"}
-        # the two scan kernels (guide-major k_seed_scan / cell-major k_cell_scan) must agree on the whole timed batch
-        def _totals(kernel):
-            ctx.set_option("scan_kernel", kernel)
-            rr = ctx.discover_device(d_guides.data_ptr(), G, args.k, args.max_ot, 0)
-            t = torch.as_tensor(_DevView(rr.d_total_count, G), device=dev).clone()
-            ctx.set_option("scan_kernel", 0)
-            return int(rr.n_hits), t
-        h0, t0_ = _totals(1)
-        h1, t1_ = _totals(2)
-        out["scan_kernels_agree_on_full_batch"] = bool(h0 == h1 == n_hits and torch.equal(t0_, t1_))
-        # BASELINE.json configs[4] flavour on the same batch: discover + CFD + Hsu2013 fused on the device
-        fs = []
-        for _ in range(3):
-            ctx.discover_device(d_guides.data_ptr(), G, args.k, args.max_ot, 3)
-            t = ctx.timings()
-            fs.append((t.total_ms, t.score_ms))
-        out["fused_discover_score"] = {"guides": G, "total_ms": float(np.median([a for a, _ in fs])),
-                                       "score_kernel_ms": float(np.median([b for _, b in fs])),
-                                       "guides_per_s": G / (float(np.median([a for a, _ in fs])) / 1e3),
-                                       "metrics": "DoenchCFD_maxOT, DoenchCFD_specificityscore, Hsu2013 (FP64, bit-identical to the oracle)"}
-        # BASELINE.json configs[3]: <= 5 mismatches + one 1-bp RNA/DNA bulge on the same batch.  An EXTENSION: the reference
-        # has no bulge search, so this line is never part of a parity claim (semantics: include/flashfry_b200.h).
-        if not args.no_bulge:
-            bs = []
-            for _ in range(3):
-                rb = ctx.discover_bulge_device(d_guides.data_ptr(), G, 5, args.max_ot, 3)
-                t = ctx.timings()
-                bs.append((t.total_ms, t.scan_ms, t.scan_launches))
-            bms = float(np.median([a for a, _, _ in bs]))
-            for _ in range(2):  # the first call allocates the pinned result buffers (pooled afterwards)
-                t0 = time.perf_counter()
-                N.check(N.lib().ff_discover_bulge(ctx._h, gp, G, 5, args.max_ot, 3, 0, C.byref(hp)))
-                bh = int(hp.contents.n_hits)
-                N.lib().ff_hits_free(hp)
-                be2e = time.perf_counter() - t0
-            out["bulge_mode"] = {"workload": "configs[3]: %d guides, <=5 mismatches + one 1-bp RNA or DNA bulge, maxOT %d, same index" % (G, args.max_ot),
-                                 "total_ms": bms, "scan_ms": float(np.median([b for _, b, _ in bs])), "windows": int(bs[-1][2]),
-                                 "guides_per_s": G / (bms / 1e3), "hits": int(rb.n_hits), "candidate_hits": int(rb.n_candidate_hits),
-                                 "overflowed_guides_note": "nearly every guide reaches maximumOffTargets: the scan walks database-order windows and drops full guides",
-                                 "e2e_guides_per_s": G / be2e, "e2e_d2h_bytes": (G + 1) * 8 + bh * 10 + G * 5,
-                                 "parity": "extension, no reference semantics: checked against a brute-force definition in tests/test_gpu_bulge.py"}
-        # BASELINE.json configs[1]: 1 000 synthetic + 100 planted guides vs the chr22 quick-start database, when the database
-        # built by __graft_entry__.build() travelled with the tree (33.5 MB of targets: L2-resident after the first pass)
-        chr22 = os.path.join(ROOT, "tests", "golden", "_chr22", "chr22_cas9ngg_database")
-        if os.path.exists(chr22) and os.path.exists(chr22 + ".header"):
-            try:
-                c2 = ff.Context(local)
-                t0 = time.perf_counter()
-                c2.load_database(chr22)
-                load_s = time.perf_counter() - t0
-                t22 = c2.copy_targets()
-                g22 = make_guides(1100, 1001, t22[:: max(1, len(t22) // 4096)], 1002, planted_frac=100.0 / 1100.0)
-                d22 = torch.from_numpy(g22.view(np.int64)).to(dev)
-                ts = []
-                for _ in range(8):
-                    r22 = c2.discover_device(d22.data_ptr(), len(g22), args.k, args.max_ot, 0)
-                    ts.append(c2.timings().total_ms)
-                out["chr22_1000_guides"] = {"workload": "configs[1]: 1 000 synthetic + 100 planted guides vs the chr22 quick-start index (%d targets), k<=%d" % (len(t22), args.k),
-                                            "total_ms": float(np.median(ts[2:])), "guides_per_s": len(g22) / (float(np.median(ts[2:])) / 1e3),
-                                            "hits": int(r22.n_hits), "cold_load_s": load_s,
-                                            "parity": "tests/test_gpu_parity.py::test_chr22_1000_guides_config (bit-exact vs the oracle)"}
-                c2.close()
-            except Exception as e:  # noqa: BLE001 -- a side measurement must not take the bench line down
-                out["chr22_1000_guides"] = {"error": str(e)}
-        if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(ctx, guides, args, threads=1, budget_guides=args.cpu_guides)
+        if wl == "discover" and not args.no_extras:
+            _extras(out, ctx, ff, N, C, torch, dev, args, guides, d_guides, g_host, gp, hp, G, k, n_t, n_hits, world, _DevView)
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         _emit(out)
+
+
+def _extras(out, ctx, ff, N, C, torch, dev, args, guides, d_guides, g_host, gp, hp, G, k, n_t, n_hits, world, _DevView):
+    """Side measurements on rank 0's shard: never inside the timed regions, never allowed to take the bench line down."""
+    def guard(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    # the two scan kernels (guide-major k_seed_scan / bin-major k_bin_scan + k_pair_scan) must agree on the whole timed batch
+    def _totals(kernel):
+        ctx.set_option("scan_kernel", kernel)
+        rr = ctx.discover_device(d_guides.data_ptr(), G, k, args.max_ot, 0)
+        t = torch.as_tensor(_DevView(rr.d_total_count, G), device=dev).clone()
+        ctx.set_option("scan_kernel", 0)
+        return int(rr.n_hits), t
+    h0, t0_ = _totals(1)
+    h1, t1_ = _totals(2)
+    out["scan_kernels_agree_on_full_batch"] = bool(h0 == h1 == n_hits and torch.equal(t0_, t1_))
+
+    def time_call(fn, reps):
+        fn(); fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    def e2e_call(kk=k, n=G):
+        N.check(N.lib().ff_discover(ctx._h, gp, n, kk, args.max_ot, 0, C.byref(hp)))
+        N.lib().ff_hits_free(hp)
+
+    def compact():
+        # the hit list as 32-bit database indices (5 instead of 9 bytes per hit over PCIe); the host mirrors the target array
+        # once and looks longs up on demand (ff_db_host_targets / ff_hits_resolve)
+        t0 = time.perf_counter()
+        N.lib().ff_db_host_targets(ctx._h)
+        mirror_s = time.perf_counter() - t0
+        ctx.set_option("compact_hits", 1)
+        try:
+            s = time_call(e2e_call, max(3, args.steps // 2))
+
+            def resolved():
+                N.check(N.lib().ff_discover(ctx._h, gp, G, k, args.max_ot, 0, C.byref(hp)))
+                N.check(N.lib().ff_hits_resolve(ctx._h, hp))
+                N.lib().ff_hits_free(hp)
+            s_res = time_call(resolved, 3)
+        finally:
+            ctx.set_option("compact_hits", 0)
+        return {"ms_per_step": s * 1e3, "guides_per_s": G / s, "d2h_bytes_per_step": (G + 1) * 8 + n_hits * 5 + G * 5,
+                "with_ff_hits_resolve_ms": s_res * 1e3, "host_mirror_build_s": mirror_s,
+                "note": "option compact_hits: ff_hits.target_index instead of ff_hits.targets; resolve = all longs looked up on the host"}
+    guard("e2e_compact_hits", compact)
+
+    def fused():
+        fs = []
+        for _ in range(3):
+            ctx.discover_device(d_guides.data_ptr(), G, k, args.max_ot, 3)
+            t = ctx.timings()
+            fs.append((t.total_ms, t.score_ms))
+        return {"guides": G, "total_ms": float(np.median([a for a, _ in fs])), "score_kernel_ms": float(np.median([b for _, b in fs])),
+                "guides_per_s": G / (float(np.median([a for a, _ in fs])) / 1e3),
+                "metrics": "DoenchCFD_maxOT, DoenchCFD_specificityscore, Hsu2013 (FP64, bit-identical to the oracle)",
+                "first_class_line": "python bench.py --workload fused  (configs[4]: 50 000 guides)"}
+    guard("fused_discover_score", fused)
+
+    # BASELINE.json configs[3]: <= 5 mismatches + one 1-bp RNA/DNA bulge on the same batch.  An EXTENSION: the reference
+    # has no bulge search, so this line is never part of a parity claim (semantics: include/flashfry_b200.h).
+    def bulge():
+        bs = []
+        for _ in range(3):
+            rb = ctx.discover_bulge_device(d_guides.data_ptr(), G, 5, args.max_ot, 3)
+            t = ctx.timings()
+            bs.append((t.total_ms, t.scan_ms, t.scan_launches))
+        bms = float(np.median([a for a, _, _ in bs]))
+        return {"workload": "configs[3]: %d guides, <=5 mismatches + one 1-bp RNA or DNA bulge, maxOT %d, same index" % (G, args.max_ot),
+                "total_ms": bms, "scan_ms": float(np.median([b for _, b, _ in bs])), "windows": int(bs[-1][2]),
+                "guides_per_s": G / (bms / 1e3), "hits": int(rb.n_hits), "candidate_hits": int(rb.n_candidate_hits),
+                "parity": "extension, no reference semantics: checked against a brute-force definition in tests/test_gpu_bulge.py",
+                "first_class_line": "python bench.py --workload bulge"}
+    if not args.no_bulge:
+        guard("bulge_mode", bulge)
+
+    # the batch-size ladder the reference publishes (BASELINE.md section 1): device-resident and end-to-end, per k
+    def ladder():
+        rows = []
+        for kk in (3, 4, 5):
+            for n in (1, 100, 1000, 10000, 100000):
+                if n > G:
+                    continue
+                reps = 20 if n <= 10000 else (5 if kk < 5 else 2)
+                dv = time_call(lambda: ctx.discover_device(d_guides.data_ptr(), n, kk, args.max_ot, 0), reps)
+                ee = time_call(lambda: e2e_call(kk, n), reps)
+                jvm = BASELINE_JVM[kk].get(n)
+                rows.append({"k": kk, "guides": n, "device_ms": dv * 1e3, "e2e_ms": ee * 1e3, "e2e_guides_per_s": n / ee,
+                             "jvm_published_s": jvm, "jvm_published_minus_44s_load_s": (jvm - 44.0) if jvm else None})
+        return {"rows": rows, "one_guide_e2e_latency_ms": [r["e2e_ms"] for r in rows if r["guides"] == 1 and r["k"] == 4][0],
+                "note": "database resident (the JVM's ~44 s are mostly its load); published JVM column: BASELINE.md section 1, one core, real hg38"}
+    if not args.no_ladder:
+        guard("batch_ladder", ladder)
+
+    # BASELINE.json configs[1]: 1 000 synthetic + 100 planted guides vs the chr22 quick-start database, when the database
+    # built by __graft_entry__.build() travelled with the tree (33.5 MB of targets: L2-resident after the first pass)
+    def chr22():
+        path = os.path.join(ROOT, "tests", "golden", "_chr22", "chr22_cas9ngg_database")
+        if not (os.path.exists(path) and os.path.exists(path + ".header")):
+            return {"skipped": "chr22 database not in the tree"}
+        c2 = ff.Context(dev.index)
+        t0 = time.perf_counter()
+        c2.load_database(path)
+        load_s = time.perf_counter() - t0
+        t22 = c2.copy_targets()
+        g22 = make_guides(1100, 1001, t22[:: max(1, len(t22) // 4096)], 1002, planted_frac=100.0 / 1100.0)
+        d22 = torch.from_numpy(g22.view(np.int64)).to(dev)
+        ts = []
+        for _ in range(8):
+            r22 = c2.discover_device(d22.data_ptr(), len(g22), k, args.max_ot, 0)
+            ts.append(c2.timings().total_ms)
+        res = {"workload": "configs[1]: 1 000 synthetic + 100 planted guides vs the chr22 quick-start index (%d targets), k<=%d" % (len(t22), k),
+               "total_ms": float(np.median(ts[2:])), "guides_per_s": len(g22) / (float(np.median(ts[2:])) / 1e3),
+               "hits": int(r22.n_hits), "cold_load_s": load_s,
+               "parity": "tests/test_gpu_parity.py::test_chr22_1000_guides_config (bit-exact vs the oracle)"}
+        c2.close()
+        return res
+    guard("chr22_1000_guides", chr22)
+
+    # Genome-like skew: 64 repeat neighbourhoods of 16 384 targets (consensus + 0..3 substitutions) inside the same-sized
+    # index, 1 % of the guides planted in them (thousands of candidates each: long segments, hot buckets, buffer growth)
+    def skewed():
+        c3 = ff.Context(dev.index)
+        c3.synth_database_skewed(ENZYME, args.targets, SEED_DB, 64, 16384, 3)
+        n3 = int(c3.info().n_targets)
+        rng = np.random.default_rng(5)
+        pool3 = np.concatenate([c3.copy_targets(int(s), 2048) for s in rng.integers(0, max(1, n3 - 2048), 16)])
+        g3 = make_guides(G, SEED_GUIDES, pool3, SEED_PLANTED, planted_frac=0.09)
+        # 1 % of the guides sit inside a neighbourhood: the family's consensus (the generator's formula, ff_db.cu
+        # k_synth_families) with 0..2 substitutions
+        n_pl = max(1, G // 100)
+        cons = family_consensus(SEED_DB, rng.integers(0, 64, n_pl))
+        for _ in range(2):
+            pos = rng.integers(0, 20, n_pl).astype(np.uint64)
+            x = rng.integers(0, 4, n_pl).astype(np.uint64) << (np.uint64(2) * (np.uint64(20) - pos))
+            cons = cons ^ x
+        g3[:n_pl] = (cons << np.uint64(4)) | np.uint64(0xA) | (np.uint64(1) << np.uint64(48))
+        d3 = torch.from_numpy(g3.view(np.int64)).to(dev)
+        ts = []
+        for _ in range(5):
+            r3 = c3.discover_device(d3.data_ptr(), len(g3), k, args.max_ot, 0)
+            t = c3.timings()
+            ts.append((t.total_ms, t.scan_ms, t.order_ms + t.cut_ms, t.scan_launches))
+        res = {"workload": "%d guides (1 %% planted inside repeat neighbourhoods) vs %d targets with 64 neighbourhoods of 16 384 (consensus + 0..3 substitutions)" % (len(g3), n3),
+               "total_ms": float(np.median([x[0] for x in ts[1:]])), "scan_ms": float(np.median([x[1] for x in ts[1:]])),
+               "order_cut_ms": float(np.median([x[2] for x in ts[1:]])), "scan_launches_steady_state": int(ts[-1][3]),
+               "hits": int(r3.n_hits), "candidate_hits": int(r3.n_candidate_hits), "planted_in_neighbourhoods": int(n_pl),
+               "guides_per_s": len(g3) / (float(np.median([x[0] for x in ts[1:]])) / 1e3),
+               "parity": "tests/test_gpu_scale.py::test_skewed_index_at_benchmark_size (2 048-guide oracle sample)"}
+        c3.close()
+        return res
+    if not args.no_skew:
+        guard("skewed_index", skewed)
+
+    if not args.no_cpu_baseline and world == 1:
+        guard("cpu_baseline", lambda: cpu_baseline(ctx, guides, args, threads=1, budget_guides=args.cpu_guides))
 
 
 def cpu_baseline(ctx, guides, args, threads, budget_guides):
@@ -404,7 +576,7 @@ def run_reference(args):
     n_t = len(t)
     rng = np.random.default_rng(17)
     pool = np.concatenate([t[int(s):int(s) + 2048] for s in rng.integers(0, max(1, n_t - 2048), 16)])
-    guides = make_guides(args.guides, SEED_GUIDES, pool, SEED_PLANTED)
+    guides = make_guides(args.guides or 100_000, SEED_GUIDES, pool, SEED_PLANTED)
     ctx.close()
     pack = o.PACK_BY_INDEX[ENZYME]
     bin_off = o.bin_offsets_from_sorted(pack, 7, t)
@@ -423,9 +595,11 @@ def run_reference(args):
                   "reference loop order on %d host threads" % (n, len(guides), n_t, threads))
     _emit({"impl": "reference", "metric": "guides/sec at <=4 mismatches vs hg38-sized index", "value": v, "unit": "guides/s",
                       "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                      "higher_is_better": True, "scaling": "weak", "vs_baseline": v / 53.7, "dtype": "u64", "data": "synthetic",
+                      "higher_is_better": True, "scaling": args.scaling, "vs_baseline": v / 53.7, "dtype": "u64", "data": "synthetic",
                       "config": {"workload": "configs[2] bounded sample: " + sample_txt, "targets": n_t, "max_mismatch": args.k,
-                                 "maximum_off_targets": args.max_ot},
+                                 "maximum_off_targets": args.max_ot,
+                                 "same_config_note": "rate over %d-guide batches (a 100 000-guide CPU step would take ~40 s); always ALL host threads, "
+                                                     "whatever --gpus says; the index is materialised by the product's generator, the timed region is the oracle only" % n},
                       "cpu_baseline": {"value": v, "unit": "guides/s", "cores": threads, "kind": "port", "sample": sample_txt},
                       "e2e": {"value": v, "unit": "guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
@@ -450,7 +624,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--targets", type=int, default=300_000_000)
-    ap.add_argument("--guides", type=int, default=100_000)
+    ap.add_argument("--guides", type=int, default=0, help="guides in the job (default: 100 000; 50 000 for --workload fused)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: ONE guide set sharded over the GPUs (BASELINE configs[2]); weak: the full batch on every GPU")
+    ap.add_argument("--workload", default="discover", choices=["discover", "fused", "bulge"],
+                    help="discover = configs[2]; fused = configs[4] (discover + CFD + Hsu2013 on the GPU, 50 000 guides); bulge = configs[3]")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline line (no side measurements)")
+    ap.add_argument("--no-ladder", action="store_true")
+    ap.add_argument("--no-skew", action="store_true")
     ap.add_argument("--k", type=int, default=4)
     ap.add_argument("--max-ot", dest="max_ot", type=int, default=2000)
     ap.add_argument("--cpu-guides", type=int, default=2048, help="guides in the cpu_baseline sample (single thread)")

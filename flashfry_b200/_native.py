@@ -50,12 +50,13 @@ class FFDeviceResult(C.Structure):
 class FFTimings(C.Structure):
     _fields_ = [("prep_ms", C.c_float), ("scan_ms", C.c_float), ("order_ms", C.c_float), ("cut_ms", C.c_float),
                 ("score_ms", C.c_float), ("total_ms", C.c_float), ("scan_launches", C.c_int),
-                ("kernel_launches", C.c_int), ("scan_bytes_read", C.c_uint64)]
+                ("kernel_launches", C.c_int), ("scan_bytes_read", C.c_uint64), ("scan_part1_ms", C.c_float),
+                ("scan_part2_ms", C.c_float), ("entries_part1", C.c_uint64), ("entries_part2", C.c_uint64)]
 
 
 # every symbol include/flashfry_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_set_option", "ff_load_database",
-           "ff_save_image", "ff_load_image", "ff_load_database_arrays", "ff_synth_database", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
+           "ff_save_image", "ff_load_image", "ff_load_database_arrays", "ff_synth_database", "ff_synth_database_skewed", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
            "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_db_host_targets", "ff_hits_resolve", "ff_score", "ff_score_enzyme", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings",
            "ff_multi_create", "ff_multi_destroy", "ff_multi_size", "ff_multi_ctx", "ff_multi_set_option", "ff_multi_load_database",
            "ff_multi_synth_database", "ff_shard_range", "ff_multi_discover", "ff_multi_device_totals"]
@@ -84,6 +85,7 @@ def lib():
     L.ff_load_database_arrays.argtypes = [vp, C.c_int, C.c_int, u64p, C.c_uint64, u64p, C.c_uint64,
                                           C.POINTER(C.c_char_p), C.c_int]
     L.ff_synth_database.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64]
+    L.ff_synth_database_skewed.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
     L.ff_db_info.argtypes = [vp, C.POINTER(FFDbInfo)]
     L.ff_db_contig.argtypes = [vp, C.c_int]
     L.ff_db_contig.restype = C.c_char_p

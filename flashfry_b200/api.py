@@ -99,7 +99,7 @@ class Context:
     def options(self, **kw):
         """Context manager: set options for a block, restore the defaults afterwards."""
         ctx = self
-        defaults = {"scan_kernel": 0, "force_general": 0, "window_cells": 0, "subbatch_min": 20000, "subbatch_c1": 65,
+        defaults = {"scan_kernel": 0, "force_general": 0, "window_cells": 0, "subbatch_min": 45000, "subbatch_c1": 65,
                     "subbatch_c2": 90, "group_sort": 1, "trace": 0, "b_spi": 0, "split_a": 0, "compact_hits": 0}
 
         class _O:
@@ -132,6 +132,9 @@ class Context:
 
     def synth_database(self, enzyme_index: int, n_targets: int, seed: int):
         N.check(N.lib().ff_synth_database(self._h, enzyme_index, n_targets, seed))
+
+    def synth_database_skewed(self, enzyme_index: int, n_targets: int, seed: int, n_families: int, family_size: int, family_subs: int = 3):
+        N.check(N.lib().ff_synth_database_skewed(self._h, enzyme_index, n_targets, seed, n_families, family_size, family_subs))
 
     def info(self) -> N.FFDbInfo:
         i = N.FFDbInfo()

@@ -109,6 +109,8 @@ static void add_timings(ff_timings *acc, const ff_timings &t) {
   acc->prep_ms += t.prep_ms; acc->scan_ms += t.scan_ms; acc->order_ms += t.order_ms; acc->cut_ms += t.cut_ms;
   acc->score_ms += t.score_ms; acc->total_ms += t.total_ms; acc->scan_launches += t.scan_launches;
   acc->kernel_launches += t.kernel_launches; acc->scan_bytes_read += t.scan_bytes_read;
+  acc->scan_part1_ms += t.scan_part1_ms; acc->scan_part2_ms += t.scan_part2_ms;
+  acc->entries_part1 += t.entries_part1; acc->entries_part2 += t.entries_part2;
 }
 
 // The host-facing discover: guides come from host memory, results go back to pinned host memory.  Large guide sets are
@@ -125,8 +127,9 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   if (n_guides > 0) FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides, n_guides * 8, cudaMemcpyHostToDevice, c->stream));
   const uint64_t *d_guides = c->scratch_guides.as<uint64_t>();
 
-  // Sub-batches of DECREASING size (65 / 25 / 10 %): the D2H of a sub-batch hides behind the scan of the next one, so
-  // only the last -- smallest -- copy is exposed, while the large first batches keep the scan's bucket reuse high.
+  // Sub-batches of DECREASING size: the D2H of a sub-batch hides behind the scan of the next one, so only the last --
+  // smallest -- copy is exposed.  Every sub-batch pays the bin scan's fixed cost (the whole index is staged once per
+  // call, ~0.25 ms on a human-sized index), which is why two sub-batches beat three at 100 000 guides.
   const int64_t min_batch = std::max(1, c->opt.subbatch_min);
   const int nb = want_positions ? 1 : (int)std::min<int64_t>(3, std::max<int64_t>(1, n_guides / min_batch));
   int kCut[4][4] = {{0, 0, 0, 0}, {0, 100, 100, 100}, {0, 60, 100, 100}, {0, 65, 90, 100}};  // cumulative % (A/B on the GPU: 7.5 ms per 100 000 guides; 50/30/20: 7.8 ms)
@@ -406,6 +409,17 @@ int ff_synth_database(ff_ctx *c, int enzyme_index, uint64_t n_targets, uint64_t 
     Pack pack;
     FF_TRY(pack_from_index(enzyme_index, &pack));
     return db_synth(c, pack, n_targets, seed);
+  });
+}
+
+int ff_synth_database_skewed(ff_ctx *c, int enzyme_index, uint64_t n_targets, uint64_t seed, uint64_t n_families, uint64_t family_size,
+                             int family_subs) {
+  return guarded([&]() -> int {
+    if (!c || family_subs < 0 || family_subs > 8) { set_error("bad argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    Pack pack;
+    FF_TRY(pack_from_index(enzyme_index, &pack));
+    return db_synth(c, pack, n_targets, seed, n_families, family_size, family_subs);
   });
 }
 

@@ -602,7 +602,8 @@ static bool bin_scan_supported(const Database &db, int hA, int64_t G) {
 }
 
 // Launch the set-up kernels (no host synchronisation) and fill the plan.
-static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, BinScanPlan *pl, int *launches) {
+static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, unsigned long long *n_compares_b, BinScanPlan *pl,
+                            int *launches) {
   Database &db = ctx->db;
   cudaStream_t st = ctx->stream;
   const int64_t G = sp.n_guides;
@@ -664,7 +665,7 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, B
   bp.next_bin = (unsigned int *)(w + o_ctr);
   PairParams &pp = pl->pp;
   pp.planes = db.B.d_planes; pp.off = db.B.d_off; pp.other = db.B.d_other; pp.canon = db.B.d_canon; pp.recs = recs;
-  pp.n_pairs = n_pairs; pp.lo_d = hA; pp.hs = bp.hs; pp.n_compares = sp.n_compares;
+  pp.n_pairs = n_pairs; pp.lo_d = hA; pp.hs = bp.hs; pp.n_compares = n_compares_b;
   pp.next_item = (unsigned long long *)(w + o_ctr + 64);
   pl->part_two = n_pairs > 0;
   pl->nb_a = db.A.n_planes / 2; pl->nb_b = db.B.n_planes / 2;
@@ -686,6 +687,7 @@ static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, u
   k_bin_scan<9><<<ctx->sm_count * 2, kBinThreads, pl->smem_a, st>>>(pl->bp);
   (*launches)++;
   if (pl->part_two) {
+    FF_CUDA(cudaEventRecord(ctx->ev[7], st));
     const int grid = ctx->sm_count * 3;
     const size_t qsm = (size_t)kPairWarps * kQCap * 16;
     if (pl->nb_b == 11) k_pair_scan<11><<<grid, kPairThreads, qsm, st>>>(pl->pp);

@@ -650,7 +650,27 @@ __global__ void k_synth_counts(uint64_t n, uint64_t seed, uint64_t family_every,
   t[i] = v | (c << 48);
 }
 
-int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed) {
+// repeat NEIGHBOURHOODS: member i of family f = the family's consensus with 0..max_subs random substitutions in the
+// protospacer (sequence-level skew: hot buckets, long candidate lists), written over the tail of the uniform values
+__global__ void k_synth_families(uint64_t n_fam, uint64_t fam_size, int max_subs, uint64_t seed, int random_bits, uint64_t pam_bits,
+                                 uint64_t *__restrict__ out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n_fam * fam_size) return;
+  const uint64_t f = i / fam_size;
+  uint64_t v = splitmix64(seed * 0x9E3779B97F4A7C15ull + 0xFA111E5ull + f) >> (64 - random_bits);
+  uint64_t h = splitmix64(seed ^ (i * 0xD6E8FEB86659FD93ull));
+  const int subs = (int)(h % (uint64_t)(max_subs + 1));
+  const int proto_bases = random_bits / 2 - 1;  // the last random base is the PAM's N
+  for (int s = 0; s < subs; ++s) {
+    h = splitmix64(h);
+    const int pos = (int)(h % (uint64_t)proto_bases);
+    const uint64_t x = 1ull + ((h >> 32) % 3ull);
+    v ^= x << (2 * (random_bits / 2 - 1 - pos));
+  }
+  out[i] = (v << 4) | pam_bits;
+}
+
+int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed, uint64_t n_families, uint64_t family_size, int family_subs) {
   if (pack.five_prime) { set_error("synthetic databases are spCas9-family only"); return FF_EUNSUPPORTED; }
   if (n_targets == 0 || n_targets > 3000000000ull) { set_error("bad synthetic database size"); return FF_EINVAL; }
   ctx->db.release();
@@ -664,6 +684,12 @@ int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed) {
   FF_CUDA(cudaMalloc(&d_b, (n_targets + 1) * 8));
   FF_CUDA(cudaMalloc(&d_n, 8));
   k_synth_values<<<(unsigned int)((n_targets + 255) / 256), 256, 0, st>>>(n_targets, seed, random_bits, pam_bits, d_a);
+  if (n_families * family_size > 0) {
+    if (n_families * family_size > n_targets / 2) { cudaFree(d_a); cudaFree(d_b); cudaFree(d_n); set_error("families larger than half the database"); return FF_EINVAL; }
+    const uint64_t nf = n_families * family_size;
+    k_synth_families<<<(unsigned int)((nf + 255) / 256), 256, 0, st>>>(n_families, family_size, family_subs, seed, random_bits, pam_bits,
+                                                                       d_a + (n_targets - nf));
+  }
   size_t tmp = 0;
   FF_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_a, d_b, n_targets, 0, 2 * pack.scan_len, st));
   FF_TRY(ctx->cub_tmp.reserve(tmp));

@@ -395,6 +395,7 @@ struct PlainStatus {
   unsigned long long n_cand, n_compares;
   long long n_hits;
   unsigned int flag, n_long;
+  unsigned long long n_compares_b;  // entries streamed by the part-two kernel of the bin scan (n_compares: part one)
 };
 
 __global__ void k_guide_hist(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ n_ptr, unsigned long long cap, int tbits,
@@ -572,7 +573,7 @@ __global__ void k_publish_status(const PlainStatus *__restrict__ stt, const int6
   if (threadIdx.x == 0) {
     host->n_cand = stt->n_cand; host->n_compares = stt->n_compares;
     host->n_hits = row_ptr_end ? *row_ptr_end : stt->n_hits;
-    host->flag = stt->flag; host->n_long = stt->n_long;
+    host->flag = stt->flag; host->n_long = stt->n_long; host->n_compares_b = stt->n_compares_b;
     __threadfence_system();
   }
 }
@@ -735,7 +736,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     bin_major = bin_major && bin_scan_supported(db, hA, G);
   }
   BinScanPlan bpl;
-  if (bin_major) FF_TRY(bin_scan_prepare(ctx, sp, hA, nB, &bpl, &launches));
+  if (bin_major) FF_TRY(bin_scan_prepare(ctx, sp, hA, nB, &d_stt->n_compares_b, &bpl, &launches));
   // Order the candidates with the per-guide pipeline (no host round trip) when segments are expected to be short.
   bool grouped = G > 0 && ctx->opt.group_sort != 0 && expected_per_guide <= 160.0;
   static bool long_attr[64] = {false};
@@ -867,11 +868,19 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   // bytes the scan kernels request (NOT the roofline's algorithmic bytes, see bench.py): per (guide, seed) the two index
   // entries, per streamed entry its bit-sliced planes (or its 4-byte word in the guide-major kernel), per guide its
   // long, per candidate hit one 8-byte key
-  tm.scan_bytes_read = (uint64_t)G * (uint64_t)(nA + nB) * 8ull + h_stt->n_compares * 4ull + (uint64_t)G * 8ull + (uint64_t)n_cand * 8ull;
+  const uint64_t ent_a = h_stt->n_compares, ent_b = h_stt->n_compares_b;
+  const double bpe_a = bin_major ? db.A.plane_stride * 4.0 / 32.0 : 4.0, bpe_b = bin_major ? db.B.plane_stride * 4.0 / 32.0 : 4.0;
+  tm.scan_bytes_read = (uint64_t)G * (uint64_t)(nA + nB) * 8ull + (uint64_t)(ent_a * bpe_a + ent_b * bpe_b) + (uint64_t)G * 8ull + (uint64_t)n_cand * 8ull;
+  tm.entries_part1 = ent_a; tm.entries_part2 = ent_b;
+  tm.scan_part1_ms = tm.scan_ms; tm.scan_part2_ms = 0.f;
+  if (bin_major && nB > 0 && G > 0) {
+    FF_CUDA(cudaEventElapsedTime(&tm.scan_part1_ms, ctx->ev[1], ctx->ev[7]));
+    FF_CUDA(cudaEventElapsedTime(&tm.scan_part2_ms, ctx->ev[7], ctx->ev[2]));
+  }
   ctx->last = tm;
 
   res->n_guides = G; res->n_hits = n_hits; res->n_positions = n_pos;
-  res->n_candidate_hits = (uint64_t)n_cand; res->n_compares = h_stt->n_compares;
+  res->n_candidate_hits = (uint64_t)n_cand; res->n_compares = ent_a + ent_b;
   res->d_row_ptr = os.row_ptr.as<int64_t>(); res->d_targets = os.out_targets.as<uint64_t>();
   res->d_mismatches = os.out_mm.as<uint8_t>(); res->d_total_count = os.total_count.as<int32_t>();
   res->d_overflowed = os.overflowed.as<uint8_t>(); res->d_bulge = nullptr;

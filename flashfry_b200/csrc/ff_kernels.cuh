@@ -53,6 +53,7 @@ int db_build_cell_offsets(ff_ctx *ctx);  // lazily: per-bucket offsets at the da
 int db_save_image(ff_ctx *ctx, const char *path);  // SoA side-car of the resident database
 int db_load_image(ff_ctx *ctx, const char *path);
 int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path);
-int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed);
+int db_synth(ff_ctx *ctx, const Pack &pack, uint64_t n_targets, uint64_t seed, uint64_t n_families = 0, uint64_t family_size = 0,
+             int family_subs = 3);
 
 }  // namespace ff

@@ -90,6 +90,11 @@ int ff_load_database_arrays(ff_ctx *ctx, int enzyme_index, int bin_width, const 
 /* Bench support: generate a synthetic spCas9-family database of ~n_targets distinct sorted targets directly in HBM
  * (uniform random protospacer+N, PAM per enzyme, count model of SURVEY.md 8(d) cfg 3).  No positions. */
 int ff_synth_database(ff_ctx *ctx, int enzyme_index, uint64_t n_targets, uint64_t seed);
+/* The same with sequence-level skew: n_families repeat neighbourhoods of family_size targets each, every member its
+ * family's consensus with 0..family_subs random substitutions (Alu-like: hot index buckets, guides with thousands of
+ * candidates).  Members replace uniform targets, duplicates collapse as usual. */
+int ff_synth_database_skewed(ff_ctx *ctx, int enzyme_index, uint64_t n_targets, uint64_t seed, uint64_t n_families,
+                             uint64_t family_size, int family_subs);
 
 typedef struct {
   int enzyme_index;      /* standards/StandardScanParameters.scala:61-80 */
@@ -244,7 +249,10 @@ typedef struct {
   float prep_ms, scan_ms, order_ms, cut_ms, score_ms, total_ms;
   int scan_launches;          /* >1 when the hit buffer had to grow and the scan was repeated */
   int kernel_launches;        /* kernels of this library launched by the call */
-  uint64_t scan_bytes_read;   /* algorithmic bytes of the scan kernel for this call */
+  uint64_t scan_bytes_read;   /* bytes the scan kernels REQUEST for this call (index entries + streamed planes + guides + hit
+                                 keys) -- not the roofline's algorithmic bytes, which bench.py computes per SURVEY.md 8(d) */
+  float scan_part1_ms, scan_part2_ms; /* bin scan: k_bin_scan (index A) / k_pair_scan (index B); else scan_ms / 0 */
+  uint64_t entries_part1, entries_part2; /* index entries compared by each */
 } ff_timings;
 int ff_last_timings(const ff_ctx *ctx, ff_timings *out);
 
