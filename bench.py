@@ -522,6 +522,14 @@ def _extras(out, ctx, ff, N, C, torch, dev, args, guides, d_guides, g_host, gp, 
     if not args.no_skew:
         guard("skewed_index", skewed)
 
+    # cold start at this size, in FlashFry's OWN on-disk format (BGZF body + .header, all bins indexed) and from the image side-car
+    def cold():
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import cold_start
+        return cold_start.measure(args.targets)
+    if not args.no_cold_start and world == 1:
+        guard("cold_start_flashfry_format", cold)
+
     if not args.no_cpu_baseline and world == 1:
         guard("cpu_baseline", lambda: cpu_baseline(ctx, guides, args, threads=1, budget_guides=args.cpu_guides))
 
@@ -632,6 +640,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="only the headline line (no side measurements)")
     ap.add_argument("--no-ladder", action="store_true")
     ap.add_argument("--no-skew", action="store_true")
+    ap.add_argument("--no-cold-start", action="store_true", help="skip writing + loading the index as a real FlashFry database (~40 s)")
     ap.add_argument("--k", type=int, default=4)
     ap.add_argument("--max-ot", dest="max_ot", type=int, default=2000)
     ap.add_argument("--cpu-guides", type=int, default=2048, help="guides in the cpu_baseline sample (single thread)")

@@ -26,8 +26,14 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "ff_common.cuh"
 #include "ff_kernels.cuh"
@@ -378,23 +384,38 @@ static int read_header(const char *path, HeaderInfo *h) {
   return FF_OK;
 }
 
-static int read_file(const char *path, std::vector<uint8_t> *out) {
-  FILE *f = fopen(path, "rb");
-  if (!f) { set_error("cannot open %s", path); return FF_EIO; }
-  fseek(f, 0, SEEK_END);
-  const long long n = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  out->resize((size_t)n);
-  const size_t got = n > 0 ? fread(out->data(), 1, (size_t)n, f) : 0;
-  fclose(f);
-  if ((long long)got != n) { set_error("short read on %s", path); return FF_EIO; }
-  return FF_OK;
-}
+// The BGZF body is mapped, not read: a human-sized database is ~4 GB on disk, the inflate threads page it in as they
+// go and nothing is copied.
+struct MappedFile {
+  const uint8_t *p = nullptr;
+  size_t n = 0;
+  int fd = -1;
+  int open_ro(const char *path) {
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) { set_error("cannot open %s", path); return FF_EIO; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { set_error("cannot stat %s", path); return FF_EIO; }
+    n = (size_t)st.st_size;
+    if (n == 0) return FF_OK;
+    void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) { set_error("cannot map %s", path); return FF_EIO; }
+    madvise(m, n, MADV_SEQUENTIAL);
+    p = static_cast<const uint8_t *>(m);
+    return FF_OK;
+  }
+  size_t size() const { return n; }
+  const uint8_t *data() const { return p; }
+  uint8_t operator[](size_t i) const { return p[i]; }
+  ~MappedFile() {
+    if (p) munmap(const_cast<uint8_t *>(p), n);
+    if (fd >= 0) ::close(fd);
+  }
+};
 
 struct Member { size_t off, len, hdr, isize, out_off; };
 
 // Walk the BGZF members through their BSIZE fields (SAM spec 4.1).
-static int scan_members(const std::vector<uint8_t> &raw, std::vector<Member> *ms) {
+static int scan_members(const MappedFile &raw, std::vector<Member> *ms) {
   size_t off = 0, out = 0;
   while (off < raw.size()) {
     if (off + 18 > raw.size() || raw[off] != 0x1f || raw[off + 1] != 0x8b || raw[off + 2] != 8 || !(raw[off + 3] & 4)) {
@@ -428,12 +449,12 @@ int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
   FF_TRY(read_header(header_path, &h));
   Pack pack;
   FF_TRY(pack_from_index(h.enzyme, &pack));
-  std::vector<uint8_t> raw;
-  FF_TRY(read_file(db_path, &raw));
+  MappedFile raw;
+  FF_TRY(raw.open_ro(db_path));
   std::vector<Member> ms;
   FF_TRY(scan_members(raw, &ms));
   const size_t total = ms.empty() ? 0 : ms.back().out_off + ms.back().isize;
-  std::vector<uint8_t> payload(total + 8);
+  std::unique_ptr<uint8_t[]> payload(new uint8_t[total + 8]);  // (uninitialised: every byte is written by an inflate)
 
   // inflate members on all host threads (they are independent gzip members)
   unsigned nthreads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
@@ -450,7 +471,7 @@ int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
           if (inflateInit2(&zs, -15) != Z_OK) { err[w] = 1; return; }
           zs.next_in = const_cast<Bytef *>(raw.data() + m.off + m.hdr);
           zs.avail_in = (uInt)(m.len - m.hdr - 8);
-          zs.next_out = payload.data() + m.out_off;
+          zs.next_out = payload.get() + m.out_off;
           zs.avail_out = (uInt)m.isize;
           const int rc = inflate(&zs, Z_FINISH);
           inflateEnd(&zs);
@@ -497,7 +518,7 @@ int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
     for (auto &t : pool) t.join();
   };
   auto block_body = [&](size_t b, const uint64_t **body, size_t *n_longs) -> bool {
-    const uint64_t *blk = reinterpret_cast<const uint64_t *>(payload.data() + bin_start[b]);  // little-endian host
+    const uint64_t *blk = reinterpret_cast<const uint64_t *>(payload.get() + bin_start[b]);  // little-endian host
     uint64_t first;
     memcpy(&first, blk, 8);
     const size_t nl = (size_t)h.nbytes[b] / 8;
@@ -523,7 +544,7 @@ int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
     bin_t[b + 1] += bin_t[b]; bin_p[b + 1] += bin_p[b];
   }
   const uint64_t n_targets = bin_t[n_bins], n_positions = bin_p[n_bins];
-  std::vector<uint64_t> targets(n_targets + 1), positions(n_positions + 1);
+  std::unique_ptr<uint64_t[]> targets(new uint64_t[n_targets + 1]), positions(new uint64_t[n_positions + 1]);
   // pass 2: fill
   for_bins([&](size_t b, unsigned) {
     const uint64_t *body = nullptr; size_t nl = 0;
@@ -537,7 +558,8 @@ int db_load_files(ff_ctx *ctx, const char *db_path, const char *header_path) {
       pi += c; i += 1 + c;
     }
   });
-  return db_from_host_arrays(ctx, pack, h.bin_width, targets.data(), n_targets, positions.data(), n_positions, h.contigs);
+  payload.reset();  // the inflated stream is no longer needed: release it before the upload
+  return db_from_host_arrays(ctx, pack, h.bin_width, targets.get(), n_targets, positions.get(), n_positions, h.contigs);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -583,39 +605,36 @@ int db_save_image(ff_ctx *ctx, const char *path) {
 }
 
 int db_load_image(ff_ctx *ctx, const char *path) {
-  FILE *f = fopen(path, "rb");
-  if (!f) { set_error("cannot open %s", path); return FF_EIO; }
+  MappedFile f;  // the arrays are uploaded straight from the mapping: no intermediate copies on the host
+  FF_TRY(f.open_ro(path));
   ImageHeader h;
-  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kImageMagic, 8) != 0 || h.version != 1) {
-    fclose(f);
+  if (f.size() < sizeof h) { set_error("%s is not a flashfry_b200 database image (bad magic or version)", path); return FF_EFORMAT; }
+  memcpy(&h, f.data(), sizeof h);
+  if (memcmp(h.magic, kImageMagic, 8) != 0 || h.version != 1) {
     set_error("%s is not a flashfry_b200 database image (bad magic or version)", path);
     return FF_EFORMAT;
   }
   Pack pack;
-  if (pack_from_index(h.enzyme_index, &pack) != FF_OK) { fclose(f); return FF_EFORMAT; }
-  {  // sizes come from the file: check them against its length before allocating anything
-    fseek(f, 0, SEEK_END);
-    const unsigned long long flen = (unsigned long long)ftell(f);
-    fseek(f, (long)sizeof h, SEEK_SET);
-    const bool ok_sizes = h.contig_bytes <= (1u << 28) && h.n_targets <= 0xFFFF0000ull && h.n_positions <= h.n_targets * 32767ull &&
-                          sizeof h + h.contig_bytes + 8ull * h.n_targets + 8ull * h.n_positions <= flen;
-    if (!ok_sizes) { fclose(f); set_error("implausible sizes in image %s", path); return FF_EFORMAT; }
+  if (pack_from_index(h.enzyme_index, &pack) != FF_OK) return FF_EFORMAT;
+  // sizes come from the file: check them against its length before trusting any of them
+  if (h.contig_bytes > (1u << 28) || (h.contig_bytes & 7) || h.n_targets > 0xFFFF0000ull || h.n_positions > h.n_targets * 32767ull) {
+    set_error("implausible sizes in image %s", path);
+    return FF_EFORMAT;
   }
-  std::string names(h.contig_bytes, '\0');
-  std::vector<uint64_t> targets(h.n_targets + 1), positions(h.n_positions + 1);
-  bool ok = h.contig_bytes == 0 || fread(&names[0], 1, h.contig_bytes, f) == h.contig_bytes;
-  ok = ok && (h.n_targets == 0 || fread(targets.data(), 8, h.n_targets, f) == h.n_targets);
-  ok = ok && (h.n_positions == 0 || fread(positions.data(), 8, h.n_positions, f) == h.n_positions);
-  fclose(f);
-  if (!ok) { set_error("truncated database image %s", path); return FF_EFORMAT; }
+  if (sizeof h + h.contig_bytes + 8ull * h.n_targets + 8ull * h.n_positions > f.size()) { set_error("truncated database image %s", path); return FF_EFORMAT; }
+  const char *names = reinterpret_cast<const char *>(f.data() + sizeof h);
   std::vector<std::string> contigs;
-  for (size_t i = 0, k = 0; k < h.n_contigs && i < names.size(); ++k) {
-    contigs.emplace_back(names.c_str() + i);
-    i += contigs.back().size() + 1;
+  for (size_t i = 0, k = 0; k < h.n_contigs && i < h.contig_bytes; ++k) {
+    const size_t len = strnlen(names + i, h.contig_bytes - i);
+    if (i + len >= h.contig_bytes) break;  // a name must end inside the table
+    contigs.emplace_back(names + i, len);
+    i += len + 1;
   }
   if (contigs.size() != h.n_contigs) { set_error("contig table of %s is damaged", path); return FF_EFORMAT; }
+  const uint64_t *targets = reinterpret_cast<const uint64_t *>(f.data() + sizeof h + h.contig_bytes);
+  const uint64_t *positions = targets + h.n_targets;
   // the index build re-validates order and counts on the device (FF_EFORMAT on a damaged image)
-  return db_from_host_arrays(ctx, pack, h.bin_width, targets.data(), h.n_targets, h.n_positions ? positions.data() : nullptr, h.n_positions, contigs);
+  return db_from_host_arrays(ctx, pack, h.bin_width, targets, h.n_targets, h.n_positions ? positions : nullptr, h.n_positions, contigs);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -313,3 +313,31 @@ def test_bulge_templates_are_equivalent_to_the_alignments(oracle):
             assert masked_mm(tr, enc(t), wr) == ham(g[:q] + g[q + 1:], t[1:])
             td, wd = template(enc(g), 2, q)
             assert masked_mm(td, enc(t), wd) == ham(g[1:], t[:q] + t[q + 1:])
+
+
+def test_streaming_database_writer_equals_the_object_writer(tmp_path):
+    """oracle/big_db.py (the streaming writer bench.py's cold-start measurement uses for a 3e8-target database) against
+    ff_oracle's per-bin writer, which the md5-pinned chr22 database comes from: same inflated blocks (linear AND indexed
+    bins), same header semantics, read back by the oracle's reader."""
+    import numpy as np
+    from oracle import big_db, ff_oracle as o
+    pack = o.PACK_BY_INDEX[3]
+    rng = np.random.default_rng(4)
+    # 40 crowded 7-mer bins (> 500 targets: indexed blocks) on a sparse background (linear blocks, many empty bins)
+    crowded = [(np.uint64(int(b)) << np.uint64(28)) | rng.integers(0, 1 << 28, 900, dtype=np.uint64) for b in rng.integers(0, 4 ** 7, 40)]
+    seq = np.unique(np.concatenate(crowded + [rng.integers(0, 1 << 42, 5000, dtype=np.uint64)]))
+    seq = (seq << np.uint64(4)) | np.uint64(0xA)
+    counts = rng.integers(1, 5, len(seq)).astype(np.int64)
+    counts[::997] = 700
+    targets = seq | (counts.astype(np.uint64) << np.uint64(48))
+    st = big_db.write_big_database(str(tmp_path / "big"), pack, targets, threads=4, bins_per_run=100)
+    assert st["indexed_bins"] >= 30 and st["positions"] == int(counts.sum())
+    pos = big_db.synthetic_positions(0, int(counts.sum()))
+    blocks, ntargets = o.make_blocks(pack, 7, seq, counts, pos)
+    o.write_database(str(tmp_path / "small"), pack, 7, blocks, ntargets, ["chrSynth%d" % (i + 1) for i in range(24)])
+    a, b = o.read_database(str(tmp_path / "big")), o.read_database(str(tmp_path / "small"))
+    for x, y in zip(a.soa(), b.soa()):
+        assert (x == y).all()
+    pa, _ = o.bgzf_inflate_all(str(tmp_path / "big"))
+    pb, _ = o.bgzf_inflate_all(str(tmp_path / "small"))
+    assert pa == pb  # the same block stream, byte for byte (member boundaries and compression level may differ)
