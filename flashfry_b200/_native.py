@@ -32,6 +32,10 @@ class FFHits(C.Structure):
                 ("bulge", C.POINTER(C.c_uint8)), ("target_index", C.POINTER(C.c_uint32))]
 
 
+class FFTsvGuide(C.Structure):
+    _fields_ = [("contig", C.c_char_p), ("start", C.c_int32), ("bases", C.c_char_p), ("context", C.c_char_p), ("forward", C.c_int32)]
+
+
 class FFDbInfo(C.Structure):
     _fields_ = [("enzyme_index", C.c_int), ("bin_width", C.c_int), ("scan_len", C.c_int), ("pam_len", C.c_int),
                 ("five_prime_pam", C.c_int), ("cmp_mask", C.c_uint64), ("n_targets", C.c_uint64),
@@ -57,7 +61,7 @@ class FFTimings(C.Structure):
 # every symbol include/flashfry_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set_stream", "ff_set_option", "ff_load_database",
            "ff_save_image", "ff_load_image", "ff_load_database_arrays", "ff_synth_database", "ff_synth_database_skewed", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
-           "ff_discover", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_db_host_targets", "ff_hits_resolve", "ff_score", "ff_score_enzyme", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings",
+           "ff_discover", "ff_hits_write_tsv", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_db_host_targets", "ff_hits_resolve", "ff_score", "ff_score_enzyme", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings",
            "ff_multi_create", "ff_multi_destroy", "ff_multi_size", "ff_multi_ctx", "ff_multi_set_option", "ff_multi_load_database",
            "ff_multi_synth_database", "ff_shard_range", "ff_multi_discover", "ff_multi_device_totals"]
 
@@ -93,6 +97,7 @@ def lib():
     L.ff_discover.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(FFHits))]
     L.ff_discover_bulge.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(FFHits))]
     L.ff_discover_bulge_device.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(FFDeviceResult)]
+    L.ff_hits_write_tsv.argtypes = [vp, C.c_char_p, C.POINTER(FFTsvGuide), C.POINTER(FFHits), C.c_int]
     L.ff_hits_free.argtypes = [C.POINTER(FFHits)]
     L.ff_hits_free.restype = None
     L.ff_db_host_targets.argtypes = [vp]

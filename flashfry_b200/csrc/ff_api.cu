@@ -520,6 +520,76 @@ int ff_hits_resolve(ff_ctx *c, ff_hits *h) {
   });
 }
 
+int ff_hits_write_tsv(ff_ctx *c, const char *path, const ff_tsv_guide *guides, const ff_hits *h, int write_positions) {
+  return guarded([&]() -> int {
+    if (!c || !path || !h || (h->n_guides > 0 && !guides)) { set_error("null argument"); return FF_EINVAL; }
+    if (!c->db.resident) { set_error("no database resident in this context"); return FF_ENODB; }
+    const uint64_t *mirror = nullptr;
+    if (!h->targets && h->n_hits > 0) {
+      if (!h->target_index) { set_error("hit list carries neither targets nor indices"); return FF_EINVAL; }
+      mirror = ff_db_host_targets(c);
+      if (!mirror) return FF_ENOMEM;
+    }
+    if (write_positions && h->n_hits > 0 && !h->pos_ptr) { set_error("positions were not requested from ff_discover"); return FF_EINVAL; }
+    FILE *f = fopen(path, "w");
+    if (!f) { set_error("cannot write %s", path); return FF_EIO; }
+    const int L = c->db.pack.scan_len;
+    const uint64_t cmp_mask = c->db.pack.cmp_mask;
+    std::string buf;
+    buf.reserve(1 << 22);
+    buf += "contig\tstart\tstop\ttarget\tcontext\toverflow\torientation\totCount\toffTargets\n";
+    char num[32];
+    auto put_int = [&](long long v) { buf.append(num, (size_t)snprintf(num, sizeof num, "%lld", v)); };
+    bool ok = true;
+    for (int64_t g = 0; g < h->n_guides && ok; ++g) {
+      const ff_tsv_guide &gd = guides[g];
+      buf += gd.contig ? gd.contig : "";
+      buf += '\t'; put_int(gd.start);
+      buf += '\t'; put_int((long long)gd.start + (long long)strlen(gd.bases ? gd.bases : ""));
+      buf += '\t'; buf += gd.bases ? gd.bases : "";
+      buf += '\t'; buf += gd.context ? gd.context : "NONE";
+      buf += h->overflowed[g] ? "\tOVERFLOW\t" : "\tOK\t";
+      buf += gd.forward ? "FWD\t" : "RVS\t";
+      put_int(h->total_count[g]);  // == the summed counts of the listed hits (CRISPRSiteOT.currentTotal)
+      buf += '\t';
+      for (int64_t i = h->row_ptr[g]; i < h->row_ptr[g + 1]; ++i) {
+        if (i > h->row_ptr[g]) buf += ',';
+        uint64_t t;
+        if (h->targets) t = h->targets[i];
+        else if (h->target_index[i] < c->host_targets_n) t = mirror[h->target_index[i]];
+        else { set_error("hit list holds a database index out of range"); ok = false; break; }
+        char seq[25];
+        for (int b = 0; b < L; ++b) seq[b] = "ACGT"[(t >> (2 * (L - 1 - b))) & 3];  // BitEncoding.bitDecodeString :85-99
+        buf.append(seq, (size_t)L);
+        buf += '_'; put_int((long long)(int16_t)(t >> 48));
+        buf += '_'; put_int(h->mismatches[i]);
+        (void)cmp_mask;
+        if (h->bulge && h->bulge[i]) { buf += (h->bulge[i] & 0xC0) == 0x40 ? "_R" : "_D"; put_int(h->bulge[i] & 0x3F); }
+        if (write_positions && h->pos_ptr[i + 1] > h->pos_ptr[i]) {
+          buf += '<';
+          for (int64_t p = h->pos_ptr[i]; p < h->pos_ptr[i + 1]; ++p) {  // BitPosition.decode :72-92
+            const uint64_t pl = h->positions[p];
+            const int contig = (int)((pl >> 32) & 0xFFFFF);
+            if (p > h->pos_ptr[i]) buf += '|';
+            if (contig >= 1 && contig <= (int)c->db.contigs.size()) buf += c->db.contigs[contig - 1];
+            else { set_error("position refers to contig %d, the database has %zu", contig, c->db.contigs.size()); ok = false; break; }
+            buf += ':'; put_int((long long)(pl & 0xFFFFFFFFull));
+            buf += ((pl >> 60) & 0xF) == 0 ? "^F" : "^R";
+          }
+          buf += '>';
+        }
+      }
+      buf += '\n';
+      if (buf.size() > (1u << 22) - 65536) { ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size(); buf.clear(); }
+    }
+    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    const bool closed = fclose(f) == 0;
+    if (!ok) { if (!*ff_last_error()) set_error("short write on %s", path); return FF_EIO; }
+    if (!closed) { set_error("short write on %s", path); return FF_EIO; }
+    return FF_OK;
+  });
+}
+
 void ff_hits_free(ff_hits *h) {
   if (!h || !h->opaque) return;
   owner_put(static_cast<HitsOwner *>(h->opaque));

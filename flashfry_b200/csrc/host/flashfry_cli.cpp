@@ -81,16 +81,28 @@ int runDiscover(int argc, char **argv) {
   ResultsAggregator guideStorage(std::move(guideOTs));
 
   fprintf(stderr, "scanning against the known targets from the genome with %zu guides\n", guideStorage.wrappedGuides.size());
+  // The TSV fast path: the CSR hit list goes straight to FlashFry's discover grammar through
+  // ff_hits_write_tsv -- no CRISPRHit object per hit (GpuTraverser::scan in flashfry_host.hpp is the object-building
+  // variant a Traverser drop-in needs; host_selftest exercises it).
   NativeContext nc(device);
   const auto t0 = std::chrono::steady_clock::now();
-  const uint64_t compares = GpuTraverser::scan(nc, a.get("database"), guideStorage, maxMismatch, positions, bulgeFlags);
+  ffCheck(ff_load_database(nc.ctx, a.get("database").c_str(), (a.get("database") + ".header").c_str()));
+  std::vector<uint64_t> guideLongs;
+  std::vector<ff_tsv_guide> rows;
+  for (auto &g : guideStorage.wrappedGuides) {
+    guideLongs.push_back(g.longEncoding);
+    rows.push_back({g.target.contig.c_str(), g.target.start(), g.target.bases.c_str(),
+                    g.target.sequenceContext.empty() ? nullptr : g.target.sequenceContext.c_str(), g.target.forwardStrand ? 1 : 0});
+  }
+  ff_hits *h = nullptr;
+  if (bulgeFlags) ffCheck(ff_discover_bulge(nc.ctx, guideLongs.data(), (int64_t)guideLongs.size(), maxMismatch, maximumOffTargets, bulgeFlags, positions ? 1 : 0, &h));
+  else ffCheck(ff_discover(nc.ctx, guideLongs.data(), (int64_t)guideLongs.size(), maxMismatch, maximumOffTargets, positions ? 1 : 0, &h));
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  fprintf(stderr, "Performed a total of %llu guide to target comparisons (load + scan %.3f s)\n", (unsigned long long)compares, secs);
+  fprintf(stderr, "Performed a total of %llu guide to target comparisons (load + scan %.3f s)\n", (unsigned long long)h->n_compares, secs);
   fprintf(stderr, "Writing final output for %zu guides\n", guideStorage.wrappedGuides.size());
-
-  TabDelimitedOutput output(a.get("output"), bitCoder, header.bitPosition, {}, true, positions);
-  for (auto &g : guideStorage.wrappedGuides) output.write(g);
-  output.close();
+  const int rc = ff_hits_write_tsv(nc.ctx, a.get("output").c_str(), rows.data(), h, positions ? 1 : 0);
+  ff_hits_free(h);
+  ffCheck(rc);
   return 0;
 }
 

@@ -456,39 +456,22 @@ struct HitAggregates {
   }
 };
 
-// scoring/ClosestHit.scala:43-76 ("minot") -- integer aggregate over the same hit list; on the GPU when a native context
-// is supplied (ff_hit_aggregates), otherwise the same reduction on the host
+// scoring/ClosestHit.scala:43-76 ("minot") -- integer aggregate over the same hit list, on the GPU (ff_hit_aggregates)
 struct ClosestHit : ScoreModel {
   NativeContext *nc = nullptr;
   std::string scoreName() const override { return "closest"; }
   std::vector<std::string> headerColumns() const override { return {"basesDiffToClosestHit", "closestHitCount", "0-1-2-3-4_mismatch"}; }
   bool validOverEnzyme(const ParameterPack &) const override { return true; }
-  void scoreGuides(std::vector<CRISPRSiteOT> &guides, const BitEncoding &bitEnc, const ParameterPack &pack) override {
-    if (nc) {
-      HitAggregates agg(*nc, pack, guides);
-      for (size_t i = 0; i < guides.size(); ++i) {
-        std::string hs;
-        for (int m = 0; m < 5; ++m) hs += (m ? "," : "") + std::to_string(agg.hist[i * 5 + m]);
-        const bool none = agg.closest[i] == INT32_MAX;
-        guides[i].namedAnnotations["basesDiffToClosestHit"] = {none ? "UNK" : std::to_string(agg.closest[i])};
-        guides[i].namedAnnotations["closestHitCount"] = {none ? "0" : std::to_string(agg.count[i])};
-        guides[i].namedAnnotations["0-1-2-3-4_mismatch"] = {hs};
-      }
-      return;
-    }
-    for (auto &g : guides) {
-      int closest = INT32_MAX, count = 0, hist[5] = {0, 0, 0, 0, 0};
-      for (auto &ot : g.offTargets) {
-        const int mm = bitEnc.mismatches(ot.sequence, g.longEncoding), c = bitEnc.getCount(ot.sequence);
-        if (mm <= 4) hist[mm] += c;
-        if (mm < closest && mm > 0) { closest = mm; count = c; }
-        else if (mm == closest) count += c;
-      }
+  void scoreGuides(std::vector<CRISPRSiteOT> &guides, const BitEncoding &, const ParameterPack &pack) override {
+    if (!nc) throw IllegalStateException("ClosestHit needs a native context: the reduction runs on the GPU, there is no host path");
+    HitAggregates agg(*nc, pack, guides);
+    for (size_t i = 0; i < guides.size(); ++i) {
       std::string hs;
-      for (int i = 0; i < 5; ++i) hs += (i ? "," : "") + std::to_string(hist[i]);
-      g.namedAnnotations["basesDiffToClosestHit"] = {closest == INT32_MAX ? "UNK" : std::to_string(closest)};
-      g.namedAnnotations["closestHitCount"] = {closest == INT32_MAX ? "0" : std::to_string(count)};
-      g.namedAnnotations["0-1-2-3-4_mismatch"] = {hs};
+      for (int m = 0; m < 5; ++m) hs += (m ? "," : "") + std::to_string(agg.hist[i * 5 + m]);
+      const bool none = agg.closest[i] == INT32_MAX;
+      guides[i].namedAnnotations["basesDiffToClosestHit"] = {none ? "UNK" : std::to_string(agg.closest[i])};
+      guides[i].namedAnnotations["closestHitCount"] = {none ? "0" : std::to_string(agg.count[i])};
+      guides[i].namedAnnotations["0-1-2-3-4_mismatch"] = {hs};
     }
   }
 };
@@ -500,9 +483,9 @@ struct DangerousSequences : ScoreModel {
   std::string scoreName() const override { return "dangerous"; }
   std::vector<std::string> headerColumns() const override { return {"dangerous_GC", "dangerous_polyT", "dangerous_in_genome"}; }
   bool validOverEnzyme(const ParameterPack &) const override { return true; }
-  void scoreGuides(std::vector<CRISPRSiteOT> &guides, const BitEncoding &bitEnc, const ParameterPack &pack) override {
-    std::unique_ptr<HitAggregates> agg;
-    if (nc) agg.reset(new HitAggregates(*nc, pack, guides));
+  void scoreGuides(std::vector<CRISPRSiteOT> &guides, const BitEncoding &, const ParameterPack &pack) override {
+    if (!nc) throw IllegalStateException("DangerousSequences needs a native context: the in-genome count runs on the GPU");
+    HitAggregates agg(*nc, pack, guides);
     size_t gi = 0;
     for (auto &g : guides) {
       std::string p0 = cleanOutput ? "0" : "NONE", p1 = p0, p2 = p0;
@@ -511,11 +494,7 @@ struct DangerousSequences : ScoreModel {
       else if (gc < .25 || gc > .75) p0 = "GC_" + javaDoubleToString(gc);
       auto r = pack.guideRange();
       if (g.target.bases.substr(r.first, r.second - r.first).find("TTTT") != std::string::npos) p1 = cleanOutput ? "1" : "PolyT";
-      int inGenome = 0;
-      if (agg) inGenome = agg->inGenome[gi];
-      else
-        for (auto &ot : g.offTargets)
-          if (bitEnc.mismatches(ot.sequence, g.longEncoding) == 0) inGenome += bitEnc.getCount(ot.sequence);
+      const int inGenome = agg.inGenome[gi];
       ++gi;
       if (inGenome > 0) p2 = cleanOutput ? std::to_string(inGenome) : "IN_GENOME=" + std::to_string(inGenome);
       g.namedAnnotations["dangerous_GC"] = {p0};

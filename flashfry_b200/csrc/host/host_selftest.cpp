@@ -39,11 +39,32 @@ int main(int argc, char **argv) {
                s.sequenceContext.empty() ? "NONE" : s.sequenceContext.c_str());
       return 0;
     }
+    if (argc >= 5 && std::string(argv[1]) == "traverse") {  // needs a GPU: the object-building Traverser drop-in
+      // (GpuTraverser::scan -> CRISPRHit per hit -> TabDelimitedOutput), what FlashFry's own discover does after a
+      // Traverser.scan; the CLI writes the same file through ff_hits_write_tsv without the objects
+      const std::string db = argv[2];
+      const bool positions = argc >= 6 && std::string(argv[5]) == "positions";
+      const int maxMismatch = argc >= 7 ? atoi(argv[6]) : 4, maxOT = argc >= 8 ? atoi(argv[7]) : 2000;
+      BinaryHeader header = BinaryHeader::readHeader(db + ".header");
+      const ParameterPack &pack = *header.inputParameterPack;
+      BitEncoding be(pack);
+      GuideMemoryStorage found;
+      findTargetSites(argv[3], &found, pack, 6);
+      std::vector<CRISPRSiteOT> ots;
+      for (auto &g : found.guideHits) ots.push_back({g, be.bitEncodeString(g.bases, 1), maxOT});
+      ResultsAggregator agg(std::move(ots));
+      NativeContext nc(0);
+      GpuTraverser::scan(nc, db, agg, maxMismatch, positions);
+      TabDelimitedOutput out(argv[4], be, header.bitPosition, {}, true, positions);
+      for (auto &g : agg.wrappedGuides) out.write(g);
+      out.close();
+      return 0;
+    }
     if (argc >= 3 && std::string(argv[1]) == "double") {
       for (int i = 2; i < argc; ++i) printf("%s\n", javaDoubleToString(strtod(argv[i], nullptr)).c_str());
       return 0;
     }
-    fprintf(stderr, "usage: host_selftest roundtrip ENZYME_INDEX in.tsv out.tsv [positions] | sites ENZYME_INDEX fasta flank | double x...\n");
+    fprintf(stderr, "usage: host_selftest roundtrip ENZYME_INDEX in.tsv out.tsv [positions] | sites ENZYME_INDEX fasta flank | traverse DB FASTA OUT [positions|nopos] [maxMismatch] [maxOT] | double x...\n");
     return 2;
   } catch (const std::exception &e) {
     fprintf(stderr, "error: %s\n", e.what());

@@ -154,6 +154,23 @@ int ff_discover(ff_ctx *ctx, const uint64_t *guides, int64_t n_guides, int max_m
                 int want_positions, ff_hits **out);
 void ff_hits_free(ff_hits *hits);
 
+/* ---- discover TSV fast path (replaces TabDelimitedOutput.write for `discover`) --------------------------------------
+ * Writes FlashFry's discover TSV (targetio/TabDelimitedHandler.scala:119-154: header line, one row per guide --
+ * contig, start, stop, target, context, overflow, orientation, otCount, offTargets -- tokens SEQ_count_mm joined by
+ * commas, crispr/CRISPRHit.scala:54-88; with write_positions the <contig:start^F|...> suffix of :75-81) straight from the
+ * CSR, without building a CRISPRHit per hit (1e7 JVM objects for 100 000 guides) and without `score` re-parsing text it
+ * could have had in memory.  guides[g] describes row g (what CRISPRSite holds); guide_longs[g] its encoding.  Works on
+ * compact hit lists too (option compact_hits: target longs are looked up in the host mirror).  Bulge hit lists add the
+ * _R<q> / _D<q> field of the CLI's --bulge extension. */
+typedef struct {
+  const char *contig;
+  int32_t start;        /* CRISPRSite.position; stop = start + strlen(bases) */
+  const char *bases;    /* the guide incl. PAM, as found in the FASTA */
+  const char *context;  /* flanked sequence, or NULL for "NONE" */
+  int32_t forward;      /* 1 = FWD, 0 = RVS */
+} ff_tsv_guide;
+int ff_hits_write_tsv(ff_ctx *ctx, const char *path, const ff_tsv_guide *guides, const ff_hits *hits, int write_positions);
+
 /* ---- EXTENSION: 1-bp bulge mode (BASELINE.json configs[3]) --------------------------------------------------
  * NOT a replacement of anything: the reference has no gap / bulge / edit-distance search (no match for
  * bulge|gap|indel|levenshtein under src/main), so there is no reference behaviour to be bit-exact with.  Semantics

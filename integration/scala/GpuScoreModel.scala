@@ -3,7 +3,7 @@ package scoring
 
 /** Doench2016CFDScore / CrisprMitEduOffTarget on the GPU: same names, columns and validity rules, so
   * `ScoreResults.getRegisteredScoringMetric` can hand these out for "doench2016cfd" / "hsu2013". */
-class GpuScoreModel(metric: Int) extends ScoreModel {
+class GpuScoreModel(metric: Int, ctx: Long) extends ScoreModel {
   private val cpu: ScoreModel = if (metric == 1) new Doench2016CFDScore() else new CrisprMitEduOffTarget()
   def scoreName() = cpu.scoreName(); def scoreDescription() = cpu.scoreDescription(); def headerColumns() = cpu.headerColumns()
   def validOverEnzyme(e: ParameterPack) = cpu.validOverEnzyme(e)
@@ -14,7 +14,7 @@ class GpuScoreModel(metric: Int) extends ScoreModel {
     if (!validOverEnzyme(pack)) { guides.foreach(g => headerColumns().foreach(c => g.namedAnnotations(c) = Array("NA"))); return }
     val rowPtr  = guides.scanLeft(0L)(_ + _.offTargets.size)
     val targets = guides.flatMap(_.offTargets.map(_.sequence))
-    val out = flashfry.NativeBridge.score(GpuTraverser.ctx, guides.map(_.longEncoding), rowPtr, targets, metric)
+    val out = flashfry.NativeBridge.score(ctx, pack.enzyme.index, guides.map(_.longEncoding), rowPtr, targets, metric)
     guides.zipWithIndex.foreach { case (g, i) =>
       if (metric == 1) {
         g.namedAnnotations("DoenchCFD_maxOT") = Array(out(0)(i).toString)                 // already thresholded at 0.023

@@ -1,12 +1,14 @@
-/* Minimal stand-in for the JDK's <jni.h>: ONLY for the syntax check of integration/jni/flashfry_b200_jni.c in an image
- * without a JDK.  It declares the JNI types and the handful of JNIEnv functions the shim uses, with the signatures of
- * the JNI specification; it is not a usable JNI header and nothing links against it. */
+/* Stand-in for the JDK's <jni.h> in an image without a JDK.  It declares the JNI types and the JNIEnv functions the shim
+ * (integration/jni/flashfry_b200_jni.c) uses, with the signatures of the JNI specification.  tests/stubs/jni_mock.c
+ * implements them over heap objects, so the shim can be EXECUTED by a C driver (tests/stubs/jni_exec.c); only the
+ * member ORDER of the function table differs from a real JNIEnv (nothing here is binary-compatible with a JVM). */
 #ifndef FF_TEST_STUB_JNI_H
 #define FF_TEST_STUB_JNI_H
 #include <stdint.h>
 
 typedef int32_t jint;
 typedef int64_t jlong;
+typedef int8_t jbyte;
 typedef uint8_t jboolean;
 typedef double jdouble;
 typedef jint jsize;
@@ -15,6 +17,9 @@ typedef jobject jclass;
 typedef jobject jstring;
 typedef jobject jarray;
 typedef jarray jlongArray;
+typedef jarray jintArray;
+typedef jarray jbyteArray;
+typedef jarray jbooleanArray;
 typedef jarray jdoubleArray;
 typedef jarray jobjectArray;
 #define JNIEXPORT __attribute__((visibility("default")))
@@ -29,16 +34,20 @@ struct JNINativeInterface_ {
   const char *(*GetStringUTFChars)(JNIEnv *, jstring, jboolean *);
   void (*ReleaseStringUTFChars)(JNIEnv *, jstring, const char *);
   jsize (*GetArrayLength)(JNIEnv *, jarray);
-  void *(*GetPrimitiveArrayCritical)(JNIEnv *, jarray, jboolean *);
-  void (*ReleasePrimitiveArrayCritical)(JNIEnv *, jarray, void *, jint);
   jlongArray (*NewLongArray)(JNIEnv *, jsize);
   void (*SetLongArrayRegion)(JNIEnv *, jlongArray, jsize, jsize, const jlong *);
-  jlong *(*GetLongArrayElements)(JNIEnv *, jlongArray, jboolean *);
-  void (*ReleaseLongArrayElements)(JNIEnv *, jlongArray, jlong *, jint);
+  void (*GetLongArrayRegion)(JNIEnv *, jlongArray, jsize, jsize, jlong *);
+  jintArray (*NewIntArray)(JNIEnv *, jsize);
+  void (*SetIntArrayRegion)(JNIEnv *, jintArray, jsize, jsize, const jint *);
+  void (*GetIntArrayRegion)(JNIEnv *, jintArray, jsize, jsize, jint *);
+  jbyteArray (*NewByteArray)(JNIEnv *, jsize);
+  void (*SetByteArrayRegion)(JNIEnv *, jbyteArray, jsize, jsize, const jbyte *);
+  void (*GetBooleanArrayRegion)(JNIEnv *, jbooleanArray, jsize, jsize, jboolean *);
   jdoubleArray (*NewDoubleArray)(JNIEnv *, jsize);
-  jdouble *(*GetDoubleArrayElements)(JNIEnv *, jdoubleArray, jboolean *);
-  void (*ReleaseDoubleArrayElements)(JNIEnv *, jdoubleArray, jdouble *, jint);
+  void (*SetDoubleArrayRegion)(JNIEnv *, jdoubleArray, jsize, jsize, const jdouble *);
   jobjectArray (*NewObjectArray)(JNIEnv *, jsize, jclass, jobject);
   void (*SetObjectArrayElement)(JNIEnv *, jobjectArray, jsize, jobject);
+  jobject (*GetObjectArrayElement)(JNIEnv *, jobjectArray, jsize);
+  jobject (*NewDirectByteBuffer)(JNIEnv *, void *, jlong);
 };
 #endif

@@ -224,7 +224,7 @@ def test_integration_sources_match_the_document_and_the_jni_shim_type_checks():
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     java = open(os.path.join(ROOT, "integration", "java", "flashfry", "NativeBridge.java")).read()
-    natives = set(re.findall(r"public static native [\w\[\]]+\s+(\w+)\(", java))
+    natives = set(re.findall(r"public static native [\w\[\].]+\s+(\w+)\(", java))
     exported = set(re.findall(r"Java_flashfry_NativeBridge_(\w+)\(", open(shim).read()))
     assert natives == exported and len(natives) >= 10
 
