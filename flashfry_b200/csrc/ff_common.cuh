@@ -135,6 +135,7 @@ struct ff_ctx {
   // Status words of a call (candidate count, flags, hit count), written by the last kernel straight into MAPPED pinned
   // host memory: a cudaMemcpy of these few bytes would queue behind the previous sub-batch's hit-list D2H in the copy engine.
   void *h_status = nullptr, *h_status_dev = nullptr;
+  unsigned int status_seq = 0;
   ff::DevBuf pos_cnt, pos_ptr, out_positions;
   ff::DevBuf cfd_per_ot, hsu_per_ot;
   ff::DevBuf scratch_guides;  // H2D staging target for ff_discover

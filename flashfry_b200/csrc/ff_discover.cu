@@ -396,6 +396,7 @@ struct PlainStatus {
   long long n_hits;
   unsigned int flag, n_long;
   unsigned long long n_compares_b;  // entries streamed by the part-two kernel of the bin scan (n_compares: part one)
+  unsigned int seq;                 // host mirror only: sequence number of the publication (written last)
 };
 
 __global__ void k_guide_hist(const uint64_t *__restrict__ keys, const unsigned long long *__restrict__ n_ptr, unsigned long long cap, int tbits,
@@ -569,13 +570,33 @@ __global__ void __launch_bounds__(256) k_sort_cut(uint32_t *__restrict__ idx, co
 }
 
 // the status words, written into mapped host memory (no copy engine involved)
-__global__ void k_publish_status(const PlainStatus *__restrict__ stt, const int64_t *__restrict__ row_ptr_end, volatile PlainStatus *host) {
+__global__ void k_publish_status(const PlainStatus *__restrict__ stt, const int64_t *__restrict__ row_ptr_end, volatile PlainStatus *host,
+                                 unsigned int seq) {
   if (threadIdx.x == 0) {
     host->n_cand = stt->n_cand; host->n_compares = stt->n_compares;
     host->n_hits = row_ptr_end ? *row_ptr_end : stt->n_hits;
     host->flag = stt->flag; host->n_long = stt->n_long; host->n_compares_b = stt->n_compares_b;
     __threadfence_system();
+    host->seq = seq;  // the host spins on this word: no driver round trip between the last kernel and the D2H that follows
+    __threadfence_system();
   }
+}
+
+// Wait for publication `seq` of the status words.  Spinning on the mapped word costs a few microseconds less than
+// cudaStreamSynchronize and, unlike it, is not delayed by copies in flight on the context's other stream; after a
+// generous number of polls the stream is synchronised anyway (a kernel fault must not hang the host).
+static int wait_status(ff_ctx *ctx, cudaStream_t st, unsigned int seq) {
+  volatile PlainStatus *h = static_cast<volatile PlainStatus *>(ctx->h_status);
+  for (long spin = 0; spin < 20000000L; ++spin) {
+    if (h->seq == seq) return FF_OK;
+    if ((spin & 1023) == 1023 && cudaStreamQuery(st) != cudaErrorNotReady) break;  // finished (or failed) meanwhile
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  FF_CUDA(cudaStreamSynchronize(st));
+  if (h->seq != seq) { set_error("status words were not published"); return FF_ECUDA; }
+  return FF_OK;
 }
 
 // one warp per guide: move the kept row from its segment to its place in the CSR
@@ -800,8 +821,8 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
       launches += 9;
       FF_CUDA(cudaEventRecord(ctx->ev[4], st));
     }
-    k_publish_status<<<1, 32, 0, st>>>(d_stt, nullptr, h_stt_dev);
-    FF_CUDA(cudaStreamSynchronize(st));
+    k_publish_status<<<1, 32, 0, st>>>(d_stt, nullptr, h_stt_dev, ++ctx->status_seq);
+    FF_TRY(wait_status(ctx, st, ctx->status_seq));
     n_cand = (int64_t)h_stt->n_cand;
     if ((size_t)n_cand > cap) {  // the buffer was too small: grow it and repeat the call
       ctx->hit_cap = (size_t)(n_cand + n_cand / 8 + 1024);
@@ -840,8 +861,8 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
     FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
     launches += 2;
-    k_publish_status<<<1, 32, 0, st>>>(d_stt, os.row_ptr.as<int64_t>() + G, h_stt_dev);
-    FF_CUDA(cudaStreamSynchronize(st));
+    k_publish_status<<<1, 32, 0, st>>>(d_stt, os.row_ptr.as<int64_t>() + G, h_stt_dev, ++ctx->status_seq);
+    FF_TRY(wait_status(ctx, st, ctx->status_seq));
     n_hits = h_stt->n_hits;
     if (G > 0 && n_hits > 0) {
       k_gather<<<blocks_for(G * 32, 256), 256, 0, st>>>(sorted, ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), db.d_targets, d_guides,
@@ -857,6 +878,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   }
   FF_CUDA(cudaGetLastError());
 
+  FF_CUDA(cudaEventSynchronize(ctx->ev[4]));  // (already complete: the status words were published after it)
   FF_CUDA(cudaEventElapsedTime(&tm.prep_ms, ctx->ev[0], ctx->ev[1]));
   FF_CUDA(cudaEventElapsedTime(&tm.scan_ms, ctx->ev[1], ctx->ev[2]));
   FF_CUDA(cudaEventElapsedTime(&tm.order_ms, ctx->ev[2], ctx->ev[3]));
