@@ -156,6 +156,27 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
   __syncwarp();
 }
 
+// The hit word of the lane's group `it` (of n + 1): cut it to the bucket's range, queue it, drain the queue when half full.
+template <bool PASS_B>
+__device__ __forceinline__ void queue_hits(uint32_t hm, int it, int n, uint32_t lo, uint32_t hi, uint32_t g0, uint32_t gid, uint32_t probe,
+                                           const HitSink &hs, uint32_t q_off, uint32_t &qcount, int lane, uint32_t lt_mask,
+                                           const uint32_t *canon, const uint32_t *other, int lo_d) {
+  if (it > n) hm = 0u;
+  if (hm) {  // which of the group's entries belong to the bucket
+    if (it == 0) hm &= 0xFFFFFFFFu << (lo & 31u);
+    if (it == n) hm &= 0xFFFFFFFFu >> (31u - ((hi - 1u) & 31u));
+  }
+  const uint32_t hb = __ballot_sync(0xffffffffu, hm != 0u);
+  if (hb) {
+    if (hm) *reinterpret_cast<uint4 *>(ff_smem + q_off + 16u * (qcount + (uint32_t)__popc(hb & lt_mask))) = make_uint4(hm, g0 + (uint32_t)it, gid, probe);
+    qcount += (uint32_t)__popc(hb);
+    if (qcount >= 32u) {
+      drain_queue<PASS_B>(hs, q_off, qcount, lane, canon, other, lo_d);
+      qcount = 0;
+    }
+  }
+}
+
 // Stream the groups of this lane's bucket [lo, hi) (empty for idle lanes).  SMEM: group `g_base` sits at byte offset
 // `base_off` of ff_smem; else at gbase[0].  The loop is warp-uniform (longest bucket of the warp); lanes past their own
 // bucket load nothing and drop their result.
@@ -212,21 +233,7 @@ __device__ __forceinline__ void stream_groups(uint32_t base_off, const uint32_t 
         pg += STRIDE;
       }
     }
-    uint32_t hm = lp.match(w);
-    if (it > n) hm = 0u;
-    if (hm) {  // which of the group's entries belong to the bucket
-      if (it == 0) hm &= 0xFFFFFFFFu << (lo & 31u);
-      if (it == n) hm &= 0xFFFFFFFFu >> (31u - ((hi - 1u) & 31u));
-    }
-    const uint32_t hb = __ballot_sync(0xffffffffu, hm != 0u);
-    if (hb) {
-      if (hm) *reinterpret_cast<uint4 *>(ff_smem + q_off + 16u * (qcount + (uint32_t)__popc(hb & lt_mask))) = make_uint4(hm, g0 + (uint32_t)it, gid, probe);
-      qcount += (uint32_t)__popc(hb);
-      if (qcount >= 32u) {
-        drain_queue<PASS_B>(hs, q_off, qcount, lane, canon, other, lo_d);
-        qcount = 0;
-      }
-    }
+    queue_hits<PASS_B>(lp.match(w), it, n, lo, hi, g0, gid, probe, hs, q_off, qcount, lane, lt_mask, canon, other, lo_d);
   }
 }
 
@@ -532,11 +539,17 @@ __global__ void k_bpairs_scatter(const uint64_t *__restrict__ guides, long long 
   recs[start[kk] + atomicAdd(cursor + kk, 1u)] = make_uint4(kk, pb, gid, 0u);
 }
 
+// 3 CTAs per SM (80 registers).  Tried on the GPU and dropped: a register double buffer of the next group (0.99 ms), two
+// groups per iteration with their loads issued together (0.90 ms; both cost a third of the resident warps), a per-lane
+// cp.async ring in shared memory (2.2 ms: LDGSTS does not merge the lanes that read the same address) -- against 0.73 ms.
+#ifndef FF_PAIR_MIN_BLOCKS
+#define FF_PAIR_MIN_BLOCKS 3
+#endif
 constexpr int kPairThreads = 256;
 constexpr int kPairWarps = kPairThreads / 32;
 
 template <int NB>
-__global__ void __launch_bounds__(kPairThreads, 3) k_pair_scan(PairParams pp) {
+__global__ void __launch_bounds__(kPairThreads, FF_PAIR_MIN_BLOCKS) k_pair_scan(PairParams pp) {
   constexpr int STRIDE = (2 * NB + 3) & ~3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t q_off = (uint32_t)warp * kQCap * 16u;  // dynamic shared memory: one hit queue per warp
@@ -688,7 +701,7 @@ static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, u
   (*launches)++;
   if (pl->part_two) {
     FF_CUDA(cudaEventRecord(ctx->ev[7], st));
-    const int grid = ctx->sm_count * 3;
+    const int grid = ctx->sm_count * FF_PAIR_MIN_BLOCKS;
     const size_t qsm = (size_t)kPairWarps * kQCap * 16;
     if (pl->nb_b == 11) k_pair_scan<11><<<grid, kPairThreads, qsm, st>>>(pl->pp);
     else k_pair_scan<10><<<grid, kPairThreads, qsm, st>>>(pl->pp);
