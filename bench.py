@@ -361,6 +361,52 @@ def run_native(args):
         _emit(out)
 
 
+def run_single_process(args):
+    """--single-process: every GPU behind ONE host process through ff_multi (what a JVM host would do): guide-sharded
+    ff_multi_discover with host buffers, one ncclAllGather of the totals inside the library.  End-to-end only."""
+    import ctypes as C
+    import torch
+    import flashfry_b200.api as ff
+    n = args.gpus
+    if torch.cuda.device_count() < n:
+        raise SystemExit("--single-process --gpus %d needs %d visible GPUs" % (n, n))
+    mc = ff.MultiContext(list(range(n)))
+    t0 = time.perf_counter()
+    mc.synth_database(ENZYME, args.targets, SEED_DB)
+    db_s = time.perf_counter() - t0
+    with ff.Context(0) as c0:  # the guides of the bench line (pool drawn from an identical replica)
+        c0.synth_database(ENZYME, args.targets, SEED_DB)
+        n_t = int(c0.info().n_targets)
+        rng = np.random.default_rng(17)
+        pool = np.concatenate([c0.copy_targets(int(s), 2048) for s in rng.integers(0, max(1, n_t - 2048), 16)])
+    guides = make_guides(args.guides or 100_000, SEED_GUIDES, pool, SEED_PLANTED)
+    G = len(guides)
+    pinned = torch.from_numpy(guides.view(np.int64)).pin_memory()
+    gp = pinned.numpy().view(np.uint64).ctypes.data_as(C.POINTER(C.c_uint64))
+    totals = np.zeros(G, np.int32)
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(max(3, args.warmup)):
+        hits = mc.discover_raw(gp, G, args.k, args.max_ot, totals)
+    t_region0 = sampler.mark()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hits = mc.discover_raw(gp, G, args.k, args.max_ot, totals)
+    s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop(t_region0, sampler.mark())
+    dev_ms = max(mc.rank_timings(r).total_ms for r in range(n))
+    _emit({"metric": _metric_name("discover", args.k), "value": G / s, "unit": "guides/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": G / s / 53.7, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": "configs[2]: %d guides in total through ff_multi_discover (ONE host process, one thread per GPU, host buffers in "
+                                  "and out, one ncclAllGather of the totals inside the library) vs %d targets, k<=%d, maxOT %d" % (G, n_t, args.k, args.max_ot),
+                      "launcher": "single process (ff_multi)", "targets": n_t, "db_build_s_all_devices": db_s},
+           "e2e": {"value": G / s, "unit": "guides/s", "h2d_bytes_per_step": 8 * G, "d2h_bytes_per_step": (G + n) * 8 + hits * 9 + G * 5,
+                   "ms_per_step": s * 1e3, "bytes_are": "whole job"},
+           "slowest_rank_device_ms_last_step": dev_ms, "hits_per_step": hits, "totals_sum": int(totals.sum()), "clocks": clocks,
+           "note": "value == e2e here: this mode only exists end to end"})
+    mc.close()
+
+
 def _extras(out, ctx, ff, N, C, torch, dev, args, guides, d_guides, g_host, gp, hp, G, k, n_t, n_hits, world, _DevView):
     """Side measurements on rank 0's shard: never inside the timed regions, never allowed to take the bench line down."""
     def guard(name, fn):
@@ -638,6 +684,8 @@ def main():
     ap.add_argument("--workload", default="discover", choices=["discover", "fused", "bulge"],
                     help="discover = configs[2]; fused = configs[4] (discover + CFD + Hsu2013 on the GPU, 50 000 guides); bulge = configs[3]")
     ap.add_argument("--no-extras", action="store_true", help="only the headline line (no side measurements)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="all --gpus behind ONE process through the C ABI's ff_multi (not the torchrun contract): end-to-end line only")
     ap.add_argument("--no-ladder", action="store_true")
     ap.add_argument("--no-skew", action="store_true")
     ap.add_argument("--no-cold-start", action="store_true", help="skip writing + loading the index as a real FlashFry database (~40 s)")
@@ -650,6 +698,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_native(args)
 
