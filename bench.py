@@ -147,10 +147,11 @@ def ncu_traffic():
     return None
 
 
-BASELINE_JVM = {  # FlashFry JVM, one core, hg38 (paper/timing_data/bwa_flashfry), seconds per run
-    3: {1: 44.0, 100: 45.1, 1000: 48.4, 10000: 90.9, 100000: 514.6},
-    4: {1: 46.4, 100: 48.5, 1000: 63.6, 10000: 224.8, 100000: 1862.9},
-    5: {1: 50.6, 100: 57.7, 1000: 130.7, 10000: 835.7, 100000: 7918.5},
+BASELINE_JVM = {  # FlashFry 1.8.1 JVM, ONE core, real hg38 (paper/timing_data/bwa_flashfry/*/runtime_set*.tar.gz),
+    # median wall-clock seconds of a whole `discover` run (database load included), by max mismatches and guide count
+    3: {1: 7.6, 100: 36.4, 1000: 44.1, 10000: 81.8, 100000: 514.0},
+    4: {1: 15.9, 100: 41.7, 1000: 61.6, 10000: 210.6, 100000: 1861.0},
+    5: {1: 24.5, 100: 50.1, 1000: 106.0, 10000: 628.2, 100000: 7924.0},
 }
 
 
@@ -502,9 +503,10 @@ def _extras(out, ctx, ff, N, C, torch, dev, args, guides, d_guides, g_host, gp, 
                 ee = time_call(lambda: e2e_call(kk, n), reps)
                 jvm = BASELINE_JVM[kk].get(n)
                 rows.append({"k": kk, "guides": n, "device_ms": dv * 1e3, "e2e_ms": ee * 1e3, "e2e_guides_per_s": n / ee,
-                             "jvm_published_s": jvm, "jvm_published_minus_44s_load_s": (jvm - 44.0) if jvm else None})
+                             "jvm_published_whole_run_s": jvm})
         return {"rows": rows, "one_guide_e2e_latency_ms": [r["e2e_ms"] for r in rows if r["guides"] == 1 and r["k"] == 4][0],
-                "note": "database resident (the JVM's ~44 s are mostly its load); published JVM column: BASELINE.md section 1, one core, real hg38"}
+                "note": "here the database is resident (cold start: cold_start_flashfry_format); the published JVM column is a whole run incl. its "
+                        "database load, one core, real hg38 (BASELINE.md section 1)"}
     if not args.no_ladder:
         guard("batch_ladder", ladder)
 

@@ -69,7 +69,7 @@ static HitsOwner *owner_get() {
 }
 static void owner_put(HitsOwner *o) {
   std::lock_guard<std::mutex> lk(g_pool_mu);
-  if (g_pool.size() < 4) { g_pool.push_back(o); return; }
+  if (g_pool.size() < 64) { g_pool.push_back(o); return; }  // (one owner per device of an ff_multi, and then some)
   o->row_ptr.release(); o->targets.release(); o->mm.release(); o->bulge.release(); o->pos_ptr.release(); o->positions.release();
   o->total.release(); o->ovf.release(); o->tidx.release();
   delete o;
