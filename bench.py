@@ -295,11 +295,21 @@ def run_native(args):
         return s, nh
     e2e_steps = args.steps if wl != "bulge" else max(2, args.steps // 5)
     e2e_s, nh = time_e2e(e2e_steps)
+    e2e_compact_s = None
+    if wl == "discover":  # the same with 32-bit database indices instead of target longs (5 instead of 9 bytes per hit)
+        ctx.set_option("compact_hits", 1)
+        e2e_compact_s, _ = time_e2e(e2e_steps)
+        ctx.set_option("compact_hits", 0)
     clocks = sampler.stop(t_region0, sampler.mark()) if rank == 0 else None  # samples taken inside the two timed regions
     per_hit = 10 if wl == "bulge" else 9
     e2e = {"value": G_job / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": 8 * G,
            "d2h_bytes_per_step": (G + 1) * 8 + nh * per_hit + G * 5 + (24 * G if wl == "fused" else 0), "ms_per_step": e2e_s * 1e3,
            "bytes_are": "per rank", "over_device_step": e2e_s * 1e3 / ms_per_step}
+    if e2e_compact_s:
+        e2e["with_compact_hits"] = {"value": G_job / e2e_compact_s, "ms_per_step": e2e_compact_s * 1e3,
+                                    "d2h_bytes_per_step": (G + 1) * 8 + nh * 5 + G * 5,
+                                    "note": "option compact_hits: ff_hits.target_index (u32) instead of ff_hits.targets (u64); longs looked up on "
+                                            "demand in the host mirror (ff_db_host_targets), as ff_hits_write_tsv and the JVM glue do"}
 
     out = None
     if rank == 0:

@@ -245,9 +245,18 @@ __device__ __forceinline__ void stream_groups(uint32_t base_off, const uint32_t 
 constexpr int kBinThreads = FF_BIN_THREADS;
 constexpr int kBinWarps = kBinThreads / 32;
 constexpr int kNbrCap = 1160;       // bin-part masks within the seed budget (7 bases, distance <= 3: 1156)
-constexpr int kSliceGroups = 736;   // groups of 32 entries a CTA can stage (x 72 B = 52 KB; a human-sized bin is ~572)
-constexpr int kPairCap = 1920;      // pairs sorted by bucket at a time (a human-sized bin with 100 000 guides has ~3200)
-constexpr int kVisitCap = 2048;     // (class, guide) visits of a bin listed in shared memory (~1300); more: binary search
+#ifndef FF_BIN_SLICE
+#define FF_BIN_SLICE 736
+#endif
+#ifndef FF_BIN_PAIRCAP
+#define FF_BIN_PAIRCAP 1920
+#endif
+#ifndef FF_BIN_VISITS
+#define FF_BIN_VISITS 2048
+#endif
+constexpr int kSliceGroups = FF_BIN_SLICE;   // groups of 32 entries a CTA can stage (x 72 B = 52 KB; a human-sized bin is ~572)
+constexpr int kPairCap = FF_BIN_PAIRCAP;     // pairs sorted by bucket at a time (a human-sized bin with 100 000 guides has ~3200)
+constexpr int kVisitCap = FF_BIN_VISITS;     // (class, guide) visits of a bin listed in shared memory (~1300); more: binary search
 
 struct BinParams {
   const uint32_t *planes, *off, *canon, *himasks, *lomasks;

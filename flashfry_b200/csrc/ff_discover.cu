@@ -582,6 +582,17 @@ __global__ void k_publish_status(const PlainStatus *__restrict__ stt, const int6
   }
 }
 
+// A few 64-bit words from device memory to the host without the copy engine (general path: per-window counters).
+__global__ void k_publish_words(const unsigned long long *a, const unsigned long long *b, const unsigned long long *c,
+                                volatile unsigned long long *host, volatile unsigned int *host_seq, unsigned int seq) {
+  if (threadIdx.x == 0) {
+    host[0] = a ? *a : 0ull; host[1] = b ? *b : 0ull; host[2] = c ? *c : 0ull;
+    __threadfence_system();
+    *host_seq = seq;
+    __threadfence_system();
+  }
+}
+
 // Wait for publication `seq` of the status words.  Spinning on the mapped word costs a few microseconds less than
 // cudaStreamSynchronize and, unlike it, is not delayed by copies in flight on the context's other stream; after a
 // generous number of polls the stream is synchronised anyway (a kernel fault must not hang the host).
@@ -614,6 +625,22 @@ __global__ void k_compact_rows(const int64_t *__restrict__ seg_start, const int6
     out_tidx[r0 + i] = idx[s0 + i];
   }
   if (g == n_guides - 1 && lane == 0) stt->n_hits = row_ptr[n_guides];
+}
+
+// Read up to three device words on the host: a kernel writes them into the mapped status block (words 16..18, i.e. past
+// PlainStatus), the host spins on the shared sequence word.
+static int fetch_words(ff_ctx *ctx, cudaStream_t st, const void *a, unsigned long long *ha, const void *b = nullptr,
+                       unsigned long long *hb = nullptr, const void *c = nullptr, unsigned long long *hc = nullptr) {
+  volatile unsigned long long *hw = static_cast<volatile unsigned long long *>(ctx->h_status) + 16;
+  unsigned long long *dw = static_cast<unsigned long long *>(ctx->h_status_dev) + 16;
+  PlainStatus *hs_dev = static_cast<PlainStatus *>(ctx->h_status_dev);
+  k_publish_words<<<1, 32, 0, st>>>(static_cast<const unsigned long long *>(a), static_cast<const unsigned long long *>(b),
+                                    static_cast<const unsigned long long *>(c), dw, &hs_dev->seq, ++ctx->status_seq);
+  FF_TRY(wait_status(ctx, st, ctx->status_seq));
+  if (ha) *ha = hw[0];
+  if (hb) *hb = hw[1];
+  if (hc) *hc = hw[2];
+  return FF_OK;
 }
 
 static inline unsigned int blocks_for(int64_t n, int threads) { return (unsigned int)((n + threads - 1) / threads); }

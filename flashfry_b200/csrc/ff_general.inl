@@ -391,8 +391,7 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
       k_pattern_scan<<<grid, kScanThreads, 0, st>>>(gp);
       launches++; scan_launches++;
       FF_CUDA(cudaEventRecord(ctx->ev[2], st));
-      FF_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
-      FF_CUDA(cudaStreamSynchronize(st));
+      FF_TRY(fetch_words(ctx, st, d_cnt, &h_cnt[0], d_cnt + 1, &h_cnt[1]));  // (mapped status words: no copy-engine queue)
       if (h_cnt[0] <= ctx->hit_cap) break;
       ctx->hit_cap = (size_t)(h_cnt[0] + h_cnt[0] / 8 + 1024);
     }
@@ -422,8 +421,7 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
         FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
         FF_CUDA(cub::DeviceSelect::Unique(ctx->cub_tmp.p, tmp_bytes, ctx->hit_keys_sorted.as<uint64_t>(), ctx->hit_keys.as<uint64_t>(), ctx->n_sel.as<int64_t>(), n_cand, st));
         launches += 2;
-        FF_CUDA(cudaMemcpyAsync(&n_uniq, ctx->n_sel.p, 8, cudaMemcpyDeviceToHost, st));
-        FF_CUDA(cudaStreamSynchronize(st));
+        { unsigned long long v = 0; FF_TRY(fetch_words(ctx, st, ctx->n_sel.p, &v)); n_uniq = (int64_t)v; }
         keys = ctx->hit_keys.as<uint64_t>();
       } else {
         n_uniq = n_cand;
@@ -443,8 +441,7 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
       FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
       FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), ctx->seg_end.as<int64_t>(), n_active + 1, st));
       launches += 2;
-      FF_CUDA(cudaMemcpyAsync(&n_keep_total, ctx->seg_end.as<int64_t>() + n_active, 8, cudaMemcpyDeviceToHost, st));
-      FF_CUDA(cudaStreamSynchronize(st));
+      { unsigned long long v = 0; FF_TRY(fetch_words(ctx, st, ctx->seg_end.as<int64_t>() + n_active, &v)); n_keep_total = (int64_t)v; }
       if (n_keep_total > 0) {
         FF_TRY(grow_keep(ctx->kept_keys, (size_t)n_kept * 8, (size_t)(n_kept + n_keep_total) * 8, st));
         k_copy_kept<<<blocks_for(n_active * 32, 256), 256, 0, st>>>(keys, ctx->seg_start.as<int64_t>(), ctx->seg_end.as<int64_t>(), n_active,
@@ -465,9 +462,7 @@ static int discover_general(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gui
       launches += 3;
       int64_t n_next = 0;
       unsigned long long collected = 0;
-      FF_CUDA(cudaMemcpyAsync(&n_next, ctx->n_sel.p, 8, cudaMemcpyDeviceToHost, st));
-      FF_CUDA(cudaMemcpyAsync(&collected, d_cnt + 2, 8, cudaMemcpyDeviceToHost, st));
-      FF_CUDA(cudaStreamSynchronize(st));
+      { unsigned long long v = 0; FF_TRY(fetch_words(ctx, st, ctx->n_sel.p, &v, d_cnt + 2, &collected)); n_next = (int64_t)v; }
       d_active = next;
       n_active = n_next;
       if (!fixed_window && n_active > 0) {
