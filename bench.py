@@ -1,24 +1,31 @@
 #!/usr/bin/env python3
 """bench.py -- guides/sec of FlashFry's off-target discovery hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N --steps K --warmup W]             # this repo's CUDA path
+    python bench.py [--gpus N --steps K --warmup W]             # this repo's CUDA path (N > 1: under torchrun, one rank per GPU)
     python bench.py --impl reference [...]                      # the reference's CPU algorithm (oracle port)
+    python bench.py --workload fused|bulge                      # BASELINE.json configs[4] / configs[3] as first-class lines
+    python bench.py --scaling weak                              # the full batch on every GPU instead of one sharded batch
+    python bench.py --single-process --gpus N                   # every GPU behind ONE process through the C ABI's ff_multi
 
-Workload (BASELINE.json configs[2], named in config.workload): 100 000 synthetic 20-bp NGG guides (+10 % planted
-near real targets) against a synthetic human-genome-sized (3e8 distinct targets) spCas9-NGG index, <= 4 mismatches,
-maximumOffTargets 2000.  The index is generated in HBM from a seed (it would be ~5 GB on disk); one replica per GPU.
-A "step" = one discover call over one batch of guides per GPU; with N GPUs every rank processes its own batch
-(guide-sharded, no data-path collective) and the ranks all-gather the per-guide hit counts at the end of the step.
+Workload (BASELINE.json configs[2], named in config.workload): 100 000 synthetic 20-bp NGG guides IN TOTAL (+10 % planted
+near real targets), sharded over the ranks ("scaling": "strong"), against a synthetic human-genome-sized (3e8 distinct
+targets) spCas9-NGG index, <= 4 mismatches, maximumOffTargets 2000.  The index is generated in HBM from a seed; one
+replica per GPU.  A "step" = one discover call over the rank's shard + one all-gather of the per-guide totals.
 
 `value`  : whole-job guides/s with guides already in HBM and results left in HBM (CUDA events, max over ranks).
-`e2e`    : the same metric through the C ABI with HOST buffers (ff_discover: H2D of the guides, D2H of the hit lists).
-`roofline`: the dominant kernel (k_cell_scan, the cell-major seed scan: one launch per index half, timed together with CUDA
-            events on the launching stream) against the measured HBM copy bandwidth.  Algorithmic bytes per call = for
-            every (guide, seed) the two 4-byte index entries + 4 bytes per index entry streamed from the seed's bucket
-            + 8 bytes per guide + 8 bytes per candidate hit written; `traffic` = the HBM bytes ncu
-            measured for the same call (L2 serves the repeated bucket reads, so it is below the algorithmic bytes).
-`bulge_mode`, `fused_discover_score`: BASELINE.json configs[3] (an extension, no reference semantics) and configs[4] on
-            the same batch.
+`e2e`    : the same metric through the C ABI with HOST buffers (ff_discover: H2D of the guides, D2H of the hit lists);
+           `e2e.with_compact_hits`: the same with 32-bit database indices instead of target longs.
+`roofline`: the two scan kernels (k_bin_scan + k_pair_scan, one launch per index half, timed with CUDA events on the
+            launching stream).  `achieved` / `frac` use SURVEY.md 8(d)'s ALGORITHMIC bytes (8 N_t + 8 G + 16 H per call)
+            against the measured HBM copy bandwidth; `traffic` / `dram_frac` = the HBM bytes ncu measured for the same call
+            (profiles/scan_traffic.json); `issue_frac`, `alu_pipe_frac` from the same capture; `compare_frac` against SURVEY's
+            one-POPC-per-entry ceiling; `requested_bytes` = what the kernels ask of L2 / shared memory (NOT HBM); `bound`
+            names what binds ("issue" for the bin-major kernels); `launches` has one entry per kernel.
+Side measurements on rank 0 at N = 1 (never inside the timed regions): both scan kernels agree on the whole batch,
+`fused_discover_score`, `bulge_mode`, `batch_ladder` (1 .. 100 000 guides x k = 3, 4, 5 next to the published JVM table),
+`chr22_1000_guides`, `skewed_index`, `e2e_compact_hits`, `cold_start_flashfry_format` (the index written as a real
+FlashFry database and loaded back), `cpu_baseline` (the oracle port on one host thread, bounded sample, doubles as a
+parity check of the timed path).
 """
 import argparse
 import json
