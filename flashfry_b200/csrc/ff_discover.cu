@@ -471,11 +471,10 @@ struct CutState {
 // occurrence counts is below max_ot (ResultsAggregator.scala:61-69 / CRISPRSiteOT.scala:39-46: append while
 // currentTotal < overflow) and write the kept rows -- target long, mismatch count, database index -- at the segment's
 // own position (k_compact_rows closes the gaps between segments).
-__device__ __forceinline__ void cut_chunk(CutState &cs, int64_t i, int64_t n, uint32_t t, int lane, const uint64_t *__restrict__ targets,
+__device__ __forceinline__ void cut_chunk(CutState &cs, int64_t i, int64_t n, uint32_t t, uint64_t tl, int lane,
                                           uint64_t guide, uint64_t cmp_mask, int max_ot, int64_t s0, uint64_t *__restrict__ st_targets,
                                           uint8_t *__restrict__ st_mm, uint32_t *__restrict__ idx) {
-  const uint64_t tl = i < n ? targets[t] : 0ull;
-  const int c = (int)(tl >> 48);
+  const int c = (int)(tl >> 48);  // tl = targets[t], 0 past the end of the segment
   int incl = c;  // a chunk sums to < 2^21
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -530,9 +529,13 @@ __device__ __forceinline__ void sort_cut_regs(CutState &cs, int64_t n, int lane,
       }
     }
   }
+  // all the gathers of the segment are issued together (one round trip to HBM per guide instead of one per chunk)
+  uint64_t tl[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) tl[e] = (e * 32 + lane < n) ? targets[v[e]] : 0ull;
 #pragma unroll
   for (int e = 0; e < E; ++e)
-    if (!cs.done && e * 32 < n) cut_chunk(cs, e * 32 + lane, n, v[e], lane, targets, guide, cmp_mask, max_ot, s0, st_targets, st_mm, idx);
+    if (!cs.done && e * 32 < n) cut_chunk(cs, e * 32 + lane, n, v[e], tl[e], lane, guide, cmp_mask, max_ot, s0, st_targets, st_mm, idx);
 }
 
 // One warp per guide: sort its candidates by database index (up to kSegSortMax: in registers; longer segments arrive
@@ -560,7 +563,8 @@ __global__ void __launch_bounds__(256) k_sort_cut(uint32_t *__restrict__ idx, co
   else
     for (int64_t base = 0; base < n && !cs.done; base += 32) {
       const int64_t i = base + lane;
-      cut_chunk(cs, i, n, i < n ? idx[s0 + i] : 0u, lane, targets, guide, cmp_mask, max_ot, s0, st_targets, st_mm, idx);
+      const uint32_t t = i < n ? idx[s0 + i] : 0u;
+      cut_chunk(cs, i, n, t, i < n ? targets[t] : 0ull, lane, guide, cmp_mask, max_ot, s0, st_targets, st_mm, idx);
     }
   if (lane == 0) {
     n_keep[g] = cs.kept;
