@@ -67,17 +67,28 @@ template <> struct PlaneCount<11> {
 // What a lane holds for its pair: the probe's bits spread to words, and 15 - budget for the carry chain.
 template <int NB> struct LaneProbe {
   uint32_t gl[NB], gh[NB], kb[4];
+  // Bit k of x spread to a word: shift it to the top of its byte (eight shifted copies of x serve every k) and let PRMT
+  // replicate that byte's sign -- 8 + one instruction per bit instead of two per bit.
   __device__ __forceinline__ void set(uint32_t probe, int budget) {
+    const uint32_t kk = 15u - (uint32_t)min(max(budget, 0), 15);
+    const uint32_t x = probe | (kk << (2 * NB));  // 2 NB probe bits, then the four bits of 15 - budget
+    uint32_t y[8];
+#pragma unroll
+    for (int sft = 0; sft < 8; ++sft) y[sft] = x << sft;
+    auto spread = [&](int k) {  // (prmt.b32 directly: __byte_perm ignores the sign-replication bit of the selector nibbles)
+      uint32_t d;
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(y[7 - (k & 7)]), "r"(0u), "r"(0x8888u | (0x1111u * (uint32_t)(k >> 3))));
+      return d;
+    };
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      gl[i] = (uint32_t)((int32_t)(probe << (31 - 2 * i)) >> 31);
-      gh[i] = (uint32_t)((int32_t)(probe << (30 - 2 * i)) >> 31);
+      gl[i] = spread(2 * i);
+      gh[i] = spread(2 * i + 1);
       asm volatile("" : "+r"(gl[i]), "+r"(gh[i]));  // keep them in registers: ptxas otherwise recomputes them inside the group loop
     }
-    const uint32_t kk = 15u - (uint32_t)min(max(budget, 0), 15);
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      kb[b] = (uint32_t)((int32_t)(kk << (31 - b)) >> 31);
+      kb[b] = spread(2 * NB + b);
       asm volatile("" : "+r"(kb[b]));
     }
   }
@@ -111,7 +122,7 @@ extern __shared__ __align__(128) uint8_t ff_smem[];
 
 constexpr int kQCap = 64;  // hit-queue entries per warp; drained at >= 32, and one iteration adds at most 32
 
-// Queue entries (uint4): x = hit word (already cut to the bucket's range), y = group, z = guide index, w = probe (part
+// Queue entries (uint4): x = hit word (already cut to the bucket's range), y = index of the entry bit 0 stands for, z = guide index, w = probe (part
 // two: for the exact d1 > hA test).  The number of queued entries lives in a warp-uniform register.
 template <bool PASS_B>
 __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, uint32_t n, int lane, const uint32_t *__restrict__ canon,
@@ -127,7 +138,7 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
       while (t) {
         const int b = __ffs((int)t) - 1;
         t &= t - 1u;
-        if (base_dist32(other[e.y * 32u + (uint32_t)b] ^ e.w) <= lo_d) vm &= ~(1u << b);
+        if (base_dist32(other[e.y + (uint32_t)b] ^ e.w) <= lo_d) vm &= ~(1u << b);
       }
     }
     const int c = __popc(vm);
@@ -148,7 +159,7 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
     while (vm) {
       const int b = __ffs((int)vm) - 1;
       vm &= vm - 1u;
-      const uint32_t idx = e.y * 32u + (uint32_t)b;
+      const uint32_t idx = e.y + (uint32_t)b;
       if (pos < hs.hit_cap) hs.hits[pos] = gk | (canon ? canon[idx] : idx);
       ++pos;
     }
@@ -156,19 +167,21 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
   __syncwarp();
 }
 
-// The hit word of the lane's group `it` (of n + 1): cut it to the bucket's range, queue it, drain the queue when half full.
+// The hit word of the lane's group `it` (of n + 1): cut it to the bucket's range -- the first group's entries below
+// lo_bit and the last group's entries from hi_bit on belong to the neighbours (or are padding) --, queue it with the index
+// of its entry 0, drain the queue when half full.
 template <bool PASS_B>
-__device__ __forceinline__ void queue_hits(uint32_t hm, int it, int n, uint32_t lo, uint32_t hi, uint32_t g0, uint32_t gid, uint32_t probe,
-                                           const HitSink &hs, uint32_t q_off, uint32_t &qcount, int lane, uint32_t lt_mask,
+__device__ __forceinline__ void queue_hits(uint32_t hm, int it, int n, uint32_t lo_bit, uint32_t hi_bit, uint32_t idx0, uint32_t gid,
+                                           uint32_t probe, const HitSink &hs, uint32_t q_off, uint32_t &qcount, int lane, uint32_t lt_mask,
                                            const uint32_t *canon, const uint32_t *other, int lo_d) {
   if (it > n) hm = 0u;
-  if (hm) {  // which of the group's entries belong to the bucket
-    if (it == 0) hm &= 0xFFFFFFFFu << (lo & 31u);
-    if (it == n) hm &= 0xFFFFFFFFu >> (31u - ((hi - 1u) & 31u));
+  if (hm) {
+    if (it == 0) hm &= 0xFFFFFFFFu << lo_bit;
+    if (it == n) hm &= 0xFFFFFFFFu >> (32u - hi_bit);
   }
   const uint32_t hb = __ballot_sync(0xffffffffu, hm != 0u);
   if (hb) {
-    if (hm) *reinterpret_cast<uint4 *>(ff_smem + q_off + 16u * (qcount + (uint32_t)__popc(hb & lt_mask))) = make_uint4(hm, g0 + (uint32_t)it, gid, probe);
+    if (hm) *reinterpret_cast<uint4 *>(ff_smem + q_off + 16u * (qcount + (uint32_t)__popc(hb & lt_mask))) = make_uint4(hm, idx0 + 32u * (uint32_t)it, gid, probe);
     qcount += (uint32_t)__popc(hb);
     if (qcount >= 32u) {
       drain_queue<PASS_B>(hs, q_off, qcount, lane, canon, other, lo_d);
@@ -177,16 +190,16 @@ __device__ __forceinline__ void queue_hits(uint32_t hm, int it, int n, uint32_t 
   }
 }
 
-// Stream the groups of this lane's bucket [lo, hi) (empty for idle lanes).  SMEM: group `g_base` sits at byte offset
-// `base_off` of ff_smem; else at gbase[0].  The loop is warp-uniform (longest bucket of the warp); lanes past their own
-// bucket load nothing and drop their result.
+// Stream the lane's n + 1 groups starting at group g0 (n = -1: idle lane).  Entry 0 of group g0 has index idx0; the
+// bucket owns the first group's entries from lo_bit on and the last group's entries below hi_bit.  SMEM: group `g_base`
+// sits at byte offset `base_off` of ff_smem; else at gbase[0].  The loop is warp-uniform (longest bucket of the warp);
+// lanes past their own bucket load nothing and drop their result.
 template <int NB, int STRIDE, bool PASS_B, bool SMEM>
-__device__ __forceinline__ void stream_groups(uint32_t base_off, const uint32_t *gbase, uint32_t g_base, uint32_t lo, uint32_t hi,
-                                              const LaneProbe<NB> &lp, uint32_t gid, uint32_t probe, const HitSink &hs, uint32_t q_off,
-                                              uint32_t &qcount, int lane, const uint32_t *canon, const uint32_t *other, int lo_d) {
-  const int n = hi > lo ? (int)(((hi - 1u) >> 5) - (lo >> 5)) : -1;  // index of the lane's last iteration
+__device__ __forceinline__ void stream_groups(uint32_t base_off, const uint32_t *gbase, uint32_t g_base, uint32_t g0, int n, uint32_t idx0,
+                                              uint32_t lo_bit, uint32_t hi_bit, const LaneProbe<NB> &lp, uint32_t gid, uint32_t probe,
+                                              const HitSink &hs, uint32_t q_off, uint32_t &qcount, int lane, const uint32_t *canon,
+                                              const uint32_t *other, int lo_d) {
   const int T = __reduce_max_sync(0xffffffffu, n);
-  const uint32_t g0 = lo >> 5;
   uint32_t soff = base_off + (g0 - g_base) * (uint32_t)(STRIDE * 4);
   const uint32_t *pg = SMEM ? nullptr : gbase + (size_t)(n >= 0 ? g0 - g_base : 0u) * STRIDE;
   uint32_t w[2 * NB];
@@ -233,7 +246,7 @@ __device__ __forceinline__ void stream_groups(uint32_t base_off, const uint32_t 
         pg += STRIDE;
       }
     }
-    queue_hits<PASS_B>(lp.match(w), it, n, lo, hi, g0, gid, probe, hs, q_off, qcount, lane, lt_mask, canon, other, lo_d);
+    queue_hits<PASS_B>(lp.match(w), it, n, lo_bit, hi_bit, idx0, gid, probe, hs, q_off, qcount, lane, lt_mask, canon, other, lo_d);
   }
 }
 
@@ -246,20 +259,20 @@ constexpr int kBinThreads = FF_BIN_THREADS;
 constexpr int kBinWarps = kBinThreads / 32;
 constexpr int kNbrCap = 1160;       // bin-part masks within the seed budget (7 bases, distance <= 3: 1156)
 #ifndef FF_BIN_SLICE
-#define FF_BIN_SLICE 736
+#define FF_BIN_SLICE 800
 #endif
 #ifndef FF_BIN_PAIRCAP
-#define FF_BIN_PAIRCAP 1920
+#define FF_BIN_PAIRCAP 1536
 #endif
 #ifndef FF_BIN_VISITS
-#define FF_BIN_VISITS 2048
+#define FF_BIN_VISITS 1536
 #endif
-constexpr int kSliceGroups = FF_BIN_SLICE;   // groups of 32 entries a CTA can stage (x 72 B = 52 KB; a human-sized bin is ~572)
+constexpr int kSliceGroups = FF_BIN_SLICE;   // groups of 32 entries a CTA can stage (x 72 B = 56 KB; a human-sized bin is ~717 bucket-aligned groups)
 constexpr int kPairCap = FF_BIN_PAIRCAP;     // pairs sorted by bucket at a time (a human-sized bin with 100 000 guides has ~3200)
 constexpr int kVisitCap = FF_BIN_VISITS;     // (class, guide) visits of a bin listed in shared memory (~1300); more: binary search
 
 struct BinParams {
-  const uint32_t *planes, *off, *canon, *himasks, *lomasks;
+  const uint32_t *planes, *off, *goff, *canon, *himasks, *lomasks;  // goff: first group of every bucket (bucket-aligned planes)
   int n_hi;            // bin-part masks within the budget
   int cum_hi[5];       // cum_hi[d] = # bin-part masks at distance <= d (d <= hA <= 3)
   int nm[4];           // nm[d] = # last-four-bases masks a guide reached at bin distance d contributes
@@ -280,7 +293,7 @@ struct BinShared {
   uint32_t bin, b0, b1, glob, g_base, bytes, use_vis, next_slice;
   uint32_t R[6], PB[6];
   uint32_t wtot[kBinWarps];
-  uint32_t off[260];
+  uint32_t off[260], goff[260];  // entries / groups: first of every bucket of the bin
   uint32_t lom[256];
   uint32_t pre[kNbrCap + 4];
   uint32_t start[kNbrCap + 4];
@@ -313,7 +326,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
     __syncthreads();
     const uint32_t bin = sh.bin;
     if (bin >= bp.n_bins) break;
-    for (int i = tid; i <= 256; i += kBinThreads) sh.off[i] = bp.off[(bin << 8) + i];
+    for (int i = tid; i <= 256; i += kBinThreads) { sh.off[i] = bp.off[(bin << 8) + i]; sh.goff[i] = bp.goff[(bin << 8) + i]; }
     // guide classes that reach this bin, and the exclusive prefix of their sizes ("visits" of the bin)
     uint32_t carry = 0;
     for (int j0 = 0; j0 < bp.n_hi; j0 += kBinThreads) {
@@ -369,15 +382,14 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
     for (;;) {
       __syncthreads();
       if (tid == 0) {
-        const uint32_t b0 = sh.b0, e0 = sh.off[b0];
-        const uint32_t gs = (e0 >> 5) & ~1u;  // even group: 16-byte aligned source for any stride that is a multiple of 2 words
-        auto groups = [&](uint32_t e1) { return e1 > e0 ? ((e1 - 1u) >> 5) - gs + 1u : 0u; };
+        const uint32_t b0 = sh.b0;
+        const uint32_t gs = sh.goff[b0] & ~1u;  // even group: 16-byte aligned source for any stride that is a multiple of 2 words
         uint32_t b1 = 256;
-        if (groups(sh.off[256]) > (uint32_t)kSliceGroups) {
+        if (sh.goff[256] - gs > (uint32_t)kSliceGroups) {
           b1 = b0 + 1;
-          while (b1 < 256 && groups(sh.off[b1 + 1]) <= (uint32_t)kSliceGroups) ++b1;
+          while (b1 < 256 && sh.goff[b1 + 1] - gs <= (uint32_t)kSliceGroups) ++b1;
         }
-        const uint32_t ng = groups(sh.off[b1]);
+        const uint32_t ng = sh.goff[b1] - gs;
         sh.b1 = b1; sh.g_base = gs;
         sh.glob = ng > (uint32_t)kSliceGroups ? 1u : 0u;
         const uint32_t bytes = sh.glob ? 0u : ((ng * STRIDE * 4u + 15u) & ~15u);
@@ -471,20 +483,21 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
           j0 = __shfl_sync(0xffffffffu, j0, 0);
           if (j0 >= nv) break;
           const uint32_t j = j0 + lane;
-          uint32_t lo = 0, hi = 0, gid = 0, probe = 0;
+          uint32_t lo = 0, len = 0, g0 = g_base, gid = 0, probe = 0;
           int budget = -1;
           if (j < nv) {
             const uint2 r = sh.rec[sh.perm[j]];
             const uint32_t bl = r.x >> 24;
-            lo = sh.off[bl]; hi = sh.off[bl + 1];
+            lo = sh.off[bl]; len = sh.off[bl + 1] - lo; g0 = sh.goff[bl];
             probe = r.x & 0xFFFFFFu; gid = r.y & 0x0FFFFFFFu; budget = (int)(r.y >> 28);
           }
-          compares += hi - lo;
+          compares += len;
           LaneProbe<NB> lp;
           lp.set(probe, budget);
-          if (j >= nv) lo = hi = g_base << 5;  // idle lanes: an empty bucket inside the slice
-          if (glob) stream_groups<NB, STRIDE, false, false>(0u, bp.planes + (size_t)g_base * STRIDE, g_base, lo, hi, lp, gid, probe, bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
-          else stream_groups<NB, STRIDE, false, true>(0u, nullptr, g_base, lo, hi, lp, gid, probe, bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
+          const int n = len ? (int)((len - 1u) >> 5) : -1;           // every bucket starts a group: ceil(len / 32) groups,
+          const uint32_t hi_bit = ((len - 1u) & 31u) + 1u;           // only the last one is cut
+          if (glob) stream_groups<NB, STRIDE, false, false>(0u, bp.planes + (size_t)g_base * STRIDE, g_base, g0, n, lo, 0u, hi_bit, lp, gid, probe, bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
+          else stream_groups<NB, STRIDE, false, true>(0u, nullptr, g_base, g0, n, lo, 0u, hi_bit, lp, gid, probe, bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
         }
       }
       if (!waited) {  // no pairs at all: still consume the copy before the buffer is reused
@@ -583,7 +596,9 @@ __global__ void __launch_bounds__(kPairThreads, FF_PAIR_MIN_BLOCKS) k_pair_scan(
     compares += hi - lo;
     LaneProbe<NB> lp;
     lp.set(probe, budget);
-    stream_groups<NB, STRIDE, true, false>(0u, pp.planes, 0u, lo, hi, lp, gid, probe, pp.hs, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
+    const int n = hi > lo ? (int)(((hi - 1u) >> 5) - (lo >> 5)) : -1;  // groups are cut at multiples of 32 entries
+    stream_groups<NB, STRIDE, true, false>(0u, pp.planes, 0u, lo >> 5, n, lo & ~31u, lo & 31u, ((hi - 1u) & 31u) + 1u, lp, gid, probe, pp.hs,
+                                           q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
   }
   drain_queue<true>(pp.hs, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
   for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
@@ -619,7 +634,7 @@ struct BinScanPlan {
 };
 
 static bool bin_scan_supported(const Database &db, int hA, int64_t G) {
-  if (!db.A.d_planes || !db.B.d_planes || db.A.n_planes != 18) return false;
+  if (!db.A.d_planes || !db.A.d_goff || !db.B.d_planes || db.A.n_planes != 18) return false;
   if (db.B.n_planes != 20 && db.B.n_planes != 22) return false;
   if (hA > 3 || db.A.cum_hi[hA] > kNbrCap) return false;
   return G < (1ll << 28);
@@ -676,7 +691,7 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
   FF_CUDA(cudaGetLastError());
 
   BinParams &bp = pl->bp;
-  bp.planes = db.A.d_planes; bp.off = db.A.d_off; bp.canon = db.A.d_canon; bp.himasks = db.A.d_himasks; bp.lomasks = db.A.d_lomasks;
+  bp.planes = db.A.d_planes; bp.off = db.A.d_off; bp.goff = db.A.d_goff; bp.canon = db.A.d_canon; bp.himasks = db.A.d_himasks; bp.lomasks = db.A.d_lomasks;
   bp.n_hi = db.A.cum_hi[hA];
   for (int d = 0; d < 5; ++d) bp.cum_hi[d] = db.A.cum_hi[std::min(d, hA)];
   for (int d = 0; d < 4; ++d) {

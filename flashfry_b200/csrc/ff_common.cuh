@@ -70,6 +70,10 @@ struct SeedIndex {
   uint32_t *d_planes = nullptr;
   int n_planes = 0, plane_stride = 0;
   uint64_t n_groups = 0;
+  // index A only: every bucket starts a group of its own (d_goff[key] = first group of the bucket; the last group of a
+  // bucket is padded).  A bucket of ~72 entries then spans ceil(72 / 32) = 3 groups instead of 3.2 .. 4 at a random
+  // alignment, and the first group needs no range mask.  nullptr: groups are cut at multiples of 32 entries (index B).
+  uint32_t *d_goff = nullptr;
   // masks over the first key_bases - 4 key bases (the "bin" of a key), sorted by distance; the masks over the last four
   // key bases live in constant memory (the same 256 for every key width)
   uint32_t *d_himasks = nullptr;   // [4^(key_bases-4)] mask | distance << 24

@@ -53,7 +53,7 @@ int pack_from_index(int idx, Pack *o) {
 
 void SeedIndex::release() {
   cudaFree(d_off); cudaFree(d_other); cudaFree(d_canon); cudaFree(d_masks); cudaFree(d_masks_w1);
-  cudaFree(d_planes); cudaFree(d_himasks); cudaFree(d_lomasks);
+  cudaFree(d_planes); cudaFree(d_goff); cudaFree(d_himasks); cudaFree(d_lomasks);
   *this = SeedIndex();
 }
 
@@ -105,6 +105,38 @@ __global__ void k_counts(const uint64_t *__restrict__ t, uint64_t n, uint64_t *_
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < n) c[i] = t[i] >> 48;
   if (i == n) c[i] = 0;
+}
+
+// groups per bucket (bucket-aligned planes of index A)
+__global__ void k_bucket_groups(const uint32_t *__restrict__ off, uint32_t n_keys, uint32_t *__restrict__ ng) {
+  const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (k < n_keys) ng[k] = (off[k + 1] - off[k] + 31u) >> 5;
+  if (k == n_keys) ng[k] = 0;
+}
+
+// Bit-slice `other` with every bucket starting its own group: one warp per group; the group's bucket is found by a
+// binary search over the group offsets, entries past the bucket's end read as all-ones (the scan masks them away).
+__global__ void k_slice_planes_aligned(const uint32_t *__restrict__ other, const uint32_t *__restrict__ off, const uint32_t *__restrict__ goff,
+                                       uint32_t n_keys, uint64_t n_groups, int n_planes, int stride, uint32_t *__restrict__ planes) {
+  const uint64_t g = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_groups) return;
+  uint32_t lo = 0, hi = n_keys;  // last key with goff[key] <= g (keys with no entries share their successor's offset)
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+    if (goff[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  uint32_t v = 0xFFFFFFFFu;
+  if (lo < n_keys && g < goff[lo + 1]) {
+    const uint64_t e = (uint64_t)off[lo] + (g - goff[lo]) * 32ull + (uint64_t)lane;
+    if (e < off[lo + 1]) v = other[e];
+  }
+  uint32_t mine = 0;
+  for (int j = 0; j < n_planes; ++j) {
+    const uint32_t w = __ballot_sync(0xffffffffu, (v >> j) & 1u);
+    if (lane == j) mine = w;
+  }
+  if (lane < stride) planes[g * stride + lane] = lane < n_planes ? mine : 0u;
 }
 
 static int base_distance(uint32_t m) { return __builtin_popcount((m | (m >> 1)) & 0x55555555u); }
@@ -198,9 +230,29 @@ static int build_seed_index(ff_ctx *ctx, SeedIndex *ix, int key_bases, int other
   if (key_bases >= 6 && other_bases >= 9 && other_bases <= 11) {
     ix->n_planes = 2 * other_bases;
     ix->plane_stride = wide_planes ? (ix->n_planes + 3) & ~3 : ix->n_planes;
-    ix->n_groups = (n + 31) / 32 + 1;
-    FF_CUDA(cudaMalloc(&ix->d_planes, ix->n_groups * ix->plane_stride * 4 + 64));
-    k_slice_planes<<<nblk(ix->n_groups * 32), 256, 0, st>>>(ix->d_other, ix->n_groups, ix->n_planes, ix->plane_stride, ix->d_planes);
+    if (wide_planes) {  // index B: long buckets, groups at multiples of 32 entries
+      ix->n_groups = (n + 31) / 32 + 1;
+      FF_CUDA(cudaMalloc(&ix->d_planes, ix->n_groups * ix->plane_stride * 4 + 64));
+      k_slice_planes<<<nblk(ix->n_groups * 32), 256, 0, st>>>(ix->d_other, ix->n_groups, ix->n_planes, ix->plane_stride, ix->d_planes);
+    } else {            // index A: short buckets, every bucket starts a group
+      uint32_t *d_ng = nullptr;
+      FF_CUDA(cudaMalloc(&d_ng, ((size_t)n_keys + 1) * 4));
+      FF_CUDA(cudaMalloc(&ix->d_goff, ((size_t)n_keys + 1) * 4));
+      k_bucket_groups<<<nblk((uint64_t)n_keys + 1), 256, 0, st>>>(ix->d_off, n_keys, d_ng);
+      size_t tmp = 0;
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_ng, ix->d_goff, (int)(n_keys + 1), st));
+      FF_TRY(ctx->cub_tmp.reserve(tmp));
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, d_ng, ix->d_goff, (int)(n_keys + 1), st));
+      uint32_t total = 0;
+      FF_CUDA(cudaMemcpyAsync(&total, ix->d_goff + n_keys, 4, cudaMemcpyDeviceToHost, st));
+      FF_CUDA(cudaStreamSynchronize(st));
+      cudaFree(d_ng);
+      ix->n_groups = (uint64_t)total + 2;  // + padding: a bin's slice is copied from an even group, in 16-byte units
+      FF_CUDA(cudaMalloc(&ix->d_planes, ix->n_groups * ix->plane_stride * 4 + 64));
+      k_slice_planes_aligned<<<nblk(ix->n_groups * 32), 256, 0, st>>>(ix->d_other, ix->d_off, ix->d_goff, n_keys, ix->n_groups, ix->n_planes,
+                                                                   ix->plane_stride, ix->d_planes);
+      ctx->db.device_bytes += ((size_t)n_keys + 1) * 4;
+    }
     std::vector<uint32_t> hi, lo;
     make_masks(key_bases - 4, &hi, ix->cum_hi);
     make_masks(4, &lo, ix->cum_lo);
