@@ -350,7 +350,8 @@ int ff_set_option(ff_ctx *c, const char *key, long long value) {
         {"subbatch_c1", &c->opt.subbatch_c1, 1, 98},      {"subbatch_c2", &c->opt.subbatch_c2, 2, 99},
         {"group_sort", &c->opt.group_sort, 0, 1},         {"b_spi", &c->opt.b_spi, 0, 32},
         {"trace", &c->opt.trace, 0, 1},
-      {"split_a", &c->opt.split_a, 0, 12},              {"compact_hits", &c->opt.compact_hits, 0, 1},
+        {"split_a", &c->opt.split_a, 0, 12},              {"compact_hits", &c->opt.compact_hits, 0, 1},
+        {"pair_kernel", &c->opt.pair_kernel, 0, 2},       {"pair_segs", &c->opt.pair_segs, 0, 8},
     };
     for (auto &t : table)
       if (strcmp(key, t.name) == 0) {

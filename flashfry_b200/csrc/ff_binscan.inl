@@ -92,10 +92,12 @@ template <int NB> struct LaneProbe {
       asm volatile("" : "+r"(kb[b]));
     }
   }
-  // bit e set <=> entry e of the group is within budget.  w = the group's plane words (w[2i] low bit, w[2i+1] high bit of base i)
-  __device__ __forceinline__ uint32_t match(const uint32_t (&w)[2 * NB]) const {
+  // bit e set <=> entry e of the group is within budget.  w = the group's plane words (w[2i] low bit, w[2i+1] high bit of base i).
+  // lo_d >= 0 (part two, warp-uniform): and has MORE than lo_d mismatches -- the pairs with d1 <= hA belong to part one.
+  __device__ __forceinline__ uint32_t match(const uint32_t (&w)[2 * NB], int lo_d = -1) const {
     uint32_t m[NB];
 #pragma unroll
+    // (tried: w ^ gl as w * (gl | 1) + gl, an IMAD on the FMA pipe, to take a quarter of the LOP3s off the ALU pipe: 2-5 % slower)
     for (int i = 0; i < NB; ++i) m[i] = (w[2 * i] ^ gl[i]) | (w[2 * i + 1] ^ gh[i]);
     uint32_t c0, c1, c2, c3;
     PlaneCount<NB>::run(m, c0, c1, c2, c3);
@@ -104,7 +106,14 @@ template <int NB> struct LaneProbe {
     cy = (c1 & kb[1]) | (cy & (c1 | kb[1]));
     cy = (c2 & kb[2]) | (cy & (c2 | kb[2]));
     cy = (c3 & kb[3]) | (cy & (c3 | kb[3]));
-    return ~cy;
+    if (lo_d < 0) return ~cy;
+    const uint32_t kl = 15u - (uint32_t)min(lo_d, 15);  // the same chain against lo_d
+    const uint32_t l0 = 0u - (kl & 1u), l1 = 0u - ((kl >> 1) & 1u), l2 = 0u - ((kl >> 2) & 1u), l3 = 0u - ((kl >> 3) & 1u);
+    uint32_t cl = c0 & l0;
+    cl = (c1 & l1) | (cl & (c1 | l1));
+    cl = (c2 & l2) | (cl & (c2 | l2));
+    cl = (c3 & l3) | (cl & (c3 | l3));
+    return ~cy & cl;
   }
 };
 
@@ -132,15 +141,7 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
   for (uint32_t i0 = 0; i0 < n; i0 += 32) {
     uint4 e = make_uint4(0u, 0u, 0u, 0u);
     if (i0 + lane < n) e = q[i0 + lane];
-    uint32_t vm = e.x;
-    if (PASS_B) {  // pass B accepts only d1 > hA (the pairs with d1 <= hA belong to pass A)
-      uint32_t t = vm;
-      while (t) {
-        const int b = __ffs((int)t) - 1;
-        t &= t - 1u;
-        if (base_dist32(other[e.y + (uint32_t)b] ^ e.w) <= lo_d) vm &= ~(1u << b);
-      }
-    }
+    uint32_t vm = e.x;  // (part two: the compare itself has dropped the entries with d1 <= hA)
     const int c = __popc(vm);
     if (c && hs.gcnt) atomicAdd(hs.gcnt + e.z, (unsigned int)c);
     int incl = c;
@@ -246,7 +247,94 @@ __device__ __forceinline__ void stream_groups(uint32_t base_off, const uint32_t 
         pg += STRIDE;
       }
     }
-    queue_hits<PASS_B>(lp.match(w), it, n, lo_bit, hi_bit, idx0, gid, probe, hs, q_off, qcount, lane, lt_mask, canon, other, lo_d);
+    queue_hits<PASS_B>(lp.match(w, PASS_B ? lo_d : -1), it, n, lo_bit, hi_bit, idx0, gid, probe, hs, q_off, qcount, lane, lt_mask, canon, other, lo_d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Shared memory by 32-bit shared-window address.  The kernels below use cluster-scoped instructions (TMA bulk copies),
+// for which ptxas rebuilds the window base (S2UR SR_CgaCtaId + UMOV + ULEA) at EVERY generic access to ff_smem -- three
+// issue slots per group in the inner loop.  Addresses formed once per round and used through ld/st.shared avoid that.
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t addr, uint32_t v) {  // (inline PTX also keeps nvcc from wrapping a lane-0
+  uint32_t r;                                                                   //  atomic in its 15-instruction warp aggregation)
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(addr), "r"(v) : "memory");
+  return r;
+}
+
+// Load the 2 NB plane words of the group at shared address `a` if r >= 0 (else keep the old words): predicated loads,
+// no branch.  STRIDE % 4 == 0: 16-byte loads (the group is 16-byte aligned), else 8-byte loads.
+template <int NB, int STRIDE> struct GroupLoad;
+template <> struct GroupLoad<9, 18> {
+  static __device__ __forceinline__ void run(uint32_t (&w)[18], uint32_t a, int r) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %19, 0;\n\t"
+        "@p ld.shared.v2.u32 {%0, %1}, [%18];\n\t@p ld.shared.v2.u32 {%2, %3}, [%18+8];\n\t@p ld.shared.v2.u32 {%4, %5}, [%18+16];\n\t"
+        "@p ld.shared.v2.u32 {%6, %7}, [%18+24];\n\t@p ld.shared.v2.u32 {%8, %9}, [%18+32];\n\t@p ld.shared.v2.u32 {%10, %11}, [%18+40];\n\t"
+        "@p ld.shared.v2.u32 {%12, %13}, [%18+48];\n\t@p ld.shared.v2.u32 {%14, %15}, [%18+56];\n\t@p ld.shared.v2.u32 {%16, %17}, [%18+64];\n\t}"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]), "+r"(w[10]),
+          "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "+r"(w[16]), "+r"(w[17])
+        : "r"(a), "r"(r));
+  }
+};
+template <> struct GroupLoad<10, 20> {
+  static __device__ __forceinline__ void run(uint32_t (&w)[20], uint32_t a, int r) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %21, 0;\n\t"
+        "@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%20];\n\t@p ld.shared.v4.u32 {%4, %5, %6, %7}, [%20+16];\n\t"
+        "@p ld.shared.v4.u32 {%8, %9, %10, %11}, [%20+32];\n\t@p ld.shared.v4.u32 {%12, %13, %14, %15}, [%20+48];\n\t"
+        "@p ld.shared.v4.u32 {%16, %17, %18, %19}, [%20+64];\n\t}"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]), "+r"(w[10]),
+          "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19])
+        : "r"(a), "r"(r));
+  }
+};
+template <> struct GroupLoad<11, 24> {
+  static __device__ __forceinline__ void run(uint32_t (&w)[22], uint32_t a, int r) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %23, 0;\n\t"
+        "@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%22];\n\t@p ld.shared.v4.u32 {%4, %5, %6, %7}, [%22+16];\n\t"
+        "@p ld.shared.v4.u32 {%8, %9, %10, %11}, [%22+32];\n\t@p ld.shared.v4.u32 {%12, %13, %14, %15}, [%22+48];\n\t"
+        "@p ld.shared.v4.u32 {%16, %17, %18, %19}, [%22+64];\n\t@p ld.shared.v2.u32 {%20, %21}, [%22+80];\n\t}"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]), "+r"(w[10]),
+          "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]),
+          "+r"(w[21])
+        : "r"(a), "r"(r));
+  }
+};
+
+// The shared-memory inner loop of both scan kernels.  The lane streams its n + 1 groups (n = -1: idle lane, and then
+// last_mask must be 0) starting at shared address `sa`; entry 0 of the first group has index idx0; first_mask / last_mask
+// cut the first / last group to the bucket's range (FIRST_CUT = false: buckets start at a group boundary).  The loop is
+// warp-uniform (longest bucket of the warp).  A lane with a non-zero hit word queues (word, index of entry 0, guide,
+// probe) at the warp's queue (shared address qa, generic offset q_off); the queue is drained when >= 32 entries wait.
+template <int NB, int STRIDE, bool PASS_B, bool FIRST_CUT>
+__device__ __forceinline__ void stream_smem(uint32_t sa, int n, uint32_t idx0, uint32_t first_mask, uint32_t last_mask, const LaneProbe<NB> &lp,
+                                            uint32_t gid, uint32_t probe, const HitSink &hs, uint32_t qa, uint32_t q_off, uint32_t &qcount,
+                                            int lane, const uint32_t *canon, const uint32_t *other, int lo_d) {
+  const int T = __reduce_max_sync(0xffffffffu, n);
+  uint32_t w[2 * NB];
+#pragma unroll
+  for (int j = 0; j < 2 * NB; ++j) w[j] = 0u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int r = n;  // groups left after this one
+  for (int it = 0; it <= T; ++it) {
+    GroupLoad<NB, STRIDE>::run(w, sa, r);
+    uint32_t cut = r > 0 ? 0xFFFFFFFFu : last_mask;  // r < 0: last_mask has been cleared
+    if (r <= 0) last_mask = 0u;
+    if (FIRST_CUT) { cut &= first_mask; first_mask = 0xFFFFFFFFu; }
+    const uint32_t hm = lp.match(w, PASS_B ? lo_d : -1) & cut;
+    const uint32_t hb = __ballot_sync(0xffffffffu, hm != 0u);
+    if (hb) {
+      if (hm)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(qa + 16u * (qcount + (uint32_t)__popc(hb & lt_mask))), "r"(hm), "r"(idx0),
+                     "r"(gid), "r"(probe) : "memory");
+      qcount += (uint32_t)__popc(hb);
+      if (qcount >= 32u) {
+        drain_queue<PASS_B>(hs, q_off, qcount, lane, canon, other, lo_d);
+        qcount = 0;
+      }
+    }
+    sa += STRIDE * 4; idx0 += 32u; --r;
   }
 }
 
@@ -319,6 +407,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
   uint32_t phase = 0;
   unsigned long long compares = 0;
   const uint32_t q_off = kShOff + (uint32_t)offsetof(BinShared, q) + (uint32_t)warp * kQCap * 16u;
+  const uint32_t sbase = smem_addr(ff_smem), claim_addr = smem_addr(&sh.next_slice);
   uint32_t qcount = 0;
   for (;;) {
     __syncthreads();  // the previous bin is finished: its slice and tables may be overwritten
@@ -479,7 +568,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
         const uint32_t nv = sh.bstart[256];
         for (;;) {  // warps take 32 sorted pairs at a time
           uint32_t j0 = 0;
-          if (lane == 0) j0 = atomicAdd(&sh.next_slice, 32u);
+          if (lane == 0) j0 = atom_add_shared(claim_addr, 32u);
           j0 = __shfl_sync(0xffffffffu, j0, 0);
           if (j0 >= nv) break;
           const uint32_t j = j0 + lane;
@@ -497,7 +586,8 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
           const int n = len ? (int)((len - 1u) >> 5) : -1;           // every bucket starts a group: ceil(len / 32) groups,
           const uint32_t hi_bit = ((len - 1u) & 31u) + 1u;           // only the last one is cut
           if (glob) stream_groups<NB, STRIDE, false, false>(0u, bp.planes + (size_t)g_base * STRIDE, g_base, g0, n, lo, 0u, hi_bit, lp, gid, probe, bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
-          else stream_groups<NB, STRIDE, false, true>(0u, nullptr, g_base, g0, n, lo, 0u, hi_bit, lp, gid, probe, bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
+          else stream_smem<NB, STRIDE, false, false>(sbase + (g0 - g_base) * (uint32_t)(STRIDE * 4), n, lo, 0xFFFFFFFFu, len ? 0xFFFFFFFFu >> (32u - hi_bit) : 0u, lp,
+                                                     gid, probe, bp.hs, sbase + q_off, q_off, qcount, lane, bp.canon, nullptr, -1);
         }
       }
       if (!waited) {  // no pairs at all: still consume the copy before the buffer is reused
@@ -522,7 +612,11 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
 // part two: (guide, seed) pairs of index B, counting-sorted by bucket
 struct PairParams {
   const uint32_t *planes, *off, *other, *canon;
-  const uint4 *recs;   // x = bucket, y = probe | budget << 24, z = guide index
+  const uint4 *recs;   // x, y = the bucket's entry range [lo, hi), z = probe | budget << 24, w = guide index; sorted by bucket
+  const uint32_t *start;  // [n_keys + 1] first sorted pair of every bucket
+  int rb_shift;        // k_pair_scan2: a "B-bin" = 2^rb_shift consecutive buckets
+  uint32_t n_bbins;
+  int seg_shift;       // k_pair_scan2: a round of 32 pairs is cut into 2^seg_shift work items (consecutive group ranges)
   long long n_pairs;
   int lo_d;
   HitSink hs;
@@ -553,12 +647,12 @@ __global__ void k_bpairs_hist(const uint64_t *__restrict__ guides, long long n_p
 
 __global__ void k_bpairs_scatter(const uint64_t *__restrict__ guides, long long n_pairs, const uint32_t *__restrict__ masks, int n_seeds,
                                  int proto_shift, uint64_t proto_mask, int b_bits, int k, const unsigned int *__restrict__ start,
-                                 unsigned int *__restrict__ cursor, uint4 *__restrict__ recs) {
+                                 unsigned int *__restrict__ cursor, const uint32_t *__restrict__ off, uint4 *__restrict__ recs) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n_pairs) return;
   uint32_t kk, pb, gid;
   b_pair(guides, masks, n_seeds, proto_shift, proto_mask, b_bits, k, idx, &kk, &pb, &gid);
-  recs[start[kk] + atomicAdd(cursor + kk, 1u)] = make_uint4(kk, pb, gid, 0u);
+  recs[start[kk] + atomicAdd(cursor + kk, 1u)] = make_uint4(off[kk], off[kk + 1], pb, gid);
 }
 
 // 3 CTAs per SM (80 registers).  Tried on the GPU and dropped: a register double buffer of the next group (0.99 ms), two
@@ -569,7 +663,10 @@ __global__ void k_bpairs_scatter(const uint64_t *__restrict__ guides, long long 
 #ifndef FF_PAIR_MIN_BLOCKS
 #define FF_PAIR_MIN_BLOCKS 3
 #endif
-constexpr int kPairThreads = 256;
+#ifndef FF_PAIR_THREADS
+#define FF_PAIR_THREADS 256
+#endif
+constexpr int kPairThreads = FF_PAIR_THREADS;
 constexpr int kPairWarps = kPairThreads / 32;
 
 template <int NB>
@@ -590,8 +687,8 @@ __global__ void __launch_bounds__(kPairThreads, FF_PAIR_MIN_BLOCKS) k_pair_scan(
     int budget = -1;
     if (pi < pp.n_pairs) {
       const uint4 r = pp.recs[pi];
-      lo = pp.off[r.x]; hi = pp.off[r.x + 1];
-      probe = r.y & 0xFFFFFFu; budget = (int)(r.y >> 24); gid = r.z;
+      lo = r.x; hi = r.y;
+      probe = r.z & 0xFFFFFFu; budget = (int)(r.z >> 24); gid = r.w;
     }
     compares += hi - lo;
     LaneProbe<NB> lp;
@@ -599,6 +696,173 @@ __global__ void __launch_bounds__(kPairThreads, FF_PAIR_MIN_BLOCKS) k_pair_scan(
     const int n = hi > lo ? (int)(((hi - 1u) >> 5) - (lo >> 5)) : -1;  // groups are cut at multiples of 32 entries
     stream_groups<NB, STRIDE, true, false>(0u, pp.planes, 0u, lo >> 5, n, lo & ~31u, lo & 31u, ((hi - 1u) & 31u) + 1u, lp, gid, probe, pp.hs,
                                            q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
+  }
+  drain_queue<true>(pp.hs, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
+  for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
+  if (lane == 0 && compares) atomicAdd(pp.n_compares, compares);
+}
+
+// Part two through shared memory.  With many guides every bucket of index B is visited (10.7 pairs per bucket at 100 000
+// guides), so the pass is a join of the sorted pair list with the whole index.  "B-bin" = 2^rb_shift consecutive buckets,
+// in index order; its run of bit-sliced groups and its slice of the sorted pair list are staged with TMA bulk copies.
+// A CTA owns a ring of TWO staging buffers and NO CTA-wide barrier: every warp walks the CTA's bins in sequence, waits
+// for the bin's "full" mbarrier, claims work items -- 32 consecutive sorted pairs x one of 2^seg_shift consecutive
+// group ranges of their buckets (a bucket is ~36 groups) -- and, when it finds none left, signs off the bin with an atomic
+// on its "left" counter and moves on to the next bin in the other buffer.  The LAST warp to leave bin i refills that
+// buffer with bin i + 2 (claims it from the global counter, reads its offsets, starts the copies): a split barrier.  Warps
+// never wait for each other unless they are a whole bin apart.  Index B comes from HBM exactly once; the group loop
+// reads shared memory (broadcast: neighbouring lanes hold pairs of the same bucket).  A bin whose run does not fit the
+// buffer streams from global memory like k_pair_scan.
+#ifndef FF_P2_GROUPS
+#define FF_P2_GROUPS 304
+#endif
+#ifndef FF_P2_BLOCKS
+#define FF_P2_BLOCKS 3
+#endif
+#ifndef FF_P2_THREADS
+#define FF_P2_THREADS 256
+#endif
+#ifndef FF_P2_RECS
+#define FF_P2_RECS 192
+#endif
+constexpr int kP2Threads = FF_P2_THREADS;
+constexpr int kP2Warps = kP2Threads / 32;
+constexpr int kP2Groups = FF_P2_GROUPS;  // groups per staging buffer (x 96 B = 29 KB)
+constexpr int kP2Recs = FF_P2_RECS;      // sorted pairs staged per buffer (more: read from global memory)
+
+struct Pair2Meta { uint32_t end, p0, p1, g_base, glob, recs_staged, pad0, pad1; };
+struct Pair2Shared {
+  unsigned long long full[2];
+  uint32_t left[2], next_item[2];
+  Pair2Meta meta[2];
+  uint4 q[kP2Warps][kQCap];
+};
+
+template <int NB> struct Pair2Layout {
+  static constexpr int STRIDE = (2 * NB + 3) & ~3;
+  static constexpr uint32_t kSlice = (uint32_t)kP2Groups * STRIDE * 4;
+  static constexpr uint32_t kRecs = 2u * kSlice;                       // uint4 recs[2][kP2Recs]
+  static constexpr uint32_t kShOff = kRecs + 2u * (uint32_t)kP2Recs * 16u;
+  static constexpr size_t kBytes = (size_t)kShOff + sizeof(Pair2Shared);
+};
+
+// One lane: find the CTA's next non-empty bin and start its copies into buffer b (or publish the end of the work).
+template <int NB>
+__device__ __forceinline__ void p2_refill(const PairParams &pp, Pair2Shared &sh, uint32_t sbase, int b) {
+  using L = Pair2Layout<NB>;
+  const uint32_t mbar = smem_addr(&sh.full[b]);
+  const uint32_t rb = (uint32_t)pp.rb_shift;
+  for (;;) {
+    const uint32_t bin = (uint32_t)atomicAdd(pp.next_item, 1ull);
+    if (bin >= pp.n_bbins) {
+      sh.meta[b].end = 1u;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+      return;
+    }
+    const uint32_t e0 = __ldg(pp.off + ((size_t)bin << rb)), e1 = __ldg(pp.off + ((size_t)(bin + 1u) << rb));
+    const uint32_t p0 = __ldg(pp.start + ((size_t)bin << rb)), p1 = __ldg(pp.start + ((size_t)(bin + 1u) << rb));
+    if (p1 == p0 || e1 == e0) continue;  // no pairs or no entries: nothing to do in this bin
+    const uint32_t g_base = e0 >> 5, ng = ((e1 - 1u) >> 5) - g_base + 1u;
+    const bool glob = ng > (uint32_t)kP2Groups;
+    const bool recs_staged = p1 - p0 <= (uint32_t)kP2Recs;
+    Pair2Meta &m = sh.meta[b];
+    m.end = 0u; m.p0 = p0; m.p1 = p1; m.g_base = g_base; m.glob = glob ? 1u : 0u; m.recs_staged = recs_staged ? 1u : 0u;
+    sh.left[b] = 0u; sh.next_item[b] = 0u;
+    const uint32_t bytes_g = glob ? 0u : ng * (uint32_t)(L::STRIDE * 4), bytes_r = recs_staged ? (p1 - p0) * 16u : 0u;
+    if (bytes_g + bytes_r == 0u) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+      return;
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes_g + bytes_r) : "memory");
+    if (bytes_g) {
+      const uint8_t *src = reinterpret_cast<const uint8_t *>(pp.planes + (size_t)g_base * L::STRIDE);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sbase + (uint32_t)b * L::kSlice), "l"(src), "r"(bytes_g), "r"(mbar) : "memory");
+    }
+    if (bytes_r)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sbase + L::kRecs + (uint32_t)b * (uint32_t)kP2Recs * 16u), "l"(pp.recs + p0), "r"(bytes_r), "r"(mbar) : "memory");
+    return;
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kP2Threads, FF_P2_BLOCKS) k_pair_scan2(PairParams pp) {
+  using L = Pair2Layout<NB>;
+  constexpr int STRIDE = L::STRIDE;
+  Pair2Shared &sh = *reinterpret_cast<Pair2Shared *>(ff_smem + L::kShOff);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t sbase = smem_addr(ff_smem);
+  const uint32_t q_off = L::kShOff + (uint32_t)offsetof(Pair2Shared, q) + (uint32_t)warp * kQCap * 16u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sh.full[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sh.full[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    p2_refill<NB>(pp, sh, sbase, 0);
+    p2_refill<NB>(pp, sh, sbase, 1);
+  }
+  __syncthreads();  // (the only CTA-wide barrier: the mbarriers exist)
+  uint32_t qcount = 0;
+  unsigned long long compares = 0;
+  const uint32_t seg_mask = (1u << pp.seg_shift) - 1u;
+  for (uint32_t i = 0;; ++i) {
+    const int b = (int)(i & 1u);
+    {  // the bin's copies have landed (or the work has ended)
+      const uint32_t mbar = smem_addr(&sh.full[b]), parity = (i >> 1) & 1u;
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    }
+    const Pair2Meta m = sh.meta[b];
+    if (m.end) break;
+    const uint32_t p0 = m.p0, p1 = m.p1, g_base = m.g_base;
+    const uint32_t claim_addr = smem_addr(&sh.next_item[b]);
+    const uint32_t slice = sbase + (uint32_t)b * L::kSlice, recs_sm = sbase + L::kRecs + (uint32_t)b * (uint32_t)kP2Recs * 16u;
+    const uint32_t n_items = ((p1 - p0 + 31u) >> 5) << pp.seg_shift;
+    for (;;) {
+      uint32_t item = 0;
+      if (lane == 0) item = atom_add_shared(claim_addr, 1u);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= n_items) break;
+      const uint32_t seg = item & seg_mask;
+      const uint32_t pl = ((item >> pp.seg_shift) << 5) + (uint32_t)lane;  // pair, relative to the bin's first
+      uint32_t lo = 0, hi = 0, gid = 0, probe = 0;
+      int budget = -1;
+      if (p0 + pl < p1) {
+        uint4 r;
+        if (m.recs_staged) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(recs_sm + pl * 16u));
+        else r = __ldg(pp.recs + p0 + pl);
+        lo = r.x; hi = r.y;
+        probe = r.z & 0xFFFFFFu; budget = (int)(r.z >> 24); gid = r.w;
+      }
+      if (seg == 0) compares += hi - lo;
+      LaneProbe<NB> lp;
+      lp.set(probe, budget);
+      // the lane's bucket spans groups g_first .. g_first + n_all - 1; this item takes the seg-th part of them
+      const uint32_t g_first = lo >> 5;
+      const uint32_t n_all = hi > lo ? ((hi - 1u) >> 5) - g_first + 1u : 0u;
+      const uint32_t ga = n_all * seg >> pp.seg_shift, gb = n_all * (seg + 1u) >> pp.seg_shift;
+      const int n = (int)gb - (int)ga - 1;  // -1: nothing for this lane
+      const uint32_t g0 = g_first + ga;
+      if (m.glob) {  // (rare: a run longer than the staging buffer) the same groups from global memory; the cuts as bit positions
+        const uint32_t lo_bit = ga == 0u ? (lo & 31u) : 0u, hi_bit = gb == n_all ? ((hi - 1u) & 31u) + 1u : 32u;
+        stream_groups<NB, STRIDE, true, false>(0u, pp.planes, 0u, g0, n, g0 << 5, lo_bit, hi_bit, lp, gid, probe, pp.hs, q_off, qcount, lane, pp.canon,
+                                               pp.other, pp.lo_d);
+      } else {
+        const uint32_t first_mask = ga == 0u ? 0xFFFFFFFFu << (lo & 31u) : 0xFFFFFFFFu;
+        const uint32_t last_mask = n < 0 ? 0u : (gb == n_all ? 0xFFFFFFFFu >> (31u - ((hi - 1u) & 31u)) : 0xFFFFFFFFu);
+        stream_smem<NB, STRIDE, true, true>(slice + (g0 - g_base) * (uint32_t)(STRIDE * 4), n, g0 << 5, first_mask, last_mask, lp, gid, probe, pp.hs,
+                                            sbase + q_off, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
+      }
+    }
+    // sign off: this warp reads nothing of bin i any more; the last one out refills the buffer with bin i + 2
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (atom_add_shared(smem_addr(&sh.left[b]), 1u) == (uint32_t)kP2Warps - 1u) p2_refill<NB>(pp, sh, sbase, b);
+    }
+    __syncwarp();
   }
   drain_queue<true>(pp.hs, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
   for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
@@ -629,6 +893,7 @@ struct BinScanPlan {
   BinParams bp;
   PairParams pp;
   bool part_two;
+  bool staged_b;   // part two through shared memory (k_pair_scan2) or lanes reading global memory (k_pair_scan)
   int nb_a, nb_b;  // other bases of the two halves
   size_t smem_a;
 };
@@ -685,7 +950,7 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
     k_bpairs_hist<<<blocks_for(n_pairs, 256), 256, 0, st>>>(sp.guides, n_pairs, db.B.d_masks, nB, sp.proto_shift, sp.proto_mask, sp.b_bits, sp.k, b_cnt);
     FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp2, b_cnt, b_start, (int)(n_keys_b + 1), st));
     k_bpairs_scatter<<<blocks_for(n_pairs, 256), 256, 0, st>>>(sp.guides, n_pairs, db.B.d_masks, nB, sp.proto_shift, sp.proto_mask, sp.b_bits, sp.k,
-                                                               b_start, b_cur, recs);
+                                                               b_start, b_cur, db.B.d_off, recs);
     *launches += 3;
   }
   FF_CUDA(cudaGetLastError());
@@ -706,6 +971,27 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
   pp.planes = db.B.d_planes; pp.off = db.B.d_off; pp.other = db.B.d_other; pp.canon = db.B.d_canon; pp.recs = recs;
   pp.n_pairs = n_pairs; pp.lo_d = hA; pp.hs = bp.hs; pp.n_compares = n_compares_b;
   pp.next_item = (unsigned long long *)(w + o_ctr + 64);
+  pp.start = b_start;
+  {  // B-bins of k_pair_scan2: as many buckets as fit the staging buffer on average, but enough bins to balance the grid
+    int kb_bits = 2 * db.B.key_bases;
+    const double groups_per_bucket = (double)db.n_targets / (double)n_keys_b / 32.0;
+    int rbs = 0;
+    auto fits = [&](int r) {  // mean run of 2^r buckets + three standard deviations (Poisson bucket sizes) within the buffer
+      const double entries = groups_per_bucket * 32.0 * (double)(1u << r);
+      return entries / 32.0 + 1.0 + 3.0 * std::sqrt(entries) / 32.0 <= (double)kP2Groups;
+    };
+    while (rbs + 1 <= kb_bits && fits(rbs + 1)) ++rbs;
+    rbs = std::min(rbs, std::max(0, kb_bits - 11));
+    pp.rb_shift = rbs; pp.n_bbins = n_keys_b >> rbs;
+    const double rounds = (double)n_pairs * (double)(1u << rbs) / (double)n_keys_b / 32.0;
+    int ss = 0;
+    while (ss < 3 && rounds * (double)(1 << ss) < 0.6 * kP2Warps && groups_per_bucket / (double)(2 << ss) >= 4.0) ++ss;
+    if (ctx->opt.pair_segs > 0) { ss = 0; while ((1 << (ss + 1)) <= ctx->opt.pair_segs) ++ss; }
+    pp.seg_shift = ss;
+  }
+  // the ring stages the WHOLE index once per call; lanes reading global memory touch only the buckets that have pairs:
+  // measured on B200 (3 x 10^8 targets) the two meet at ~11 pairs per bucket (100 000 guides); the ring wins beyond
+  pl->staged_b = ctx->opt.pair_kernel == 2 || (ctx->opt.pair_kernel == 0 && (double)n_pairs >= 12.0 * (double)n_keys_b);
   pl->part_two = n_pairs > 0;
   pl->nb_a = db.A.n_planes / 2; pl->nb_b = db.B.n_planes / 2;
   pl->smem_a = (size_t)kSliceGroups * db.A.n_planes * 4 + sizeof(BinShared);
@@ -727,10 +1013,23 @@ static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, u
   (*launches)++;
   if (pl->part_two) {
     FF_CUDA(cudaEventRecord(ctx->ev[7], st));
-    const int grid = ctx->sm_count * FF_PAIR_MIN_BLOCKS;
-    const size_t qsm = (size_t)kPairWarps * kQCap * 16;
-    if (pl->nb_b == 11) k_pair_scan<11><<<grid, kPairThreads, qsm, st>>>(pl->pp);
-    else k_pair_scan<10><<<grid, kPairThreads, qsm, st>>>(pl->pp);
+    if (pl->staged_b) {
+      const size_t sm2 = pl->nb_b == 11 ? Pair2Layout<11>::kBytes : Pair2Layout<10>::kBytes;
+      static bool attr2[64] = {false};
+      if (!attr2[ctx->device & 63]) {
+        FF_CUDA(cudaFuncSetAttribute(k_pair_scan2<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pair2Layout<11>::kBytes));
+        FF_CUDA(cudaFuncSetAttribute(k_pair_scan2<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pair2Layout<10>::kBytes));
+        attr2[ctx->device & 63] = true;
+      }
+      const int grid = (int)std::min<uint32_t>((uint32_t)(ctx->sm_count * FF_P2_BLOCKS), pl->pp.n_bbins);
+      if (pl->nb_b == 11) k_pair_scan2<11><<<grid, kP2Threads, sm2, st>>>(pl->pp);
+      else k_pair_scan2<10><<<grid, kP2Threads, sm2, st>>>(pl->pp);
+    } else {
+      const int grid = ctx->sm_count * FF_PAIR_MIN_BLOCKS;
+      const size_t qsm = (size_t)kPairWarps * kQCap * 16;
+      if (pl->nb_b == 11) k_pair_scan<11><<<grid, kPairThreads, qsm, st>>>(pl->pp);
+      else k_pair_scan<10><<<grid, kPairThreads, qsm, st>>>(pl->pp);
+    }
     (*launches)++;
   }
   FF_CUDA(cudaGetLastError());

@@ -118,6 +118,9 @@ struct Options {
   int split_a = 0;         // > 0: bases in the part-one key of the next database build
   int trace = 0;           // 1 = ff_discover prints host-side timestamps of its sub-batches to stderr
   int compact_hits = 0;    // ff_discover: 1 = ship database indices instead of target longs (ff_hits.target_index)
+  int pair_kernel = 0;     // part two of the bin-major scan: 0 = by pairs per bucket, 1 = k_pair_scan (lanes read global memory),
+                           // 2 = k_pair_scan2 (B-bins staged in shared memory by a two-buffer TMA ring)
+  int pair_segs = 0;       // > 0: work items per round of 32 pairs in k_pair_scan2 (1, 2, 4, 8); 0 = by batch size
 };
 
 }  // namespace ff

@@ -506,9 +506,12 @@ def test_bin_major_scan_equals_guide_major_and_oracle(small_ctx, small_db, oracl
     guides = np.concatenate([helpers.random_guides(oracle, db.pack, 17 + k, 333),
                              helpers.planted_guides(db.pack, targets, 71 + k, 400, max_subs=5)])
     ref = oracle.discover_blocks(db, guides, k, 2000)
-    with small_ctx.options(scan_kernel=2):
-        got = small_ctx.discover(guides, k, 2000, positions=True)
-        helpers.assert_hits_equal(got, ref, check_positions=True)
+    for pair_kernel in (1, 2):  # part two: lanes reading global memory / B-bins staged by the TMA ring
+        with small_ctx.options(scan_kernel=2, pair_kernel=pair_kernel):
+            got = small_ctx.discover(guides, k, 2000, positions=True)
+            helpers.assert_hits_equal(got, ref, check_positions=True)
+    with small_ctx.options(scan_kernel=2, pair_kernel=2, pair_segs=8):
+        helpers.assert_hits_equal(small_ctx.discover(guides, k, 2000), ref)
     with small_ctx.options(scan_kernel=1):
         helpers.assert_hits_equal(small_ctx.discover(guides, k, 2000, positions=True), ref, check_positions=True)
 
@@ -528,7 +531,9 @@ def test_bin_major_scan_other_enzymes_and_edge_cases(ff, oracle, tmp_path):
             ctx.load_database(dbp)
             for k, max_ot in ((4, 2000), (3, 2), (0, 2000)):
                 ref = oracle.discover_blocks(db, guides, k, max_ot)
-                helpers.assert_hits_equal(ctx.discover(guides, k, max_ot, positions=True), ref, check_positions=True)
+                for pair_kernel in (1, 2):
+                    ctx.set_option("pair_kernel", pair_kernel)
+                    helpers.assert_hits_equal(ctx.discover(guides, k, max_ot, positions=True), ref, check_positions=True)
             one = ctx.discover(guides[:1], 4, 2000)
             helpers.assert_hits_equal(one, oracle.discover_blocks(db, guides[:1], 4, 2000))
             assert ctx.discover(guides[:0], 4, 2000).n_guides == 0
@@ -548,8 +553,10 @@ def test_bin_major_scan_skewed_batches(ff, oracle):
         two = np.concatenate([np.repeat(seeds[1:2], 500), helpers.planted_guides(pack, targets[:2000], 3, 500, max_subs=2)])
         for guides, max_ot in ((same, 2000), (same, 10 ** 6), (two, 50), (seeds[:1], 2000)):
             ref = oracle.discover_soa(pack, 7, targets, bin_off, guides, 4, max_ot)
-            got = ctx.discover(guides, 4, max_ot)
-            helpers.assert_hits_equal(got, ref)
+            for pair_kernel in (1, 2):
+                ctx.set_option("pair_kernel", pair_kernel)
+                got = ctx.discover(guides, 4, max_ot)
+                helpers.assert_hits_equal(got, ref)
         assert int(ref.row_ptr[-1]) > 0
 
 
@@ -602,7 +609,13 @@ def test_bin_major_scan_oversized_bins_and_buckets(ff, oracle):
         tail = np.unique(rng.integers(0, 1 << free, size=int(n * 1.3), dtype=np.uint64))[:n]
         return ((np.uint64(fixed) << np.uint64(free)) | tail) << np.uint64(4) | np.uint64(0xA)
 
-    seqs = np.unique(np.concatenate([block(11, 30_000), block(7, 40_000), block(0, 50_000)]))
+    def tail_block(n):  # n distinct targets sharing their LAST 9 protospacer bases: one long bucket of index B
+        fixed = np.uint64(int(rng.integers(0, 1 << 18)))
+        head = np.unique(rng.integers(0, 1 << 22, size=int(n * 1.3), dtype=np.uint64))[:n]
+        proto = (head << np.uint64(18)) | fixed
+        return ((proto << np.uint64(2)) | rng.integers(0, 4, len(head)).astype(np.uint64)) << np.uint64(4) | np.uint64(0xA)
+
+    seqs = np.unique(np.concatenate([block(11, 30_000), block(7, 40_000), block(0, 50_000), tail_block(20_000)]))
     counts = rng.integers(1, 4, len(seqs)).astype(np.uint64)
     targets = seqs | (counts << np.uint64(48))
     bin_off = oracle.bin_offsets_from_sorted(pack, 7, targets)
@@ -611,8 +624,9 @@ def test_bin_major_scan_oversized_bins_and_buckets(ff, oracle):
         ctx.load_database_arrays(3, targets)
         for max_ot in (2000, 10 ** 7):
             ref = oracle.discover_soa(pack, 7, targets, bin_off, guides, 4, max_ot, n_threads=os.cpu_count() or 1)
-            with ctx.options(scan_kernel=2):
-                helpers.assert_hits_equal(ctx.discover(guides, 4, max_ot), ref)
+            for pair_kernel in (1, 2):  # (2: a B-bin whose run of groups exceeds the ring's buffer streams from global memory)
+                with ctx.options(scan_kernel=2, pair_kernel=pair_kernel):
+                    helpers.assert_hits_equal(ctx.discover(guides, 4, max_ot), ref)
             with ctx.options(scan_kernel=1):
                 helpers.assert_hits_equal(ctx.discover(guides, 4, max_ot), ref)
         assert int(ref.row_ptr[-1]) > 10_000  # the planted guides really sit in the big bucket / bin

@@ -44,14 +44,17 @@ def test_benchmark_size_both_scan_kernels_equal_the_oracle(big, oracle):
     for kernel in (1, 2):
         with ctx.options(scan_kernel=kernel):
             _hits_equal(ctx.discover(sample, 4, 2000), ref)
+    with ctx.options(scan_kernel=2, pair_kernel=2):  # part two through the two-buffer TMA ring (default only beyond ~110 000 guides)
+        _hits_equal(ctx.discover(sample, 4, 2000), ref)
     # the sample inside the full batch, through the host entry point with its sub-batches (bin-major kernels by default)
     full = ctx.discover(guides, 4, 2000)
     n = int(ref.row_ptr[-1])
     assert (full.row_ptr[:2049] == ref.row_ptr).all() and (full.targets[:n] == ref.targets).all() and (full.mismatches[:n] == ref.mismatches).all()
     assert (full.total_count[:2048] == ref.total_count).all() and (full.overflowed[:2048] == ref.overflowed).all()
-    with ctx.options(scan_kernel=1):
-        other = ctx.discover(guides, 4, 2000)
-    assert (other.row_ptr == full.row_ptr).all() and (other.targets == full.targets).all() and (other.mismatches == full.mismatches).all()
+    for opts in ({"scan_kernel": 1}, {"pair_kernel": 2}):
+        with ctx.options(**opts):
+            other = ctx.discover(guides, 4, 2000)
+        assert (other.row_ptr == full.row_ptr).all() and (other.targets == full.targets).all() and (other.mismatches == full.mismatches).all()
     # compact hit lists at this size
     with ctx.options(compact_hits=1):
         comp = ctx.discover(guides[:20000], 4, 2000, resolve=True)

@@ -31,14 +31,18 @@ guides = bench.make_guides(G, bench.SEED_GUIDES, sample, bench.SEED_PLANTED)
 d_g = torch.from_numpy(guides.view(np.int64)).cuda()
 
 ref = None
-for m in modes:
-    ctx.set_option("scan_kernel", int(m))
+for m in modes:  # "2" or "2:pair_kernel=1:pair_segs=8" (scan kernel, then options)
+    parts = m.split(":")
+    ctx.set_option("scan_kernel", int(parts[0]))
+    for kv in parts[1:]:
+        key, val = kv.split("=")
+        ctx.set_option(key, int(val))
     best = None
     for r in range(reps):
         res = ctx.discover_device(d_g.data_ptr(), len(guides), k, 2000)
         tm = ctx.timings()
         if best is None or tm.total_ms < best[0]:
-            best = (tm.total_ms, tm.prep_ms, tm.scan_ms, tm.order_ms, tm.cut_ms)
+            best = (tm.total_ms, tm.prep_ms, tm.scan_ms, tm.order_ms, tm.cut_ms, tm.scan_part1_ms, tm.scan_part2_ms)
     H = int(res.n_hits)
     rp = torch.empty(len(guides) + 1, dtype=torch.int64, device="cuda")
     tg = torch.empty(max(H, 1), dtype=torch.int64, device="cuda")
@@ -51,7 +55,7 @@ for m in modes:
         cudart.cudaMemcpy(C.c_void_p(mm.data_ptr()), C.c_void_p(res.d_mismatches), C.c_size_t(H), 3)
     torch.cuda.synchronize()
     cur = (rp.cpu().numpy(), tg.cpu().numpy()[:H], mm.cpu().numpy()[:H])
-    print("mode %s: total %.3f ms (prep %.3f scan %.3f order %.3f cut %.3f) hits %d cand %d compares %.3e" %
+    print("mode %s: total %.3f ms (prep %.3f scan %.3f order %.3f cut %.3f; part one %.3f part two %.3f) hits %d cand %d compares %.3e" %
           ((m,) + best + (H, int(res.n_candidate_hits), float(res.n_compares))), flush=True)
     if ref is None:
         ref = cur
