@@ -63,7 +63,10 @@ SYMBOLS = ["ff_create", "ff_destroy", "ff_last_error", "ff_abi_version", "ff_set
            "ff_save_image", "ff_load_image", "ff_load_database_arrays", "ff_synth_database", "ff_synth_database_skewed", "ff_db_info", "ff_db_contig", "ff_db_copy_targets",
            "ff_discover", "ff_hits_write_tsv", "ff_discover_bulge", "ff_discover_bulge_device", "ff_hits_free", "ff_db_host_targets", "ff_hits_resolve", "ff_score", "ff_score_enzyme", "ff_hit_aggregates", "ff_discover_score", "ff_discover_device", "ff_last_timings",
            "ff_multi_create", "ff_multi_destroy", "ff_multi_size", "ff_multi_ctx", "ff_multi_set_option", "ff_multi_load_database",
-           "ff_multi_synth_database", "ff_shard_range", "ff_multi_discover", "ff_multi_device_totals"]
+           "ff_multi_synth_database", "ff_shard_range", "ff_multi_discover", "ff_multi_device_totals",
+           "ff_peer_export", "ff_peer_attach", "ff_peer_detach", "ff_discover_sharded_device", "ff_discover_sharded",
+           "ff_peer_totals_device"]
+FF_PEER_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -125,6 +128,13 @@ def lib():
     L.ff_multi_discover.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.POINTER(FFHits)), i32p]
     L.ff_multi_device_totals.argtypes = [vp, C.c_int]
     L.ff_multi_device_totals.restype = vp
+    L.ff_peer_export.argtypes = [vp, C.c_uint64, C.c_int64, vp, C.POINTER(vp)]
+    L.ff_peer_attach.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.ff_peer_detach.argtypes = [vp]
+    L.ff_discover_sharded_device.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.POINTER(FFDeviceResult)]
+    L.ff_discover_sharded.argtypes = [vp, u64p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.POINTER(FFHits))]
+    L.ff_peer_totals_device.argtypes = [vp]
+    L.ff_peer_totals_device.restype = vp
     _lib = L
     return L
 

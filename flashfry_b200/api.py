@@ -231,6 +231,43 @@ class Context:
                                            metrics, C.byref(r)))
         return r
 
+    # ---- database-sharded discover over NVLink peer memory (one process per GPU: exchange the handles, e.g. with
+    # torch.distributed.all_gather; include/flashfry_b200.h, ff_peer_*) ----
+    def peer_export(self, hit_cap: int = 0, guide_cap: int = 0) -> bytes:
+        """Make this rank's exchange block; returns its CUDA IPC handle (64 bytes) for the other ranks."""
+        h = (C.c_ubyte * N.FF_PEER_HANDLE_BYTES)()
+        N.check(N.lib().ff_peer_export(self._h, hit_cap, guide_cap, C.cast(h, C.c_void_p), None))
+        return bytes(h)
+
+    def peer_attach(self, rank: int, world: int, handles: Sequence[bytes]):
+        """Map the exchange blocks of all ranks (handles[r] from rank r's peer_export)."""
+        buf = b"".join(handles)
+        assert len(buf) == world * N.FF_PEER_HANDLE_BYTES
+        arr = (C.c_ubyte * len(buf)).from_buffer_copy(buf)
+        N.check(N.lib().ff_peer_attach(self._h, rank, world, C.cast(arr, C.c_void_p), None))
+
+    def peer_detach(self):
+        N.check(N.lib().ff_peer_detach(self._h))
+
+    def discover_sharded_device(self, d_guides_all_ptr: int, n_guides_all: int, max_mismatch: int = 4,
+                                maximum_off_targets: int = 2000, metrics: int = 0) -> N.FFDeviceResult:
+        """All guides in (identical on every rank), the rows of this rank's guides out (ff_shard_range)."""
+        r = N.FFDeviceResult()
+        N.check(N.lib().ff_discover_sharded_device(self._h, C.c_void_p(d_guides_all_ptr), n_guides_all, max_mismatch,
+                                                   maximum_off_targets, metrics, C.byref(r)))
+        return r
+
+    def discover_sharded(self, guides_all, max_mismatch: int = 4, maximum_off_targets: int = 2000) -> "Hits":
+        g = _u64(guides_all)
+        hp = C.POINTER(N.FFHits)()
+        N.check(N.lib().ff_discover_sharded(self._h, g.ctypes.data_as(C.POINTER(C.c_uint64)), len(g), max_mismatch,
+                                            maximum_off_targets, C.byref(hp)))
+        return _take_hits(hp)
+
+    def peer_totals_ptr(self) -> int:
+        """Device pointer to the all-gathered per-guide totals (int32[n_guides_all]) after a sharded call."""
+        return int(N.lib().ff_peer_totals_device(self._h) or 0)
+
     def timings(self) -> N.FFTimings:
         t = N.FFTimings()
         N.check(N.lib().ff_last_timings(self._h, C.byref(t)))

@@ -308,6 +308,8 @@ int ff_create(ff_ctx **out, int device_id) {
   });
 }
 
+static void peer_unmap(ff_ctx *c);
+
 void ff_destroy(ff_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -318,6 +320,8 @@ void ff_destroy(ff_ctx *c) {
                     &c->pos_ptr, &c->out_positions, &c->cfd_per_ot, &c->hsu_per_ot, &c->scratch_guides, &c->running, &c->active, &c->active2,
                     &c->act_flags, &c->seg_end, &c->kept_keys, &c->kept_sorted, &c->n_sel, &c->cell_ws, &c->idx32, &c->st_targets, &c->st_mm};
   for (DevBuf *b : bufs) b->release();
+  peer_unmap(c);
+  c->peer.block.release();
   if (c->h_status) cudaFreeHost(c->h_status);
   c->host_targets.release();
   for (auto &os : c->out) {
@@ -708,6 +712,157 @@ int ff_discover_bulge_device(ff_ctx *c, const uint64_t *d_guides, int64_t n_guid
     out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
     out->d_cfd_max = out->d_cfd_specificity = out->d_hsu2013 = nullptr;
     out->d_bulge = r.d_bulge;
+    return FF_OK;
+  });
+}
+
+// ---- database-sharded discover (ff_shard.inl) --------------------------------------------------------------
+static void peer_unmap(ff_ctx *c) {
+  PeerLink &pl = c->peer;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    if (pl.ipc_opened[r] && pl.base[r]) cudaIpcCloseMemHandle(pl.base[r]);
+    pl.ipc_opened[r] = false;
+    pl.base[r] = nullptr;
+  }
+  pl.ready = false;
+}
+
+int ff_peer_export(ff_ctx *c, uint64_t hit_cap, int64_t guide_cap, void *handle_out, void **block_out) {
+  return guarded([&]() -> int {
+    if (!c || !handle_out) { set_error("null argument"); return FF_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == FF_PEER_HANDLE_BYTES, "IPC handle size");
+    FF_CUDA(cudaSetDevice(c->device));
+    PeerLink &pl = c->peer;
+    peer_unmap(c);
+    if (hit_cap == 0) hit_cap = 1ull << 24;
+    if (guide_cap <= 0) guide_cap = 1ll << 20;
+    if (hit_cap > (1ull << 31) || guide_cap > (1ll << 28)) { set_error("exchange block too large"); return FF_EINVAL; }
+    pl.block.release();
+    FF_TRY(pl.block.reserve(kPeerHeadBytes + (size_t)hit_cap * 8 + (size_t)guide_cap * 4));
+    FF_CUDA(cudaMemset(pl.block.p, 0, kPeerHeadBytes));
+    pl.hit_cap = (size_t)hit_cap; pl.g_cap = guide_cap; pl.epoch = 0;
+    cudaIpcMemHandle_t h;
+    FF_CUDA(cudaIpcGetMemHandle(&h, pl.block.p));
+    memcpy(handle_out, &h, sizeof(h));
+    if (block_out) *block_out = pl.block.p;
+    return FF_OK;
+  });
+}
+
+int ff_peer_attach(ff_ctx *c, int rank, int world, const void *handles, void *const *blocks) {
+  return guarded([&]() -> int {
+    if (!c) { set_error("null context"); return FF_EINVAL; }
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("bad rank / world (at most %d ranks)", kMaxPeers); return FF_EINVAL; }
+    if (world > 1 && !handles && !blocks) { set_error("neither IPC handles nor block pointers given"); return FF_EINVAL; }
+    PeerLink &pl = c->peer;
+    if (!pl.block.p) { set_error("ff_peer_export first"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    peer_unmap(c);
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) { pl.base[r] = pl.block.as<uint8_t>(); continue; }
+      if (blocks) {  // same process: enable peer access to the block's device (unless it is this device)
+        cudaPointerAttributes at;
+        FF_CUDA(cudaPointerGetAttributes(&at, blocks[r]));
+        if (at.type != cudaMemoryTypeDevice) { set_error("block of rank %d is not device memory", r); return FF_EINVAL; }
+        if (at.device != c->device) {
+          int can = 0;
+          FF_CUDA(cudaDeviceCanAccessPeer(&can, c->device, at.device));
+          if (!can) { set_error("device %d cannot access device %d", c->device, at.device); return FF_EUNSUPPORTED; }
+          const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+          cudaGetLastError();
+        }
+        pl.base[r] = static_cast<uint8_t *>(blocks[r]);
+      } else {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const uint8_t *>(handles) + (size_t)r * FF_PEER_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        FF_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        pl.base[r] = static_cast<uint8_t *>(p);
+        pl.ipc_opened[r] = true;
+      }
+    }
+    pl.rank = rank; pl.world = world; pl.epoch = 0;
+    FF_CUDA(cudaMemset(pl.block.p, 0, kPeerHeadBytes));  // (every rank attaches before the first sharded call: counters start at 0)
+    pl.ready = true;
+    return FF_OK;
+  });
+}
+
+int ff_peer_detach(ff_ctx *c) {
+  return guarded([&]() -> int {
+    if (!c) { set_error("null context"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    cudaStreamSynchronize(c->stream);
+    peer_unmap(c);
+    return FF_OK;
+  });
+}
+
+const int32_t *ff_peer_totals_device(ff_ctx *c) {
+  if (!c || !c->peer.block.p) return nullptr;
+  return reinterpret_cast<const int32_t *>(c->peer.block.as<uint8_t>() + kPeerHeadBytes + c->peer.hit_cap * 8);
+}
+
+int ff_discover_sharded_device(ff_ctx *c, const uint64_t *d_guides_all, int64_t n_all, int max_mm, int max_ot, uint32_t metrics,
+                               ff_device_result *out) {
+  return guarded([&]() -> int {
+    if (!c || !out) { set_error("null argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    DeviceResult r;
+    FF_TRY(discover_sharded(c, d_guides_all, n_all, max_mm, max_ot, 0, &r));
+    const int64_t first = c->peer.world > 0 ? n_all * c->peer.rank / c->peer.world : 0;
+    FF_TRY(score_slot(c, d_guides_all + first, r, metrics, 0));
+    out->d_bulge = nullptr;
+    out->n_guides = r.n_guides; out->n_hits = r.n_hits; out->n_candidate_hits = r.n_candidate_hits; out->n_compares = r.n_compares;
+    out->d_row_ptr = r.d_row_ptr; out->d_targets = r.d_targets; out->d_mismatches = r.d_mismatches;
+    out->d_total_count = r.d_total_count; out->d_overflowed = r.d_overflowed;
+    out->d_cfd_max = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_max.as<double>() : nullptr;
+    out->d_cfd_specificity = (metrics & FF_METRIC_CFD) ? c->out[0].cfd_spec.as<double>() : nullptr;
+    out->d_hsu2013 = (metrics & FF_METRIC_HSU2013) ? c->out[0].hsu.as<double>() : nullptr;
+    return FF_OK;
+  });
+}
+
+int ff_discover_sharded(ff_ctx *c, const uint64_t *guides_all, int64_t n_all, int max_mm, int max_ot, ff_hits **out) {
+  return guarded([&]() -> int {
+    if (!c || !out || (n_all > 0 && !guides_all)) { set_error("null argument"); return FF_EINVAL; }
+    *out = nullptr;
+    if (n_all < 0) { set_error("bad discover argument"); return FF_EINVAL; }
+    FF_CUDA(cudaSetDevice(c->device));
+    FF_TRY(c->scratch_guides.reserve((n_all > 0 ? n_all : 1) * 8));
+    if (n_all > 0) FF_CUDA(cudaMemcpyAsync(c->scratch_guides.p, guides_all, n_all * 8, cudaMemcpyHostToDevice, c->stream));
+    DeviceResult r;
+    FF_TRY(discover_sharded(c, c->scratch_guides.as<uint64_t>(), n_all, max_mm, max_ot, 0, &r));
+    HitsOwner *o = owner_get();
+    if (!o) { set_error("out of host memory"); return FF_ENOMEM; }
+    int rc = FF_OK;
+    const int64_t G = r.n_guides, H = r.n_hits;
+    const bool compact = c->opt.compact_hits != 0;
+    if ((rc = o->row_ptr.reserve((G + 1) * 8)) || (rc = o->total.reserve((G + 1) * 4)) || (rc = o->ovf.reserve(G + 1)) ||
+        (rc = o->mm.reserve(H + 1)) || (rc = compact ? o->tidx.reserve((H + 1) * 4) : o->targets.reserve((H + 1) * 8))) {
+      owner_put(o);
+      return rc;
+    }
+    cudaStream_t st = c->stream;  // (the stream is idle: discover_sharded waits for its status words)
+    cudaError_t e = cudaMemcpyAsync(o->row_ptr.p, r.d_row_ptr, (G + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && H > 0)
+      e = compact ? cudaMemcpyAsync(o->tidx.p, r.d_tidx, H * 4, cudaMemcpyDeviceToHost, st) : cudaMemcpyAsync(o->targets.p, r.d_targets, H * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && H > 0) e = cudaMemcpyAsync(o->mm.p, r.d_mismatches, H, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && G > 0) e = cudaMemcpyAsync(o->total.p, r.d_total_count, G * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && G > 0) e = cudaMemcpyAsync(o->ovf.p, r.d_overflowed, G, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { owner_put(o); return cuda_fail(e, "D2H of discover results", __FILE__, __LINE__); }
+    ff_hits &h = o->pub;
+    h.n_guides = G; h.n_hits = H;
+    h.row_ptr = o->row_ptr.as<int64_t>(); h.targets = compact ? nullptr : o->targets.as<uint64_t>(); h.mismatches = o->mm.as<uint8_t>();
+    h.target_index = compact ? o->tidx.as<uint32_t>() : nullptr;
+    h.pos_ptr = nullptr; h.positions = nullptr;
+    h.total_count = o->total.as<int32_t>(); h.overflowed = o->ovf.as<uint8_t>();
+    h.n_compares = r.n_compares; h.n_candidate_hits = r.n_candidate_hits;
+    h.bulge = nullptr;
+    h.opaque = o;
+    *out = &h;
     return FF_OK;
   });
 }

@@ -117,13 +117,34 @@ template <int NB> struct LaneProbe {
   }
 };
 
+// Where candidates go.  world == 1: this context's buffer.  world > 1 (database-sharded discover, section 7 of DESIGN.md):
+// every rank scans ITS part of the index for ALL guides and pushes each candidate straight into the exchange block of
+// the rank that OWNS the guide -- peer memory over NVLink (P2P stores, one remote atomic per warp drain and owner) --,
+// so the hand-over of the candidates is fused into the scan and the owner finds its guides' candidates in its own HBM.
 struct HitSink {
   uint64_t *hits;
   unsigned long long *hit_count;
   unsigned long long hit_cap;
   int tbits;
   unsigned int *gcnt;  // per-guide candidate counts for the ordering that follows (nullptr: not wanted)
+  int world;                         // ranks of the exchange (1: no exchange)
+  unsigned int first[kMaxPeers + 1];  // first guide owned by every rank (ff_shard_range), first[world] = all guides
+  uint8_t *peer[kMaxPeers];          // exchange block of every rank: PeerCtr, totals, candidate keys
 };
+
+struct PeerCtr {  // head of an exchange block (256 bytes)
+  unsigned long long hit_count;  // candidates pushed into this block in the current step
+  unsigned int arrive;           // barrier arrivals, monotonically increasing
+  unsigned int error;            // a barrier timed out
+};
+constexpr size_t kPeerHead = kPeerHeadBytes;
+
+__device__ __forceinline__ int sink_owner(const HitSink &hs, uint32_t g) {
+  int o = (int)(((unsigned long long)g * (unsigned)hs.world) / hs.first[hs.world]);
+  while (g >= hs.first[o + 1]) ++o;  // (floors: the estimate is off by one at most, more only with fewer guides than ranks)
+  while (g < hs.first[o]) --o;
+  return o;
+}
 
 // All shared memory of the two kernels is addressed as byte offsets into this one array: a generic pointer to shared
 // memory costs an S2R + LEA (the shared window base) at every use inside the group loop.
@@ -143,6 +164,38 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
     if (i0 + lane < n) e = q[i0 + lane];
     uint32_t vm = e.x;  // (part two: the compare itself has dropped the entries with d1 <= hA)
     const int c = __popc(vm);
+    if (hs.world > 1) {  // push to the owners' exchange blocks: positions from one (remote) atomic per owner present in the warp
+      const int own = c ? sink_owner(hs, e.z) : -1;
+      unsigned long long pos = 0;
+      for (int o = 0; o < hs.world; ++o) {
+        const unsigned int vote = __ballot_sync(0xffffffffu, own == o);
+        if (!vote) continue;
+        const int mine = own == o ? c : 0;
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 31) base = atomicAdd(reinterpret_cast<unsigned long long *>(hs.peer[o]), (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        if (own == o) pos = base + (unsigned long long)(incl - mine);
+      }
+      if (c) {
+        uint64_t *dst = reinterpret_cast<uint64_t *>(hs.peer[own] + kPeerHead);
+        const uint64_t gk = (uint64_t)(e.z - hs.first[own]) << hs.tbits;  // the owner numbers its guides from 0
+        while (vm) {
+          const int b = __ffs((int)vm) - 1;
+          vm &= vm - 1u;
+          const uint32_t idx = e.y + (uint32_t)b;
+          if (pos < hs.hit_cap) dst[pos] = gk | (canon ? canon[idx] : idx);
+          ++pos;
+        }
+      }
+      continue;
+    }
     if (c && hs.gcnt) atomicAdd(hs.gcnt + e.z, (unsigned int)c);
     int incl = c;
 #pragma unroll
@@ -366,7 +419,8 @@ struct BinParams {
   int nm[4];           // nm[d] = # last-four-bases masks a guide reached at bin distance d contributes
   uint32_t rcp[4];     // floor(2^32 / nm[d])
   int hA, k;
-  uint32_t n_bins;
+  uint32_t n_bins;     // scan bins [bin_base, n_bins): this rank's part of the index (all of it unless database-sharded)
+  uint32_t bin_base;
   const uint2 *sg;     // guides listed by the bin of their own key: x = probe | (last four key bases) << 24, y = guide index
   const int *cls_off;  // [n_bins + 1]
   HitSink hs;
@@ -411,7 +465,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
   uint32_t qcount = 0;
   for (;;) {
     __syncthreads();  // the previous bin is finished: its slice and tables may be overwritten
-    if (tid == 0) sh.bin = atomicAdd(bp.next_bin, 1u);
+    if (tid == 0) sh.bin = bp.bin_base + atomicAdd(bp.next_bin, 1u);
     __syncthreads();
     const uint32_t bin = sh.bin;
     if (bin >= bp.n_bins) break;
@@ -604,6 +658,7 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
     }
   }
   drain_queue<false>(bp.hs, q_off, qcount, lane, bp.canon, nullptr, -1);
+  if (bp.hs.world > 1) __threadfence_system();  // candidates pushed to peers are visible before this rank reaches the barrier
   for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
   if (lane == 0 && compares) atomicAdd(bp.n_compares, compares);
 }
@@ -617,6 +672,8 @@ struct PairParams {
   int rb_shift;        // k_pair_scan2: a "B-bin" = 2^rb_shift consecutive buckets
   uint32_t n_bbins;
   int seg_shift;       // k_pair_scan2: a round of 32 pairs is cut into 2^seg_shift work items (consecutive group ranges)
+  uint32_t bbin_base;  // k_pair_scan2 scans B-bins [bbin_base, n_bbins)
+  const unsigned int *n_pairs_dev;  // database-sharded: only this rank's buckets have pairs; their number is start[n_keys]
   long long n_pairs;
   int lo_d;
   HitSink hs;
@@ -637,22 +694,23 @@ __device__ __forceinline__ void b_pair(const uint64_t *guides, const uint32_t *m
 }
 
 __global__ void k_bpairs_hist(const uint64_t *__restrict__ guides, long long n_pairs, const uint32_t *__restrict__ masks, int n_seeds,
-                              int proto_shift, uint64_t proto_mask, int b_bits, int k, unsigned int *__restrict__ cnt) {
+                              int proto_shift, uint64_t proto_mask, int b_bits, int k, uint32_t b_lo, uint32_t b_hi, unsigned int *__restrict__ cnt) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n_pairs) return;
   uint32_t kk, pb, gid;
   b_pair(guides, masks, n_seeds, proto_shift, proto_mask, b_bits, k, idx, &kk, &pb, &gid);
-  atomicAdd(cnt + kk, 1u);
+  if (kk - b_lo < b_hi - b_lo) atomicAdd(cnt + kk, 1u);  // (buckets outside [b_lo, b_hi) belong to other ranks)
 }
 
 __global__ void k_bpairs_scatter(const uint64_t *__restrict__ guides, long long n_pairs, const uint32_t *__restrict__ masks, int n_seeds,
-                                 int proto_shift, uint64_t proto_mask, int b_bits, int k, const unsigned int *__restrict__ start,
-                                 unsigned int *__restrict__ cursor, const uint32_t *__restrict__ off, uint4 *__restrict__ recs) {
+                                 int proto_shift, uint64_t proto_mask, int b_bits, int k, uint32_t b_lo, uint32_t b_hi,
+                                 const unsigned int *__restrict__ start, unsigned int *__restrict__ cursor, const uint32_t *__restrict__ off,
+                                 uint4 *__restrict__ recs) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n_pairs) return;
   uint32_t kk, pb, gid;
   b_pair(guides, masks, n_seeds, proto_shift, proto_mask, b_bits, k, idx, &kk, &pb, &gid);
-  recs[start[kk] + atomicAdd(cursor + kk, 1u)] = make_uint4(off[kk], off[kk + 1], pb, gid);
+  if (kk - b_lo < b_hi - b_lo) recs[start[kk] + atomicAdd(cursor + kk, 1u)] = make_uint4(off[kk], off[kk + 1], pb, gid);
 }
 
 // 3 CTAs per SM (80 registers).  Tried on the GPU and dropped: a register double buffer of the next group (0.99 ms), two
@@ -676,7 +734,8 @@ __global__ void __launch_bounds__(kPairThreads, FF_PAIR_MIN_BLOCKS) k_pair_scan(
   const uint32_t q_off = (uint32_t)warp * kQCap * 16u;  // dynamic shared memory: one hit queue per warp
   uint32_t qcount = 0;
   unsigned long long compares = 0;
-  const long long n_items = (pp.n_pairs + 31) / 32;
+  const long long n_pairs = pp.n_pairs_dev ? (long long)*pp.n_pairs_dev : pp.n_pairs;
+  const long long n_items = (n_pairs + 31) / 32;
   for (;;) {  // items are claimed in bucket order: the whole grid walks the index front to back
     unsigned long long item = 0;
     if (lane == 0) item = atomicAdd(pp.next_item, 1ull);
@@ -685,7 +744,7 @@ __global__ void __launch_bounds__(kPairThreads, FF_PAIR_MIN_BLOCKS) k_pair_scan(
     const long long pi = (long long)item * 32 + lane;
     uint32_t lo = 0, hi = 0, gid = 0, probe = 0;
     int budget = -1;
-    if (pi < pp.n_pairs) {
+    if (pi < n_pairs) {
       const uint4 r = pp.recs[pi];
       lo = r.x; hi = r.y;
       probe = r.z & 0xFFFFFFu; budget = (int)(r.z >> 24); gid = r.w;
@@ -698,6 +757,7 @@ __global__ void __launch_bounds__(kPairThreads, FF_PAIR_MIN_BLOCKS) k_pair_scan(
                                            q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
   }
   drain_queue<true>(pp.hs, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
+  if (pp.hs.world > 1) __threadfence_system();
   for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
   if (lane == 0 && compares) atomicAdd(pp.n_compares, compares);
 }
@@ -753,7 +813,7 @@ __device__ __forceinline__ void p2_refill(const PairParams &pp, Pair2Shared &sh,
   const uint32_t mbar = smem_addr(&sh.full[b]);
   const uint32_t rb = (uint32_t)pp.rb_shift;
   for (;;) {
-    const uint32_t bin = (uint32_t)atomicAdd(pp.next_item, 1ull);
+    const uint32_t bin = pp.bbin_base + (uint32_t)atomicAdd(pp.next_item, 1ull);
     if (bin >= pp.n_bbins) {
       sh.meta[b].end = 1u;
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
@@ -865,6 +925,7 @@ __global__ void __launch_bounds__(kP2Threads, FF_P2_BLOCKS) k_pair_scan2(PairPar
     __syncwarp();
   }
   drain_queue<true>(pp.hs, q_off, qcount, lane, pp.canon, pp.other, pp.lo_d);
+  if (pp.hs.world > 1) __threadfence_system();
   for (int o = 16; o > 0; o >>= 1) compares += __shfl_down_sync(0xffffffffu, compares, o);
   if (lane == 0 && compares) atomicAdd(pp.n_compares, compares);
 }
@@ -894,6 +955,8 @@ struct BinScanPlan {
   PairParams pp;
   bool part_two;
   bool staged_b;   // part two through shared memory (k_pair_scan2) or lanes reading global memory (k_pair_scan)
+  bool shard;      // database-sharded: candidates go to `sink` (the owners' exchange blocks)
+  HitSink sink;
   int nb_a, nb_b;  // other bases of the two halves
   size_t smem_a;
 };
@@ -906,8 +969,15 @@ static bool bin_scan_supported(const Database &db, int hA, int64_t G) {
 }
 
 // Launch the set-up kernels (no host synchronisation) and fill the plan.
+// Database-sharded discover: this rank scans bins / buckets [rank / world, (rank + 1) / world) of both index halves for all
+// the guides; `sink` (world, first[], peer[], hit_cap, tbits) says where the candidates go.
+struct ScanShard {
+  int rank = 0, world = 1;
+  HitSink sink = {};
+};
+
 static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, unsigned long long *n_compares_b, BinScanPlan *pl,
-                            int *launches) {
+                            int *launches, const ScanShard *shard = nullptr) {
   Database &db = ctx->db;
   cudaStream_t st = ctx->stream;
   const int64_t G = sp.n_guides;
@@ -946,11 +1016,37 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
     k_bin_guide_scatter<<<blocks_for(G, 256), 256, 0, st>>>(sp.guides, G, sp.proto_shift, sp.proto_mask, sp.b_bits, cls_off, cls_cur, sg);
     *launches += 3;
   }
+  // B-bins of k_pair_scan2: as many buckets as fit the staging buffer on average, but enough bins to balance the grid
+  PairParams &pp = pl->pp;
+  {
+    int kb_bits = 2 * db.B.key_bases;
+    const double groups_per_bucket = (double)db.n_targets / (double)n_keys_b / 32.0;
+    int rbs = 0;
+    auto fits = [&](int r) {  // mean run of 2^r buckets + three standard deviations (Poisson bucket sizes) within the buffer
+      const double entries = groups_per_bucket * 32.0 * (double)(1u << r);
+      return entries / 32.0 + 1.0 + 3.0 * std::sqrt(entries) / 32.0 <= (double)kP2Groups;
+    };
+    while (rbs + 1 <= kb_bits && fits(rbs + 1)) ++rbs;
+    rbs = std::min(rbs, std::max(0, kb_bits - 11));
+    pp.rb_shift = rbs; pp.n_bbins = n_keys_b >> rbs; pp.bbin_base = 0;
+    const double rounds = (double)n_pairs * (double)(1u << rbs) / (double)n_keys_b / 32.0;
+    int ss = 0;
+    while (ss < 3 && rounds * (double)(1 << ss) < 0.6 * kP2Warps && groups_per_bucket / (double)(2 << ss) >= 4.0) ++ss;
+    if (ctx->opt.pair_segs > 0) { ss = 0; while ((1 << (ss + 1)) <= ctx->opt.pair_segs) ++ss; }
+    pp.seg_shift = ss;
+  }
+  uint32_t bin_lo = 0, bin_hi = n_bins, b_lo = 0, b_hi = n_keys_b;
+  if (shard && shard->world > 1) {
+    bin_lo = (uint32_t)((uint64_t)n_bins * shard->rank / shard->world); bin_hi = (uint32_t)((uint64_t)n_bins * (shard->rank + 1) / shard->world);
+    const uint32_t bb_lo = (uint32_t)((uint64_t)pp.n_bbins * shard->rank / shard->world), bb_hi = (uint32_t)((uint64_t)pp.n_bbins * (shard->rank + 1) / shard->world);
+    pp.bbin_base = bb_lo; pp.n_bbins = bb_hi;
+    b_lo = bb_lo << pp.rb_shift; b_hi = bb_hi << pp.rb_shift;
+  }
   if (n_pairs > 0) {
-    k_bpairs_hist<<<blocks_for(n_pairs, 256), 256, 0, st>>>(sp.guides, n_pairs, db.B.d_masks, nB, sp.proto_shift, sp.proto_mask, sp.b_bits, sp.k, b_cnt);
+    k_bpairs_hist<<<blocks_for(n_pairs, 256), 256, 0, st>>>(sp.guides, n_pairs, db.B.d_masks, nB, sp.proto_shift, sp.proto_mask, sp.b_bits, sp.k, b_lo, b_hi, b_cnt);
     FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp2, b_cnt, b_start, (int)(n_keys_b + 1), st));
     k_bpairs_scatter<<<blocks_for(n_pairs, 256), 256, 0, st>>>(sp.guides, n_pairs, db.B.d_masks, nB, sp.proto_shift, sp.proto_mask, sp.b_bits, sp.k,
-                                                               b_start, b_cur, db.B.d_off, recs);
+                                                               b_lo, b_hi, b_start, b_cur, db.B.d_off, recs);
     *launches += 3;
   }
   FF_CUDA(cudaGetLastError());
@@ -963,32 +1059,17 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
     bp.nm[d] = d <= hA ? db.A.cum_lo[std::min(hA - d, 4)] : 1;
     bp.rcp[d] = bp.nm[d] > 1 ? (uint32_t)(0x100000000ull / (uint64_t)bp.nm[d]) : 0xFFFFFFFFu;
   }
-  bp.hA = hA; bp.k = sp.k; bp.n_bins = n_bins; bp.sg = sg; bp.cls_off = cls_off;
+  bp.hA = hA; bp.k = sp.k; bp.n_bins = bin_hi; bp.bin_base = bin_lo; bp.sg = sg; bp.cls_off = cls_off;
   bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits, nullptr};
+  pl->shard = shard && shard->world > 1;
+  if (pl->shard) pl->sink = shard->sink;
   bp.n_compares = sp.n_compares;
   bp.next_bin = (unsigned int *)(w + o_ctr);
-  PairParams &pp = pl->pp;
   pp.planes = db.B.d_planes; pp.off = db.B.d_off; pp.other = db.B.d_other; pp.canon = db.B.d_canon; pp.recs = recs;
   pp.n_pairs = n_pairs; pp.lo_d = hA; pp.hs = bp.hs; pp.n_compares = n_compares_b;
   pp.next_item = (unsigned long long *)(w + o_ctr + 64);
   pp.start = b_start;
-  {  // B-bins of k_pair_scan2: as many buckets as fit the staging buffer on average, but enough bins to balance the grid
-    int kb_bits = 2 * db.B.key_bases;
-    const double groups_per_bucket = (double)db.n_targets / (double)n_keys_b / 32.0;
-    int rbs = 0;
-    auto fits = [&](int r) {  // mean run of 2^r buckets + three standard deviations (Poisson bucket sizes) within the buffer
-      const double entries = groups_per_bucket * 32.0 * (double)(1u << r);
-      return entries / 32.0 + 1.0 + 3.0 * std::sqrt(entries) / 32.0 <= (double)kP2Groups;
-    };
-    while (rbs + 1 <= kb_bits && fits(rbs + 1)) ++rbs;
-    rbs = std::min(rbs, std::max(0, kb_bits - 11));
-    pp.rb_shift = rbs; pp.n_bbins = n_keys_b >> rbs;
-    const double rounds = (double)n_pairs * (double)(1u << rbs) / (double)n_keys_b / 32.0;
-    int ss = 0;
-    while (ss < 3 && rounds * (double)(1 << ss) < 0.6 * kP2Warps && groups_per_bucket / (double)(2 << ss) >= 4.0) ++ss;
-    if (ctx->opt.pair_segs > 0) { ss = 0; while ((1 << (ss + 1)) <= ctx->opt.pair_segs) ++ss; }
-    pp.seg_shift = ss;
-  }
+  pp.n_pairs_dev = pl->shard ? b_start + n_keys_b : nullptr;
   // the ring stages the WHOLE index once per call; lanes reading global memory touch only the buckets that have pairs:
   // measured on B200 (3 x 10^8 targets) the two meet at ~11 pairs per bucket (100 000 guides); the ring wins beyond
   pl->staged_b = ctx->opt.pair_kernel == 2 || (ctx->opt.pair_kernel == 0 && (double)n_pairs >= 12.0 * (double)n_keys_b);
@@ -1002,6 +1083,7 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
 static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, unsigned int *gcnt, int *launches) {
   cudaStream_t st = ctx->stream;
   pl->bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits, gcnt};
+  if (pl->shard) { pl->bp.hs = pl->sink; pl->bp.hs.tbits = sp.tbits; pl->bp.hs.gcnt = nullptr; }
   pl->pp.hs = pl->bp.hs;
   FF_CUDA(cudaMemsetAsync(pl->bp.next_bin, 0, 128, st));
   static bool attr_set[64] = {false};

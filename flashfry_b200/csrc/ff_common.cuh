@@ -123,6 +123,20 @@ struct Options {
   int pair_segs = 0;       // > 0: work items per round of 32 pairs in k_pair_scan2 (1, 2, 4, 8); 0 = by batch size
 };
 
+// Database-sharded discover (ff_shard.inl): this rank's exchange block and the mapped blocks of its peers.
+constexpr int kMaxPeers = 8;
+constexpr size_t kPeerHeadBytes = 256;  // PeerCtr at the head of an exchange block
+struct PeerLink {
+  bool ready = false;
+  int rank = 0, world = 1;
+  DevBuf block;                         // own block: PeerCtr (256 B) | candidate keys u64[hit_cap] | per-guide totals i32[g_cap]
+  size_t hit_cap = 0;
+  int64_t g_cap = 0;
+  uint8_t *base[kMaxPeers] = {nullptr};  // every rank's block (base[rank] = own); peers mapped by CUDA IPC or peer access
+  bool ipc_opened[kMaxPeers] = {false};
+  unsigned int epoch = 0;               // barriers passed (all ranks call them in the same sequence)
+};
+
 }  // namespace ff
 
 struct ff_ctx {
@@ -157,6 +171,7 @@ struct ff_ctx {
   cudaEvent_t slot_copied[2] = {nullptr, nullptr};  // D2H of the slot's previous contents has finished
   size_t hit_cap = 0;
 
+  ff::PeerLink peer;
   cudaEvent_t ev[8] = {nullptr};
   ff_timings last = {};
   std::vector<ff::HostBuf *> host_pool;

@@ -708,6 +708,77 @@ struct U32ToI64 {
   __host__ __device__ int64_t operator()(unsigned int v) const { return (int64_t)v; }
 };
 
+// The scan's view of a call: both index halves, the pass plan for this k, the key layout.
+static void fill_scan_params(ff_ctx *ctx, const uint64_t *d_guides, int64_t G, int max_mm, ScanParams *spp, int *hA_out, int *nA_out, int *nB_out) {
+  Database &db = ctx->db;
+  ScanParams &sp = *spp;
+  const int k_eff = std::min(max_mm, db.proto_bases);  // more mismatches than compared bases changes nothing
+  int hA = 0, nA = 1, nB = 0;
+  plan_passes(db, k_eff, &hA, &nA, &nB);
+  sp.guides = d_guides; sp.n_guides = G;
+  sp.A.off = db.A.d_off; sp.A.other = db.A.d_other; sp.A.canon = db.A.d_canon; sp.A.masks = db.A.d_masks;
+  sp.A.n_seeds = nA; sp.A.seeds_per_item = 32; sp.A.items = (nA + 31) / 32;
+  sp.B.off = db.B.d_off; sp.B.other = db.B.d_other; sp.B.canon = db.B.d_canon; sp.B.masks = db.B.d_masks;
+  sp.B.n_seeds = nB;
+  {  // part-two buckets are 4^(a-b) times longer: hand them out in smaller batches
+    const double bucket_b = (double)db.n_targets / (double)(1ull << (2 * db.B.key_bases));
+    int spi = bucket_b > 2048 ? 1 : bucket_b > 512 ? 4 : bucket_b > 128 ? 8 : 32;
+    if (ctx->opt.b_spi > 0) spi = ctx->opt.b_spi;
+    sp.B.seeds_per_item = spi; sp.B.items = (nB + spi - 1) / spi;
+  }
+  sp.items_per_guide = sp.A.items + sp.B.items;
+  sp.proto_shift = db.proto_shift; sp.b_bits = 2 * db.B.key_bases; sp.proto_mask = (1ull << (2 * db.proto_bases)) - 1ull;
+  sp.k = k_eff; sp.hA = hA;
+  int tbits = 1;
+  while ((1ull << tbits) < db.n_targets + 1) tbits++;
+  sp.tbits = tbits;
+  sp.hits = nullptr; sp.hit_count = nullptr; sp.hit_cap = 0; sp.n_compares = nullptr;
+  *hA_out = hA; *nA_out = nA; *nB_out = nB;
+}
+
+// The per-guide ordering pipeline (section 3c of DESIGN.md), all on the stream, no host round trip: candidates
+// `hits[0 .. min(d_stt->n_cand, cap))` (guide << tbits | database index) -> CSR rows in the output slot.  `cnt` holds the
+// per-guide candidate counts (need_hist: take them here), `cursor` is zeroed scratch of the same size + the long-segment list.
+static int order_grouped(ff_ctx *ctx, ff_ctx::OutSlot &os, const uint64_t *hits, PlainStatus *d_stt, size_t cap, int tbits, unsigned int *cnt,
+                         unsigned int *cursor, bool need_hist, const uint64_t *d_guides, int64_t G, int max_ot, int *launches_out) {
+  Database &db = ctx->db;
+  cudaStream_t st = ctx->stream;
+  const int64_t Gp = G > 0 ? G : 1;
+  size_t tmp_bytes = 0;
+  int launches = 0;
+  const bool bin_major = !need_hist;
+  {
+      FF_TRY(ctx->idx32.reserve((cap + 1) * 4));
+      FF_TRY(ctx->st_targets.reserve((cap + 1) * 8));
+      FF_TRY(ctx->st_mm.reserve(cap + 1));
+      uint32_t *long_list = reinterpret_cast<uint32_t *>(cursor + Gp);
+      const int sgrid = ctx->sm_count * 16;
+      if (!bin_major) k_guide_hist<<<sgrid, 256, 0, st>>>(hits, &d_stt->n_cand, cap, tbits, cnt);
+      cub::TransformInputIterator<int64_t, U32ToI64, unsigned int *> cnt64(cnt, U32ToI64());
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
+      FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
+      k_guide_scatter<<<sgrid, 256, 0, st>>>(hits, &d_stt->n_cand, cap, tbits, ctx->seg_start.as<int64_t>(), cursor, ctx->idx32.as<uint32_t>());
+      k_mark_long<<<blocks_for(G, 256), 256, 0, st>>>(ctx->seg_start.as<int64_t>(), G, long_list, d_stt);
+      k_sort_long<<<kLongCap, 512, kLongMax * 4, st>>>(ctx->idx32.as<uint32_t>(), ctx->seg_start.as<int64_t>(), long_list, d_stt);
+      FF_CUDA(cudaEventRecord(ctx->ev[3], st));
+      k_sort_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->idx32.as<uint32_t>(), ctx->seg_start.as<int64_t>(), G, db.d_targets, d_guides,
+                                                         db.pack.cmp_mask, max_ot, ctx->st_targets.as<uint64_t>(), ctx->st_mm.as<uint8_t>(),
+                                                         ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>(), d_stt, cap);
+      FF_CUDA(cudaMemsetAsync(ctx->n_keep.as<int64_t>() + G, 0, 8, st));
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
+      FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
+      FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
+      k_compact_rows<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), G, ctx->st_targets.as<uint64_t>(),
+                                                             ctx->st_mm.as<uint8_t>(), ctx->idx32.as<uint32_t>(), os.out_targets.as<uint64_t>(),
+                                                             os.out_mm.as<uint8_t>(), os.out_tidx.as<uint32_t>(), d_stt);
+      launches += 9;
+      FF_CUDA(cudaEventRecord(ctx->ev[4], st));
+    }
+  *launches_out += launches;
+  return FF_OK;
+}
+
 static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
                           bool want_positions, int slot, DeviceResult *res) {
   Database &db = ctx->db;
@@ -731,27 +802,10 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   FF_CUDA(cudaEventRecord(ctx->ev[0], st));
 
   // ---- plan the two passes for this k
-  const int k_eff = std::min(max_mm, db.proto_bases);  // more mismatches than compared bases changes nothing
   ScanParams sp;
   int hA = 0, nA = 1, nB = 0;
-  plan_passes(db, k_eff, &hA, &nA, &nB);
-  sp.guides = d_guides; sp.n_guides = G;
-  sp.A.off = db.A.d_off; sp.A.other = db.A.d_other; sp.A.canon = db.A.d_canon; sp.A.masks = db.A.d_masks;
-  sp.A.n_seeds = nA; sp.A.seeds_per_item = 32; sp.A.items = (nA + 31) / 32;
-  sp.B.off = db.B.d_off; sp.B.other = db.B.d_other; sp.B.canon = db.B.d_canon; sp.B.masks = db.B.d_masks;
-  sp.B.n_seeds = nB;
-  {  // part-two buckets are 4^(a-b) times longer: hand them out in smaller batches
-    const double bucket_b = (double)db.n_targets / (double)(1ull << (2 * db.B.key_bases));
-    int spi = bucket_b > 2048 ? 1 : bucket_b > 512 ? 4 : bucket_b > 128 ? 8 : 32;
-    if (ctx->opt.b_spi > 0) spi = ctx->opt.b_spi;
-    sp.B.seeds_per_item = spi; sp.B.items = (nB + spi - 1) / spi;
-  }
-  sp.items_per_guide = sp.A.items + sp.B.items;
-  sp.proto_shift = db.proto_shift; sp.b_bits = 2 * db.B.key_bases; sp.proto_mask = (1ull << (2 * db.proto_bases)) - 1ull;
-  sp.k = k_eff; sp.hA = hA;
-  int tbits = 1;
-  while ((1ull << tbits) < db.n_targets + 1) tbits++;
-  sp.tbits = tbits;
+  fill_scan_params(ctx, d_guides, G, max_mm, &sp, &hA, &nA, &nB);
+  const int k_eff = sp.k, tbits = sp.tbits;
 
   // ---- candidate buffer: expected candidates per random guide = N x P(a random P-mer is within k) (116 at k = 4 on a
   // human-sized index); start with 1.4x that (+ slack), never more than 2^28 keys up front -- the call is repeated with
@@ -824,34 +878,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
       scan_launches++;
     }
     FF_CUDA(cudaEventRecord(ctx->ev[2], st));
-    if (grouped) {
-      FF_TRY(ctx->idx32.reserve((cap + 1) * 4));
-      FF_TRY(ctx->st_targets.reserve((cap + 1) * 8));
-      FF_TRY(ctx->st_mm.reserve(cap + 1));
-      uint32_t *long_list = reinterpret_cast<uint32_t *>(cursor + Gp);
-      const int sgrid = ctx->sm_count * 16;
-      if (!bin_major) k_guide_hist<<<sgrid, 256, 0, st>>>(sp.hits, &d_stt->n_cand, cap, tbits, cnt);
-      cub::TransformInputIterator<int64_t, U32ToI64, unsigned int *> cnt64(cnt, U32ToI64());
-      FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
-      FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
-      FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
-      k_guide_scatter<<<sgrid, 256, 0, st>>>(sp.hits, &d_stt->n_cand, cap, tbits, ctx->seg_start.as<int64_t>(), cursor, ctx->idx32.as<uint32_t>());
-      k_mark_long<<<blocks_for(G, 256), 256, 0, st>>>(ctx->seg_start.as<int64_t>(), G, long_list, d_stt);
-      k_sort_long<<<kLongCap, 512, kLongMax * 4, st>>>(ctx->idx32.as<uint32_t>(), ctx->seg_start.as<int64_t>(), long_list, d_stt);
-      FF_CUDA(cudaEventRecord(ctx->ev[3], st));
-      k_sort_cut<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->idx32.as<uint32_t>(), ctx->seg_start.as<int64_t>(), G, db.d_targets, d_guides,
-                                                         db.pack.cmp_mask, max_ot, ctx->st_targets.as<uint64_t>(), ctx->st_mm.as<uint8_t>(),
-                                                         ctx->n_keep.as<int64_t>(), os.total_count.as<int32_t>(), os.overflowed.as<uint8_t>(), d_stt, cap);
-      FF_CUDA(cudaMemsetAsync(ctx->n_keep.as<int64_t>() + G, 0, 8, st));
-      FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
-      FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
-      FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, ctx->n_keep.as<int64_t>(), os.row_ptr.as<int64_t>(), G + 1, st));
-      k_compact_rows<<<blocks_for(G * 32, 256), 256, 0, st>>>(ctx->seg_start.as<int64_t>(), os.row_ptr.as<int64_t>(), G, ctx->st_targets.as<uint64_t>(),
-                                                             ctx->st_mm.as<uint8_t>(), ctx->idx32.as<uint32_t>(), os.out_targets.as<uint64_t>(),
-                                                             os.out_mm.as<uint8_t>(), os.out_tidx.as<uint32_t>(), d_stt);
-      launches += 9;
-      FF_CUDA(cudaEventRecord(ctx->ev[4], st));
-    }
+    if (grouped) FF_TRY(order_grouped(ctx, os, sp.hits, d_stt, cap, tbits, cnt, cursor, !bin_major, d_guides, G, max_ot, &launches));
     k_publish_status<<<1, 32, 0, st>>>(d_stt, nullptr, h_stt_dev, ++ctx->status_seq);
     FF_TRY(wait_status(ctx, st, ctx->status_seq));
     n_cand = (int64_t)h_stt->n_cand;
@@ -941,6 +968,7 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
   return FF_OK;
 }
 
+#include "ff_shard.inl"
 #include "ff_general.inl"
 
 }  // namespace ff

@@ -37,6 +37,9 @@ struct DeviceResult {
 int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mm, int max_ot,
                        bool want_positions, int bulge_flags, int slot, DeviceResult *res);
 
+// database-sharded discover (ff_shard.inl): all guides in, this rank's guides' rows out; ff_peer_attach must have run
+int discover_sharded(ff_ctx *ctx, const uint64_t *d_guides_all, int64_t n_guides_all, int max_mm, int max_ot, int slot, DeviceResult *res);
+
 // ff_score.cu : CFD + Hsu2013 over a CSR hit list resident in HBM.  Any output may be null.
 int score_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, const int64_t *d_row_ptr,
                     const uint64_t *d_targets, int64_t n_hits, uint32_t metrics, double *d_cfd_max,

@@ -6,7 +6,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <condition_variable>
+#include <cstring>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -100,6 +102,11 @@ struct ff_multi {
   std::vector<ff::Worker *> workers;
   std::vector<ff::DevBuf> send, all;  // per device: its shard's totals (padded), the gathered vector
   ff::HostBuf gathered;               // rank 0's copy of the gathered vector
+  // database-sharded mode (ff_shard.inl): option shard_mode = 1; exchange blocks are made and mapped on first use
+  int shard_mode = 0;
+  long long peer_hit_cap = 0;
+  int64_t peer_g_cap = 0;
+  bool peers_ready = false;
 };
 
 using namespace ff;
@@ -158,7 +165,10 @@ int ff_multi_create(ff_multi **out, const int *device_ids, int n_devices) {
       const int rc = ff_create(&m->ctx[r], device_ids[r]);
       if (rc != FF_OK) { ff_multi_destroy(m); return rc; }
     }
-    if (n_devices > 1) {
+    bool distinct = true;  // (the same device twice: two ranks on one GPU, for tests of the sharded mode; NCCL refuses that)
+    for (int a = 0; a < n_devices; ++a)
+      for (int b = a + 1; b < n_devices; ++b) distinct = distinct && device_ids[a] != device_ids[b];
+    if (n_devices > 1 && distinct) {
       std::lock_guard<std::mutex> lk(g_nccl_mu);
       if (!g_nccl.load()) { set_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "symbol missing"); ff_multi_destroy(m); return FF_EUNSUPPORTED; }
       m->comm.assign(n_devices, nullptr);
@@ -180,8 +190,33 @@ int ff_multi_size(const ff_multi *m) { return m ? m->n : 0; }
 ff_ctx *ff_multi_ctx(ff_multi *m, int rank) { return (m && rank >= 0 && rank < m->n) ? m->ctx[rank] : nullptr; }
 
 int ff_multi_set_option(ff_multi *m, const char *key, long long value) {
-  if (!m) { set_error("null argument"); return FF_EINVAL; }
+  if (!m || !key) { set_error("null argument"); return FF_EINVAL; }
+  if (strcmp(key, "shard_mode") == 0) {  // 0 = shard the guides (ncclAllGather of totals), 1 = shard the index work (NVLink peer memory)
+    if (value < 0 || value > 1) { set_error("option shard_mode: 0 or 1"); return FF_EINVAL; }
+    m->shard_mode = (int)value;
+    return FF_OK;
+  }
+  if (strcmp(key, "peer_hit_cap") == 0) {
+    if (value < 0 || value > (1ll << 31)) { set_error("option peer_hit_cap out of range"); return FF_EINVAL; }
+    m->peer_hit_cap = value; m->peers_ready = false;
+    return FF_OK;
+  }
   for (ff_ctx *c : m->ctx) FF_TRY(ff_set_option(c, key, value));
+  return FF_OK;
+}
+
+// database-sharded mode: make the exchange blocks and map them into every context (same process: peer access)
+static int multi_peers(ff_multi *m, int64_t n_guides) {
+  if (m->peers_ready && n_guides <= m->peer_g_cap) return FF_OK;
+  const int n = m->n;
+  const int64_t g_cap = std::max<int64_t>(n_guides, 1 << 20);
+  std::vector<void *> blocks(n, nullptr);
+  for (int r = 0; r < n; ++r) {
+    unsigned char handle[FF_PEER_HANDLE_BYTES];
+    FF_TRY(ff_peer_export(m->ctx[r], (uint64_t)m->peer_hit_cap, g_cap, handle, &blocks[r]));
+  }
+  FF_TRY(on_all(m, [=](int r) { return ff_peer_attach(m->ctx[r], r, n, nullptr, blocks.data()); }));
+  m->peer_g_cap = g_cap; m->peers_ready = true;
   return FF_OK;
 }
 
@@ -194,6 +229,8 @@ int ff_multi_synth_database(ff_multi *m, int enzyme_index, uint64_t n_targets, u
 // devices over NVLink with ncclBroadcast, and every device builds its own seed index.
 int ff_multi_load_database(ff_multi *m, const char *db_path, const char *header_path) {
   if (!m || !db_path) { set_error("null argument"); return FF_EINVAL; }
+  if (m->n > 1 && m->comm.empty())  // (two ranks on one device: no NCCL; every context reads the files itself)
+    return on_all(m, [=](int r) { return ff_load_database(m->ctx[r], db_path, header_path); });
   FF_TRY(ff_load_database(m->ctx[0], db_path, header_path));
   if (m->n == 1) return FF_OK;
   const Database &src = m->ctx[0]->db;
@@ -229,6 +266,22 @@ int ff_multi_discover(ff_multi *m, const uint64_t *guides, int64_t n_guides, int
   if (!m || !out || n_guides < 0 || (n_guides > 0 && !guides)) { set_error("bad argument"); return FF_EINVAL; }
   for (int r = 0; r < m->n; ++r) out[r] = nullptr;
   const int n = m->n;
+  if (m->shard_mode == 1 && n > 1 && !want_positions) {
+    // every rank scans 1/n of the index for all guides; candidates, barriers and the all-gather of the totals go through
+    // peer memory (ff_shard.inl).  A guide set the sharded ordering does not take falls through to the guide-sharded call.
+    FF_TRY(multi_peers(m, n_guides));
+    const int rc = on_all(m, [=](int r) { return ff_discover_sharded(m->ctx[r], guides, n_guides, max_mismatch, max_off_targets, &out[r]); });
+    if (rc == FF_OK) {
+      if (total_count_all && n_guides > 0) {
+        FF_CUDA(cudaSetDevice(m->ctx[0]->device));
+        FF_CUDA(cudaMemcpy(total_count_all, ff_peer_totals_device(m->ctx[0]), (size_t)n_guides * 4, cudaMemcpyDeviceToHost));
+      }
+      return FF_OK;
+    }
+    for (int r = 0; r < n; ++r) { if (out[r]) ff_hits_free(out[r]); out[r] = nullptr; }
+    if (rc != FF_EUNSUPPORTED) return rc;
+  }
+  if (n > 1 && m->comm.empty()) { set_error("guide-sharded discover needs NCCL, i.e. distinct devices"); return FF_EUNSUPPORTED; }
   const int64_t per = (n_guides + n - 1) / n > 0 ? (n_guides + n - 1) / n : 1;  // padded shard length of the all-gather
   int rc = on_all(m, [=](int r) -> int {
     ff_ctx *c = m->ctx[r];

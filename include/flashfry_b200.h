@@ -234,6 +234,32 @@ int ff_discover_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
 int ff_discover_bulge_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, int max_mismatch,
                              int max_off_targets, int bulge_flags, ff_device_result *out);
 
+/* ---- database-sharded discover over NVLink peer memory ------------------------------------------------------
+ * Strong scaling of ONE guide set over the GPUs of a box (reference/traverser/Traverser.scala:52-59 hands a traverser all
+ * guides and the whole database; the reference itself is single-process, OffTargetDiscovery.scala:117).  Every rank holds
+ * an index replica, scans 1/world of the INDEX for ALL guides, and the scan kernels push each candidate straight into the
+ * exchange block of the rank that owns the guide (ff_shard_range) -- P2P stores + remote atomics, barriers and the
+ * all-gather of the per-guide totals included: no NCCL on this path.  Rows are identical to ff_discover's.
+ *   1. every rank: ff_peer_export        -> its block exists; handle = CUDA IPC handle (other processes), *block_out = pointer
+ *   2. every rank: ff_peer_attach        with the handles of all ranks (one process per GPU) or their pointers (one process)
+ *   3. every rank, same arguments:        ff_discover_sharded[_device](all guides) -> rows of ITS guides
+ * A call that fails on one rank makes the others return FF_ECUDA after a 4 s barrier time-out instead of hanging. */
+#define FF_PEER_HANDLE_BYTES 64
+int ff_peer_export(ff_ctx *ctx, uint64_t hit_cap /* candidate keys per block; 0 = 2^24 */, int64_t guide_cap /* all guides; 0 = 2^20 */,
+                   void *handle_out /* FF_PEER_HANDLE_BYTES */, void **block_out /* may be NULL */);
+int ff_peer_attach(ff_ctx *ctx, int rank, int world, const void *handles /* world x FF_PEER_HANDLE_BYTES, or NULL */,
+                   void *const *blocks /* world device pointers of this process, or NULL */);
+int ff_peer_detach(ff_ctx *ctx);
+/* d_guides_all: ALL guides (identical on every rank), already in HBM.  out: rows of guides [first, first + count) of this
+ * rank (ff_shard_range(n_guides_all, world, rank)); d_total_count = this rank's slice. */
+int ff_discover_sharded_device(ff_ctx *ctx, const uint64_t *d_guides_all, int64_t n_guides_all, int max_mismatch,
+                               int max_off_targets, uint32_t metrics, ff_device_result *out);
+/* the same with host buffers: H2D of all guides, D2H of this rank's rows (ff_hits of its guides) */
+int ff_discover_sharded(ff_ctx *ctx, const uint64_t *guides_all, int64_t n_guides_all, int max_mismatch, int max_off_targets,
+                        ff_hits **out);
+/* after a sharded call: device pointer to CRISPRSiteOT.currentTotal of ALL guides (int32[n_guides_all]), on every rank */
+const int32_t *ff_peer_totals_device(ff_ctx *ctx);
+
 /* ---- several GPUs behind one host process ------------------------------------------------------------------
  * The reference is a single process (modules/OffTargetDiscovery.scala:117: "multithreaded (not supported currently)"); a
  * JVM host reaches every GPU of a box through one ff_multi: one ff_ctx and one persistent host thread per device, every
