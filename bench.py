@@ -214,6 +214,33 @@ def run_native(args):
     ctx.set_stream(stream.cuda_stream)
     d_guides = torch.from_numpy(guides.view(np.int64)).to(dev)
 
+    # N > 1, one guide set: shard the INDEX WORK instead of the guides (ff_shard.inl) -- every rank scans 1/N of the index
+    # for all guides and the scan kernels push the candidates to the guide's owner over NVLink peer memory.  The exchange
+    # blocks are mapped with CUDA IPC handles exchanged once through torch.distributed; any rank that cannot map them
+    # sends every rank back to guide sharding.
+    db_sharded, d_all, shard_note = False, None, None
+    if world > 1 and args.scaling == "strong" and wl in ("discover", "fused") and args.shard != "guides":
+        ok = 1
+        try:
+            hit_cap = max(1 << 24, int(2.0 * 130.0 * G_job / world))
+            handle = ctx.peer_export(hit_cap, max(G_job, 1 << 20))
+        except Exception as e:  # noqa: BLE001
+            ok, shard_note, handle = 0, "peer_export failed: %s" % e, b"\0" * 64
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        if ok:
+            try:
+                ctx.peer_attach(rank, world, handles)
+            except Exception as e:  # noqa: BLE001
+                ok, shard_note = 0, "peer_attach failed: %s" % e
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        db_sharded = bool(flag.item())
+        if db_sharded:
+            d_all = torch.from_numpy(all_guides.view(np.int64)).to(dev)
+        elif args.shard == "database":
+            raise SystemExit("--shard database: %s" % (shard_note or "a peer rank could not map the exchange blocks"))
+
     class _DevView:  # wrap a context-owned device pointer for torch without copying
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
@@ -221,6 +248,8 @@ def run_native(args):
     counts_weak = torch.empty(world * G, dtype=torch.int32, device=dev) if (world > 1 and args.scaling == "weak") else None
 
     def step():
+        if db_sharded:  # candidates, barriers and the all-gather of the totals all go through peer memory: no NCCL call
+            return ctx.discover_sharded_device(d_all.data_ptr(), G_job, k, args.max_ot, 3 if wl == "fused" else 0)
         if wl == "bulge":
             r = ctx.discover_bulge_device(d_guides.data_ptr(), G, k, args.max_ot, 3)
         else:
@@ -254,7 +283,7 @@ def run_native(args):
         r = step()
         tm = ctx.timings()
         tms.append((tm.scan_ms, tm.scan_part1_ms, tm.scan_part2_ms, tm.prep_ms, tm.order_ms, tm.cut_ms, tm.score_ms))
-        launches += tm.kernel_launches + (1 if world > 1 else 0)
+        launches += tm.kernel_launches + (1 if world > 1 and not db_sharded else 0)
     e1.record(stream)
     sync_all()
     ms = e0.elapsed_time(e1)
@@ -266,17 +295,39 @@ def run_native(args):
     value = G_job / (ms_per_step / 1e3)
     n_hits, cand = int(r.n_hits), int(r.n_candidate_hits)
     ent1, ent2, req_bytes, scan_launches = int(tm.entries_part1), int(tm.entries_part2), int(tm.scan_bytes_read), int(tm.scan_launches)
+    sharded_ok = None
+    if db_sharded:  # the sharded rows of this rank's guides against the single-GPU call on the same shard, all ranks
+        def _rows(res):
+            v = lambda ptr, n, ts: torch.as_tensor(_Dev(ptr, n, ts), device=dev).clone()  # noqa: E731
+            return (v(res.d_row_ptr, G + 1, "<i8"), v(res.d_targets, max(int(res.n_hits), 1), "<i8")[:int(res.n_hits)],
+                    v(res.d_mismatches, max(int(res.n_hits), 1), "|u1")[:int(res.n_hits)], v(res.d_total_count, max(G, 1), "<i4")[:G])
+
+        class _Dev:
+            def __init__(self, ptr, n, ts):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": ts, "data": (ptr, False), "version": 2}
+        a_rows = _rows(r)
+        tot_all = torch.as_tensor(_Dev(ctx.peer_totals_ptr(), G_job, "<i4"), device=dev).clone()
+        b_rows = _rows(ctx.discover_device(d_guides.data_ptr(), G, k, args.max_ot, 0))
+        same = all(x.shape == y.shape and torch.equal(x, y) for x, y in zip(a_rows, b_rows)) and torch.equal(tot_all[lo:hi], b_rows[3])
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_ok = bool(flag.item())
 
     # ---- e2e through the C ABI with HOST buffers (pinned guides in, hit lists out), same shard, same steps
     pinned = torch.from_numpy(guides.view(np.int64)).pin_memory()
     g_host = pinned.numpy().view(np.uint64)
     hp = C.POINTER(N.FFHits)()
     gp = g_host.ctypes.data_as(C.POINTER(C.c_uint64))
+    if db_sharded:
+        pinned_all = torch.from_numpy(all_guides.view(np.int64)).pin_memory()
+        gp_all = pinned_all.numpy().view(np.uint64).ctypes.data_as(C.POINTER(C.c_uint64))
     sc = [np.zeros(max(G, 1)) for _ in range(3)]
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
 
     def e2e_step():
-        if wl == "fused":
+        if db_sharded and wl == "discover":  # H2D of ALL guides on every rank, D2H of the rank's own rows
+            N.check(N.lib().ff_discover_sharded(ctx._h, gp_all, G_job, k, args.max_ot, C.byref(hp)))
+        elif wl == "fused":
             N.check(N.lib().ff_discover_score(ctx._h, gp, G, k, args.max_ot, 0, 3, C.byref(hp), dp(sc[0]), dp(sc[1]), dp(sc[2])))
         elif wl == "bulge":
             N.check(N.lib().ff_discover_bulge(ctx._h, gp, G, k, args.max_ot, 3, 0, C.byref(hp)))
@@ -309,7 +360,7 @@ def run_native(args):
         ctx.set_option("compact_hits", 0)
     clocks = sampler.stop(t_region0, sampler.mark()) if rank == 0 else None  # samples taken inside the two timed regions
     per_hit = 10 if wl == "bulge" else 9
-    e2e = {"value": G_job / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": 8 * G,
+    e2e = {"value": G_job / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": 8 * (G_job if db_sharded and wl == "discover" else G),
            "d2h_bytes_per_step": (G + 1) * 8 + nh * per_hit + G * 5 + (24 * G if wl == "fused" else 0), "ms_per_step": e2e_s * 1e3,
            "bytes_are": "per rank", "over_device_step": e2e_s * 1e3 / ms_per_step}
     if e2e_compact_s:
@@ -359,10 +410,14 @@ def run_native(args):
                "scaling": args.scaling, "vs_baseline": (value / 53.7) if wl == "discover" and k == 4 else None, "dtype": "u64", "data": "synthetic",
                "config": {"workload": "%s: %d synthetic NGG guides (+10%% planted) %s vs synthetic %d-target spCas9-NGG index, k<=%d%s, maxOT %d" % (
                               {"discover": "configs[2]", "fused": "configs[4] (discover + CFD + Hsu2013 fused)", "bulge": "configs[3] (1-bp bulge extension)"}[wl],
-                              G_job, "in total, guide-sharded over %d GPU(s)" % world if args.scaling == "strong" else "= %d per GPU" % G,
+                              G_job, ("in total, over %d GPU(s)" % world) if args.scaling == "strong" else "= %d per GPU" % G,
                               n_t, k, " + one 1-bp RNA/DNA bulge" if wl == "bulge" else "", args.max_ot),
                           "guides_total": G_job, "guides_per_gpu": G, "targets": n_t, "max_mismatch": k, "maximum_off_targets": args.max_ot,
-                          "parallelism": "guide-sharded x%d, one index replica per GPU, one NCCL all-gather of int32 totals per step" % world,
+                          "parallelism": ("database-sharded x%d: one index replica per GPU, every rank scans 1/%d of the index for ALL guides, the scan kernels push "
+                                          "candidates to the guide's owner over NVLink peer memory (P2P stores + remote atomics), barriers and the all-gather of "
+                                          "the totals through the same exchange blocks (no NCCL on the data path)" % (world, world)) if db_sharded else
+                                         "guide-sharded x%d, one index replica per GPU, one NCCL all-gather of int32 totals per step" % world,
+                          "sharded_rows_equal_single_gpu_rows": sharded_ok, "shard_fallback_reason": shard_note,
                           "l2": "index (%.1f GB) is larger than L2, re-streamed every step" % (info.device_bytes / 1e9),
                           "seed_split": "first %d | last %d protospacer bases" % (int(info.seed_split_a), 20 - int(info.seed_split_a)),
                           "db_build_s": db_s},
@@ -389,6 +444,8 @@ def run_single_process(args):
     if torch.cuda.device_count() < n:
         raise SystemExit("--single-process --gpus %d needs %d visible GPUs" % (n, n))
     mc = ff.MultiContext(list(range(n)))
+    if n > 1 and args.shard != "guides":
+        mc.set_option("shard_mode", 1)  # shard the index work; candidates reach the guide's owner over NVLink peer memory
     t0 = time.perf_counter()
     mc.synth_database(ENZYME, args.targets, SEED_DB)
     db_s = time.perf_counter() - t0
@@ -417,7 +474,8 @@ def run_single_process(args):
            "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": G / s / 53.7, "dtype": "u64", "data": "synthetic",
            "config": {"workload": "configs[2]: %d guides in total through ff_multi_discover (ONE host process, one thread per GPU, host buffers in "
                                   "and out, one ncclAllGather of the totals inside the library) vs %d targets, k<=%d, maxOT %d" % (G, n_t, args.k, args.max_ot),
-                      "launcher": "single process (ff_multi)", "targets": n_t, "db_build_s_all_devices": db_s},
+                      "launcher": "single process (ff_multi)", "targets": n_t, "db_build_s_all_devices": db_s,
+                      "shard_mode": "database (NVLink peer memory)" if (n > 1 and args.shard != "guides") else "guides (ncclAllGather of totals)"},
            "e2e": {"value": G / s, "unit": "guides/s", "h2d_bytes_per_step": 8 * G, "d2h_bytes_per_step": (G + n) * 8 + hits * 9 + G * 5,
                    "ms_per_step": s * 1e3, "bytes_are": "whole job"},
            "slowest_rank_device_ms_last_step": dev_ms, "hits_per_step": hits, "totals_sum": int(totals.sum()), "clocks": clocks,
@@ -703,6 +761,8 @@ def main():
     ap.add_argument("--workload", default="discover", choices=["discover", "fused", "bulge"],
                     help="discover = configs[2]; fused = configs[4] (discover + CFD + Hsu2013 on the GPU, 50 000 guides); bulge = configs[3]")
     ap.add_argument("--no-extras", action="store_true", help="only the headline line (no side measurements)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "guides", "database"],
+                    help="N > 1, strong scaling: shard the guides (NCCL all-gather of totals) or the index work (NVLink peer memory); auto = database")
     ap.add_argument("--single-process", action="store_true",
                     help="all --gpus behind ONE process through the C ABI's ff_multi (not the torchrun contract): end-to-end line only")
     ap.add_argument("--no-ladder", action="store_true")

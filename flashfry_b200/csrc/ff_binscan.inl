@@ -119,29 +119,33 @@ template <int NB> struct LaneProbe {
 
 // Where candidates go.  world == 1: this context's buffer.  world > 1 (database-sharded discover, section 7 of DESIGN.md):
 // every rank scans ITS part of the index for ALL guides and pushes each candidate straight into the exchange block of
-// the rank that OWNS the guide -- peer memory over NVLink (P2P stores, one remote atomic per warp drain and owner) --,
-// so the hand-over of the candidates is fused into the scan and the owner finds its guides' candidates in its own HBM.
+// the rank that OWNS the guide -- peer memory over NVLink.  The owner's block has one REGION per source rank, so a
+// position needs no remote round trip: the source counts what it sent to every owner with LOCAL atomics (`sent`), the
+// keys travel as fire-and-forget P2P stores, and one remote store per owner at the end of the scan tells it how many keys
+// its region holds (k_peer_counts).  The hand-over of the candidates is fused into the scan.
 struct HitSink {
   uint64_t *hits;
   unsigned long long *hit_count;
-  unsigned long long hit_cap;
+  unsigned long long hit_cap;         // world > 1: keys per REGION (block capacity / world)
   int tbits;
   unsigned int *gcnt;  // per-guide candidate counts for the ordering that follows (nullptr: not wanted)
-  int world;                         // ranks of the exchange (1: no exchange)
+  int world, rank;                    // ranks of the exchange (world <= 1: no exchange)
+  float owner_scale;                  // world / all guides
   unsigned int first[kMaxPeers + 1];  // first guide owned by every rank (ff_shard_range), first[world] = all guides
-  uint8_t *peer[kMaxPeers];          // exchange block of every rank: PeerCtr, totals, candidate keys
+  uint8_t *peer[kMaxPeers];          // exchange block of every rank: PeerCtr, candidate keys (world regions), totals
 };
 
-struct PeerCtr {  // head of an exchange block (256 bytes)
-  unsigned long long hit_count;  // candidates pushed into this block in the current step
-  unsigned int arrive;           // barrier arrivals, monotonically increasing
-  unsigned int error;            // a barrier timed out
+struct PeerCtr {  // head of an exchange block (kPeerHeadBytes)
+  unsigned int arrive;               // barrier arrivals, monotonically increasing (remote atomics)
+  unsigned int pad;
+  unsigned int sent[kMaxPeers];      // LOCAL: keys this rank has pushed to every owner in the current step
+  unsigned int recv[kMaxPeers];      // written by the sources: keys in each region of this block
 };
 constexpr size_t kPeerHead = kPeerHeadBytes;
 
 __device__ __forceinline__ int sink_owner(const HitSink &hs, uint32_t g) {
-  int o = (int)(((unsigned long long)g * (unsigned)hs.world) / hs.first[hs.world]);
-  while (g >= hs.first[o + 1]) ++o;  // (floors: the estimate is off by one at most, more only with fewer guides than ranks)
+  int o = min((int)((float)g * hs.owner_scale), hs.world - 1);  // first[r] = n r / world: the estimate is off by one at most,
+  while (g >= hs.first[o + 1]) ++o;                             // more only with fewer guides than ranks
   while (g < hs.first[o]) --o;
   return o;
 }
@@ -164,27 +168,30 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
     if (i0 + lane < n) e = q[i0 + lane];
     uint32_t vm = e.x;  // (part two: the compare itself has dropped the entries with d1 <= hA)
     const int c = __popc(vm);
-    if (hs.world > 1) {  // push to the owners' exchange blocks: positions from one (remote) atomic per owner present in the warp
+    if (hs.world > 1) {  // push to the owners' exchange blocks (region hs.rank of each): no remote round trip
       const int own = c ? sink_owner(hs, e.z) : -1;
-      unsigned long long pos = 0;
+      unsigned int my_total = 0;  // lane o: what this warp sends to owner o
       for (int o = 0; o < hs.world; ++o) {
-        const unsigned int vote = __ballot_sync(0xffffffffu, own == o);
-        if (!vote) continue;
-        const int mine = own == o ? c : 0;
-        int incl = mine;
+        const unsigned int t = __reduce_add_sync(0xffffffffu, own == o ? (unsigned int)c : 0u);
+        if (lane == o) my_total = t;
+      }
+      unsigned int base_l = 0;
+      if (my_total) base_l = atomicAdd(&reinterpret_cast<PeerCtr *>(hs.peer[hs.rank])->sent[lane], my_total);  // (local memory)
+      unsigned int pref = 0;
+      for (int o = 0; o < hs.world; ++o) {
+        if (!__ballot_sync(0xffffffffu, own == o)) continue;
+        const unsigned int mine = own == o ? (unsigned int)c : 0u;
+        unsigned int incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, d);
+          const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += v;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned long long base = 0;
-        if (lane == 31) base = atomicAdd(reinterpret_cast<unsigned long long *>(hs.peer[o]), (unsigned long long)total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        if (own == o) pos = base + (unsigned long long)(incl - mine);
+        if (own == o) pref = incl - mine;
       }
+      unsigned long long pos = (unsigned long long)__shfl_sync(0xffffffffu, base_l, own >= 0 ? own : 0) + pref;
       if (c) {
-        uint64_t *dst = reinterpret_cast<uint64_t *>(hs.peer[own] + kPeerHead);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(hs.peer[own] + kPeerHead) + (size_t)hs.rank * hs.hit_cap;
         const uint64_t gk = (uint64_t)(e.z - hs.first[own]) << hs.tbits;  // the owner numbers its guides from 0
         while (vm) {
           const int b = __ffs((int)vm) - 1;
@@ -977,7 +984,7 @@ struct ScanShard {
 };
 
 static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, unsigned long long *n_compares_b, BinScanPlan *pl,
-                            int *launches, const ScanShard *shard = nullptr) {
+                            int *launches, const ScanShard *shard = nullptr, bool reserve_only = false) {
   Database &db = ctx->db;
   cudaStream_t st = ctx->stream;
   const int64_t G = sp.n_guides;
@@ -1010,6 +1017,7 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
   FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cls_cnt, cls_off, (int)(n_bins + 1), st));
   FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, b_cnt, b_start, (int)(n_keys_b + 1), st));
   FF_TRY(ctx->cub_tmp.reserve(std::max(tmp, tmp2)));
+  if (reserve_only) return FF_OK;  // (the workspaces exist now; nothing was launched)
   if (G > 0) {
     k_bin_guide_hist<<<blocks_for(G, 256), 256, 0, st>>>(sp.guides, G, sp.proto_shift, sp.proto_mask, sp.b_bits, cls_cnt);
     FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, cls_cnt, cls_off, (int)(n_bins + 1), st));

@@ -129,7 +129,7 @@ constexpr size_t kPeerHeadBytes = 256;  // PeerCtr at the head of an exchange bl
 struct PeerLink {
   bool ready = false;
   int rank = 0, world = 1;
-  DevBuf block;                         // own block: PeerCtr (256 B) | candidate keys u64[hit_cap] | per-guide totals i32[g_cap]
+  DevBuf block;                         // own block: PeerCtr (256 B) | candidate keys u64[hit_cap] in `world` regions | per-guide totals i32[g_cap]
   size_t hit_cap = 0;
   int64_t g_cap = 0;
   uint8_t *base[kMaxPeers] = {nullptr};  // every rank's block (base[rank] = own); peers mapped by CUDA IPC or peer access

@@ -39,6 +39,8 @@ int discover_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, 
 
 // database-sharded discover (ff_shard.inl): all guides in, this rank's guides' rows out; ff_peer_attach must have run
 int discover_sharded(ff_ctx *ctx, const uint64_t *d_guides_all, int64_t n_guides_all, int max_mm, int max_ot, int slot, DeviceResult *res);
+// all workspaces of such a call; warm: every kernel of the path loaded too (ranks sharing one device: see ff_shard.inl)
+int discover_sharded_reserve(ff_ctx *ctx, int64_t n_guides_all, int max_mm, bool warm);
 
 // ff_score.cu : CFD + Hsu2013 over a CSR hit list resident in HBM.  Any output may be null.
 int score_on_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guides, const int64_t *d_row_ptr,

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <string>
 #include <thread>
 
 #include "ff_common.cuh"
@@ -106,7 +107,7 @@ struct ff_multi {
   int shard_mode = 0;
   long long peer_hit_cap = 0;
   int64_t peer_g_cap = 0;
-  bool peers_ready = false;
+  bool peers_ready = false, warmed = false;
 };
 
 using namespace ff;
@@ -117,7 +118,8 @@ static int on_all(ff_multi *m, const std::function<int(int)> &fn) {
   int rc = FF_OK;
   for (int r = 0; r < m->n; ++r) {
     const int x = m->workers[r]->wait();
-    if (x != FF_OK && rc == FF_OK) { rc = x; set_error("device %d: %s", m->devices[r], m->workers[r]->err); }
+    if (x != FF_OK && rc == FF_OK) { rc = x; set_error("rank %d (device %d): %s", r, m->devices[r], m->workers[r]->err); }
+    else if (x != FF_OK) { std::string both = std::string(ff_last_error()) + " | rank " + std::to_string(r) + ": " + m->workers[r]->err; set_error("%s", both.c_str()); }
   }
   return rc;
 }
@@ -270,6 +272,23 @@ int ff_multi_discover(ff_multi *m, const uint64_t *guides, int64_t n_guides, int
     // every rank scans 1/n of the index for all guides; candidates, barriers and the all-gather of the totals go through
     // peer memory (ff_shard.inl).  A guide set the sharded ordering does not take falls through to the guide-sharded call.
     FF_TRY(multi_peers(m, n_guides));
+    // workspaces first, on every rank (ranks that share a device must not allocate while another one waits in a barrier)
+    const bool shared_device = m->comm.empty();  // (ranks on ONE device: tests.  Then one rank at a time, kernels pre-loaded)
+    auto reserve = [=](int r) -> int {
+      FF_CUDA(cudaSetDevice(m->ctx[r]->device));
+      FF_TRY(m->ctx[r]->scratch_guides.reserve((n_guides > 0 ? n_guides : 1) * 8));
+      return discover_sharded_reserve(m->ctx[r], n_guides, max_mismatch, shared_device && !m->warmed);
+    };
+    if (shared_device) {
+      for (int r = 0; r < n; ++r) {
+        m->workers[r]->submit([=]() { return reserve(r); });
+        const int x = m->workers[r]->wait();
+        if (x != FF_OK) { set_error("rank %d: %s", r, m->workers[r]->err); return x; }
+      }
+      m->warmed = true;
+    } else {
+      FF_TRY(on_all(m, reserve));
+    }
     const int rc = on_all(m, [=](int r) { return ff_discover_sharded(m->ctx[r], guides, n_guides, max_mismatch, max_off_targets, &out[r]); });
     if (rc == FF_OK) {
       if (total_count_all && n_guides > 0) {
