@@ -136,6 +136,7 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   if (c->opt.subbatch_c1 > 0 && c->opt.subbatch_c1 < c->opt.subbatch_c2 && c->opt.subbatch_c2 < 100) {
     kCut[3][1] = c->opt.subbatch_c1; kCut[3][2] = c->opt.subbatch_c2;
   }
+  if (c->opt.subbatch_two > 0 && c->opt.subbatch_two < 100) kCut[2][1] = c->opt.subbatch_two;
 
   const auto t_start = std::chrono::steady_clock::now();
   auto trace = [&](const char *what, int b) {
@@ -356,6 +357,8 @@ int ff_set_option(ff_ctx *c, const char *key, long long value) {
         {"trace", &c->opt.trace, 0, 1},
         {"split_a", &c->opt.split_a, 0, 12},              {"compact_hits", &c->opt.compact_hits, 0, 1},
         {"pair_kernel", &c->opt.pair_kernel, 0, 2},       {"pair_segs", &c->opt.pair_segs, 0, 8},
+        {"subbatch_two", &c->opt.subbatch_two, 1, 99},
+        {"peer_local_only", &c->opt.peer_local_only, 0, 1}, {"debug_bin_div", &c->opt.debug_bin_div, 0, 64},
     };
     for (auto &t : table)
       if (strcmp(key, t.name) == 0) {

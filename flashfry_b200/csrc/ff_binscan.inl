@@ -1044,6 +1044,7 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
     pp.seg_shift = ss;
   }
   uint32_t bin_lo = 0, bin_hi = n_bins, b_lo = 0, b_hi = n_keys_b;
+  if (ctx->opt.debug_bin_div > 1) bin_hi = n_bins / (uint32_t)ctx->opt.debug_bin_div;  // (diagnostic: part one over a fraction of the bins; rows incomplete)
   if (shard && shard->world > 1) {
     bin_lo = (uint32_t)((uint64_t)n_bins * shard->rank / shard->world); bin_hi = (uint32_t)((uint64_t)n_bins * (shard->rank + 1) / shard->world);
     const uint32_t bb_lo = (uint32_t)((uint64_t)pp.n_bbins * shard->rank / shard->world), bb_hi = (uint32_t)((uint64_t)pp.n_bbins * (shard->rank + 1) / shard->world);

@@ -113,6 +113,7 @@ struct Options {
   int subbatch_min = 45000;           // ff_discover cuts a guide set into up to three sub-batches of at least this size
                                       // (measured on B200: two sub-batches 60 / 40 % beat one and three for 100 000 guides)
   int subbatch_c1 = 65, subbatch_c2 = 90;  // cumulative % of the first two of three sub-batches
+  int subbatch_two = 60;                   // % of the guides in the first of two sub-batches
   int group_sort = 1;      // 0 = always order hits with the radix sort
   int b_spi = 0;           // > 0: seeds per work item of the part-two pass of k_seed_scan / k_pattern_scan
   int split_a = 0;         // > 0: bases in the part-one key of the next database build
@@ -120,6 +121,8 @@ struct Options {
   int compact_hits = 0;    // ff_discover: 1 = ship database indices instead of target longs (ff_hits.target_index)
   int pair_kernel = 0;     // part two of the bin-major scan: 0 = by pairs per bucket, 1 = k_pair_scan (lanes read global memory),
                            // 2 = k_pair_scan2 (B-bins staged in shared memory by a two-buffer TMA ring)
+  int debug_bin_div = 0;   // diagnostic: > 1 = part one of the bin-major scan covers only the first 1/n of the bins (timing; rows incomplete)
+  int peer_local_only = 0; // diagnostic: the sharded scan keeps every candidate in its own block (timing without NVLink stores; rows are wrong)
   int pair_segs = 0;       // > 0: work items per round of 32 pairs in k_pair_scan2 (1, 2, 4, 8); 0 = by batch size
 };
 

@@ -100,7 +100,7 @@ static int discover_sharded_impl(ff_ctx *ctx, const uint64_t *d_guides_all, int6
   shard.sink.world = world; shard.sink.rank = rank; shard.sink.hit_cap = region_cap;
   shard.sink.owner_scale = n_all > 0 ? (float)world / (float)n_all : 0.f;
   for (int r = 0; r <= world; ++r) shard.sink.first[r] = (unsigned int)(n_all * r / world);  // ff_shard_range
-  for (int r = 0; r < world; ++r) shard.sink.peer[r] = pl.base[r];
+  for (int r = 0; r < world; ++r) shard.sink.peer[r] = ctx->opt.peer_local_only ? pl.base[rank] : pl.base[r];  // (diagnostic: no NVLink stores, wrong rows)
   const int64_t first = shard.sink.first[rank], G = (int64_t)shard.sink.first[rank + 1] - first, Gp = G > 0 ? G : 1;
   const uint64_t *d_guides = d_guides_all + first;
 
@@ -186,7 +186,7 @@ static int discover_sharded_impl(ff_ctx *ctx, const uint64_t *d_guides_all, int6
               "ff_peer_export with a larger hit_cap", cap, region_cap);
     return FF_ENOMEM;
   }
-  if (h_stt->flag & 0xFFu) { set_error("database-sharded discover: a guide with more candidates than the per-guide sort takes; use the guide-sharded call"); return FF_EUNSUPPORTED; }
+  if ((h_stt->flag & 0xFFu) && !ctx->opt.peer_local_only) { set_error("database-sharded discover: a guide with more candidates than the per-guide sort takes; use the guide-sharded call"); return FF_EUNSUPPORTED; }
   const int64_t n_hits = G > 0 ? h_stt->n_hits : 0;
   FF_CUDA(cudaEventSynchronize(ctx->ev[4]));
   FF_CUDA(cudaEventElapsedTime(&tm.prep_ms, ctx->ev[0], ctx->ev[1]));

@@ -31,7 +31,11 @@ def run(label, resolve=False, reps=20):
     print(label, "%.2f ms" % ((time.perf_counter() - t0) / reps * 1e3), flush=True)
 
 
-for cuts, mb in (("65,90", 20000), ("50,80", 20000), ("40,75", 20000), ("60,100", 45000), ("65,90", 1000000)):
-    c1, c2 = cuts.split(","); ctx.set_option("subbatch_c1", int(c1)); ctx.set_option("subbatch_c2", min(99, int(c2))); ctx.set_option("subbatch_min", mb)
-    ctx.set_option("compact_hits", 0); run("full    cuts %s min %d:" % (cuts, mb))
-    ctx.set_option("compact_hits", 1); run("compact cuts %s min %d:" % (cuts, mb)); run("compact+resolve           :", True)
+for two in (55, 60, 65, 70, 75):
+    ctx.set_option("subbatch_two", two); ctx.set_option("subbatch_min", 45000)
+    ctx.set_option("compact_hits", 0); run("full    two sub-batches, first %d %%:" % two)
+    ctx.set_option("compact_hits", 1); run("compact two sub-batches, first %d %%:" % two)
+ctx.set_option("compact_hits", 0)
+for cuts, mb in (("55,85", 30000), ("60,88", 30000), ("65,90", 30000)):
+    c1, c2 = cuts.split(","); ctx.set_option("subbatch_c1", int(c1)); ctx.set_option("subbatch_c2", int(c2)); ctx.set_option("subbatch_min", mb)
+    run("full    three sub-batches %s:" % cuts)
