@@ -240,7 +240,17 @@ def run_native(args):
             d_all = torch.from_numpy(all_guides.view(np.int64)).to(dev)
             if os.environ.get("FF_PEER_LOCAL_ONLY"):
                 ctx.set_option("peer_local_only", 1)
-        elif args.shard == "database":
+            try:  # one trial step: a rank that fails (its peers then leave their barriers after 4 s) sends everyone to guide sharding
+                ctx.discover_sharded_device(d_all.data_ptr(), G_job, k, args.max_ot, 0)
+            except Exception as e:  # noqa: BLE001
+                ok, shard_note = 0, "trial step failed: %s" % e
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            db_sharded = bool(flag.item())
+            if not db_sharded:
+                ctx.peer_detach()
+                shard_note = shard_note or "the trial step failed on another rank"
+        if not db_sharded and args.shard == "database":
             raise SystemExit("--shard database: %s" % (shard_note or "a peer rank could not map the exchange blocks"))
 
     class _DevView:  # wrap a context-owned device pointer for torch without copying

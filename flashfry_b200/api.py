@@ -101,7 +101,7 @@ class Context:
         ctx = self
         defaults = {"scan_kernel": 0, "force_general": 0, "window_cells": 0, "subbatch_min": 45000, "subbatch_c1": 65,
                     "subbatch_c2": 90, "group_sort": 1, "trace": 0, "b_spi": 0, "split_a": 0, "compact_hits": 0, "pair_kernel": 0,
-                    "pair_segs": 0, "subbatch_two": 60, "peer_local_only": 0, "debug_bin_div": 0}
+                    "pair_segs": 0, "subbatch_two": 70, "peer_local_only": 0, "debug_bin_div": 0}
 
         class _O:
             def __enter__(self_o):

@@ -132,7 +132,7 @@ static int discover_host(ff_ctx *c, const uint64_t *guides, int64_t n_guides, in
   // call, ~0.25 ms on a human-sized index), which is why two sub-batches beat three at 100 000 guides.
   const int64_t min_batch = std::max(1, c->opt.subbatch_min);
   const int nb = want_positions ? 1 : (int)std::min<int64_t>(3, std::max<int64_t>(1, n_guides / min_batch));
-  int kCut[4][4] = {{0, 0, 0, 0}, {0, 100, 100, 100}, {0, 60, 100, 100}, {0, 65, 90, 100}};  // cumulative % (A/B on the GPU: 7.5 ms per 100 000 guides; 50/30/20: 7.8 ms)
+  int kCut[4][4] = {{0, 0, 0, 0}, {0, 100, 100, 100}, {0, 70, 100, 100}, {0, 65, 90, 100}};  // cumulative % (measured, 100 000 guides: 70 / 30 -> 4.16 ms, 60 / 40 -> 4.25, three sub-batches 4.38)
   if (c->opt.subbatch_c1 > 0 && c->opt.subbatch_c1 < c->opt.subbatch_c2 && c->opt.subbatch_c2 < 100) {
     kCut[3][1] = c->opt.subbatch_c1; kCut[3][2] = c->opt.subbatch_c2;
   }

@@ -113,7 +113,7 @@ struct Options {
   int subbatch_min = 45000;           // ff_discover cuts a guide set into up to three sub-batches of at least this size
                                       // (measured on B200: two sub-batches 60 / 40 % beat one and three for 100 000 guides)
   int subbatch_c1 = 65, subbatch_c2 = 90;  // cumulative % of the first two of three sub-batches
-  int subbatch_two = 60;                   // % of the guides in the first of two sub-batches
+  int subbatch_two = 70;                   // % of the guides in the first of two sub-batches
   int group_sort = 1;      // 0 = always order hits with the radix sort
   int b_spi = 0;           // > 0: seeds per work item of the part-two pass of k_seed_scan / k_pattern_scan
   int split_a = 0;         // > 0: bases in the part-one key of the next database build

@@ -1,13 +1,22 @@
 #!/bin/bash
-# The round's multi-GPU measurements (run with: gpurun --gpus 8 -- bash tools/scale_run.sh).  One JSON line per run.
-out=gpurun_out/r2_scale.jsonl
-: > $out
-tr() { n=$1; shift; if [ $n -eq 1 ]; then python bench.py --gpus 1 "$@"; else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n "$@"; fi; }
-for n in 1 2 4 8; do tr $n --steps 20 --warmup 5 --no-extras >> $out 2>> gpurun_out/r2_scale.err; done
-for n in 2 8; do tr $n --steps 20 --warmup 5 --no-extras --scaling weak >> $out 2>> gpurun_out/r2_scale.err; done
-tr 8 --steps 20 --warmup 5 --workload fused >> $out 2>> gpurun_out/r2_scale.err
-tr 8 --steps 5 --warmup 3 --workload bulge >> $out 2>> gpurun_out/r2_scale.err
-tr 1 --steps 20 --warmup 5 --workload fused >> $out 2>> gpurun_out/r2_scale.err
-for n in 1 2 4 8; do python bench.py --single-process --gpus $n --steps 20 --warmup 5 >> $out 2>> gpurun_out/r2_scale.err; done
-nvidia-smi topo -m > gpurun_out/r2_topo.txt 2>&1
+# The round's multi-GPU measurements, one JSON line per run.  N GPUs cost N x the box time, so every rank count gets its
+# own call:  gpurun --gpus 8 -- bash tools/scale_run.sh 8 ;  gpurun --gpus 4 -- bash tools/scale_run.sh 4 ; ...
+n=${1:-8}
+out=gpurun_out/r3_scale_n$n.jsonl
+err=gpurun_out/r3_scale_n$n.err
+: > $out; : > $err
+tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n "$@"; }
+tr --steps 20 --warmup 5 --no-extras >> $out 2>> $err                    # strong, index work sharded over NVLink peer memory
+tr --steps 20 --warmup 5 --no-extras --shard guides >> $out 2>> $err     # strong, guides sharded (NCCL all-gather of totals)
+if [ "$n" = "8" ]; then
+  tr --steps 20 --warmup 5 --workload fused >> $out 2>> $err              # configs[4]
+  python bench.py --single-process --gpus $n --steps 20 --warmup 5 >> $out 2>> $err
+  nvidia-smi topo -m > gpurun_out/r3_topo.txt 2>&1
+fi
 wc -l $out
+python - <<P
+import json
+for l in open("$out"):
+    d=json.loads(l)
+    print(d["n_gpus"], d["config"].get("parallelism", d["config"].get("shard_mode",""))[:40], "value %.4g ms %.3f | e2e %.4g ms %.3f" % (d["value"], d["ms_per_step"], d.get("e2e",{}).get("value",0), d.get("e2e",{}).get("ms_per_step",0)), d.get("roofline",{}).get("step_breakdown_ms"), d["config"].get("sharded_rows_equal_single_gpu_rows"), d["config"].get("shard_fallback_reason"))
+P
