@@ -219,7 +219,11 @@ def run_native(args):
     # blocks are mapped with CUDA IPC handles exchanged once through torch.distributed; any rank that cannot map them
     # sends every rank back to guide sharding.
     db_sharded, d_all, shard_note = False, None, None
-    if world > 1 and args.scaling == "strong" and wl in ("discover", "fused") and args.shard != "guides":
+    # auto: measured on 8 x B200 (profiles/r3_scale_*.jsonl) the sharded index work wins on device time from 4 GPUs on (+3 % at 4,
+    # +16 % at 8, fused +46 % at 8) but loses end to end (its barriers make all ranks copy their rows to the host at the same
+    # moment: 106 MB into one socket); it is the default from 8 GPUs on.
+    want_db = args.shard == "database" or (args.shard == "auto" and world >= 8)
+    if world > 1 and args.scaling == "strong" and wl in ("discover", "fused") and want_db:
         ok = 1
         try:
             hit_cap = max(1 << 24, int(2.0 * 130.0 * G_job / world))
@@ -774,7 +778,7 @@ def main():
                     help="discover = configs[2]; fused = configs[4] (discover + CFD + Hsu2013 on the GPU, 50 000 guides); bulge = configs[3]")
     ap.add_argument("--no-extras", action="store_true", help="only the headline line (no side measurements)")
     ap.add_argument("--shard", default="auto", choices=["auto", "guides", "database"],
-                    help="N > 1, strong scaling: shard the guides (NCCL all-gather of totals) or the index work (NVLink peer memory); auto = database")
+                    help="N > 1, strong scaling: shard the guides (NCCL all-gather of totals) or the index work (NVLink peer memory); auto = database from 8 GPUs on")
     ap.add_argument("--single-process", action="store_true",
                     help="all --gpus behind ONE process through the C ABI's ff_multi (not the torchrun contract): end-to-end line only")
     ap.add_argument("--no-ladder", action="store_true")

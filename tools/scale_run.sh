@@ -6,10 +6,10 @@ out=gpurun_out/r3_scale_n$n.jsonl
 err=gpurun_out/r3_scale_n$n.err
 : > $out; : > $err
 tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n "$@"; }
-tr --steps 20 --warmup 5 --no-extras >> $out 2>> $err                    # strong, index work sharded over NVLink peer memory
+tr --steps 20 --warmup 5 --no-extras --shard database >> $out 2>> $err   # strong, index work sharded over NVLink peer memory
 tr --steps 20 --warmup 5 --no-extras --shard guides >> $out 2>> $err     # strong, guides sharded (NCCL all-gather of totals)
 if [ "$n" = "8" ]; then
-  tr --steps 20 --warmup 5 --workload fused >> $out 2>> $err              # configs[4]
+  tr --steps 20 --warmup 5 --workload fused --shard database >> $out 2>> $err   # configs[4]
   python bench.py --single-process --gpus $n --steps 20 --warmup 5 >> $out 2>> $err
   nvidia-smi topo -m > gpurun_out/r3_topo.txt 2>&1
 fi
