@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(kP2Threads, FF_P2_BLOCKS) k_pair_scan2(PairPar
     {  // the bin's copies have landed (or the work has ended)
       const uint32_t mbar = smem_addr(&sh.full[b]), parity = (i >> 1) & 1u;
       uint32_t done = 0;
-      while (!done)
+      while (!done)  // (tried: __nanosleep between polls -- no change, try_wait suspends the warp itself)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
     }
@@ -926,8 +926,11 @@ __global__ void __launch_bounds__(kP2Threads, FF_P2_BLOCKS) k_pair_scan2(PairPar
     // sign off: this warp reads nothing of bin i any more; the last one out refills the buffer with bin i + 2
     __syncwarp();
     if (lane == 0) {
-      __threadfence_block();
-      if (atom_add_shared(smem_addr(&sh.left[b]), 1u) == (uint32_t)kP2Warps - 1u) p2_refill<NB>(pp, sh, sbase, b);
+      __threadfence_block();  // release: this warp's reads of the bin's words and slice are done ...
+      if (atom_add_shared(smem_addr(&sh.left[b]), 1u) == (uint32_t)kP2Warps - 1u) {
+        __threadfence_block();  // ... acquire: so are those of every other warp; the buffer may be overwritten
+        p2_refill<NB>(pp, sh, sbase, b);
+      }
     }
     __syncwarp();
   }
