@@ -6,11 +6,14 @@
     python bench.py --workload fused|bulge                      # BASELINE.json configs[4] / configs[3] as first-class lines
     python bench.py --scaling weak                              # the full batch on every GPU instead of one sharded batch
     python bench.py --single-process --gpus N                   # every GPU behind ONE process through the C ABI's ff_multi
+    python bench.py --shard guides|database                     # N > 1: what is sharded (auto: the index work from 8 GPUs on)
 
 Workload (BASELINE.json configs[2], named in config.workload): 100 000 synthetic 20-bp NGG guides IN TOTAL (+10 % planted
 near real targets), sharded over the ranks ("scaling": "strong"), against a synthetic human-genome-sized (3e8 distinct
 targets) spCas9-NGG index, <= 4 mismatches, maximumOffTargets 2000.  The index is generated in HBM from a seed; one
-replica per GPU.  A "step" = one discover call over the rank's shard + one all-gather of the per-guide totals.
+replica per GPU.  A "step" = one discover call over the rank's shard + one all-gather of the per-guide totals; with
+--shard database every rank scans 1/N of the index for ALL guides and the candidates, the barriers and the all-gather of the
+totals go through NVLink peer memory (flashfry_b200/csrc/ff_shard.inl), each rank ending with the rows of its own guides.
 
 `value`  : whole-job guides/s with guides already in HBM and results left in HBM (CUDA events, max over ranks).
 `e2e`    : the same metric through the C ABI with HOST buffers (ff_discover: H2D of the guides, D2H of the hit lists);

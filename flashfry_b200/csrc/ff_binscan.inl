@@ -410,13 +410,13 @@ constexpr int kNbrCap = 1160;       // bin-part masks within the seed budget (7 
 #define FF_BIN_SLICE 800
 #endif
 #ifndef FF_BIN_PAIRCAP
-#define FF_BIN_PAIRCAP 1536
+#define FF_BIN_PAIRCAP 2016
 #endif
 #ifndef FF_BIN_VISITS
 #define FF_BIN_VISITS 1536
 #endif
 constexpr int kSliceGroups = FF_BIN_SLICE;   // groups of 32 entries a CTA can stage (x 72 B = 56 KB; a human-sized bin is ~717 bucket-aligned groups)
-constexpr int kPairCap = FF_BIN_PAIRCAP;     // pairs sorted by bucket at a time (a human-sized bin with 100 000 guides has ~3200)
+constexpr int kPairCap = FF_BIN_PAIRCAP;     // pairs sorted by bucket at a time (a human-sized bin with 100 000 guides has ~3200: two chunks)
 constexpr int kVisitCap = FF_BIN_VISITS;     // (class, guide) visits of a bin listed in shared memory (~1300); more: binary search
 
 struct BinParams {
@@ -559,8 +559,10 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
       const bool glob = sh.glob != 0;
       bool waited = sh.bytes == 0;
       const uint32_t n_pairs = sh.PB[bp.hA + 1];
-      for (uint32_t c0 = 0; c0 < n_pairs; c0 += kPairCap) {
-        const uint32_t cn = min((uint32_t)kPairCap, n_pairs - c0);
+      // chunks of equal size (a human-sized bin with 100 000 guides: 3216 pairs -> 2 x 1608, not 2016 + 1200)
+      const uint32_t n_chunks = (n_pairs + kPairCap - 1) / kPairCap, chunk = n_chunks ? (n_pairs + n_chunks - 1) / n_chunks : 0;
+      for (uint32_t c0 = 0; c0 < n_pairs; c0 += chunk) {
+        const uint32_t cn = min(chunk, n_pairs - c0);
         if (tid < 256) sh.cnt[tid] = 0;
         __syncthreads();
         if (tid == 0) sh.next_slice = 0;  // (every warp has left the previous chunk's claim loop)

@@ -47,6 +47,9 @@ public final class NativeBridge {
    *  guides [r n / d, (r + 1) n / d)) and fills totals[nGuides] with the NCCL-all-gathered per-guide totals. */
   public static native long multiCreate(int[] devices);
   public static native void multiDestroy(long multi);
+  /** ff_multi_set_option: every context option, plus "shard_mode" (0 = shard the guides, 1 = shard the index work: the
+   *  candidates reach the guide's owner over NVLink peer memory) and "peer_hit_cap". */
+  public static native void multiSetOption(long multi, String key, long value);
   public static native void multiLoadDatabase(long multi, String dbPath);
   public static native long[] multiDiscover(long multi, long[] guides, int maxMismatch, int maxOffTargets, boolean wantPositions, int[] totals);
 }

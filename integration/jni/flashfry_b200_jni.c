@@ -264,6 +264,12 @@ JNIEXPORT jlong JNICALL Java_flashfry_NativeBridge_multiCreate(JNIEnv *env, jcla
   return (jlong)(intptr_t)m;
 }
 JNIEXPORT void JNICALL Java_flashfry_NativeBridge_multiDestroy(JNIEnv *env, jclass c, jlong m) { ff_multi_destroy((ff_multi *)(intptr_t)m); }
+JNIEXPORT void JNICALL Java_flashfry_NativeBridge_multiSetOption(JNIEnv *env, jclass c, jlong m, jstring key, jlong value) {
+  const char *k = (*env)->GetStringUTFChars(env, key, NULL);
+  int rc = ff_multi_set_option((ff_multi *)(intptr_t)m, k, (long long)value);
+  (*env)->ReleaseStringUTFChars(env, key, k);
+  if (rc != FF_OK) throw_ise(env, NULL);
+}
 JNIEXPORT void JNICALL Java_flashfry_NativeBridge_multiLoadDatabase(JNIEnv *env, jclass c, jlong m, jstring path) {
   const char *p = (*env)->GetStringUTFChars(env, path, NULL);
   int rc = ff_multi_load_database((ff_multi *)(intptr_t)m, p, NULL);

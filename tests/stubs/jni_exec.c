@@ -164,6 +164,20 @@ int main(int argc, char **argv) {
     CHECK(hits == ref->n_hits);
     Java_flashfry_NativeBridge_multiDestroy(env, NULL, m);
   }
+  /* the same with the index work sharded (shard_mode = 1: candidates over peer memory); two ranks, on one device if need be */
+  {
+    jint devs[2] = {0, n_gpus >= 2 ? 1 : 0};
+    jlong m = Java_flashfry_NativeBridge_multiCreate(env, NULL, mock_array('I', 2, devs)); NOEXC(); CHECK(m != 0);
+    Java_flashfry_NativeBridge_multiSetOption(env, NULL, m, mock_string("shard_mode"), 1); NOEXC();
+    Java_flashfry_NativeBridge_multiLoadDatabase(env, NULL, m, mock_string(db)); NOEXC();
+    jintArray totals = mock_array('I', G, NULL);
+    jlongArray hh = Java_flashfry_NativeBridge_multiDiscover(env, NULL, m, jg, 4, 2000, 0, totals); NOEXC(); CHECK(hh && MOCK(hh)->n == 2);
+    CHECK(memcmp(INTS(totals), ref->total_count, G * 4) == 0);
+    int64_t hits = 0;
+    for (int r = 0; r < 2; ++r) { hits += HITS(LONGS(hh)[r])->n_hits; Java_flashfry_NativeBridge_hitsFree(env, NULL, LONGS(hh)[r]); }
+    CHECK(hits == ref->n_hits);
+    Java_flashfry_NativeBridge_multiDestroy(env, NULL, m);
+  }
 
   Java_flashfry_NativeBridge_hitsFree(env, NULL, h);
   ff_hits_free(ref);

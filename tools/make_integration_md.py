@@ -30,7 +30,7 @@ what all other tests exercise (ctypes, and the C++ host mirror `flashfry_b200/cs
 | (optional) discover + score in one go | two CLI runs through a TSV | `ff_discover_score`: the hit list is scored while still in HBM |
 | `scoring/ClosestHit.scala:43-76` (`minot`), `DangerousSequences.scala:61-65` (in-genome count) | per-guide loops over the hit list | `ff_hit_aggregates` (integer reductions on the GPU) |
 | (optional) cold start | BGZF inflate + block walk on every run (~40 s on hg38) | `ff_load_database`: 2.8 s for a 3e8-target database on 16 host threads; `ff_save_image` / `ff_load_image`: a flat side-car (not a FlashFry format) |
-| (optional) every GPU of the box | the JVM is one process | `multiCreate` / `multiDiscover` → `ff_multi_*`: guide shards on every device, one NCCL all-gather of the totals |
+| (optional) every GPU of the box | the JVM is one process | `multiCreate` / `multiDiscover` → `ff_multi_*`: guide shards on every device, one NCCL all-gather of the totals; `multiSetOption("shard_mode", 1)` shards the INDEX WORK instead (every device scans 1/n of the index for all guides, candidates travel to the guide's owner over NVLink peer memory; `ff_shard.inl`) -- same rows, faster from 4 GPUs on |
 | (optional) fewer bytes over PCIe | — | `setOption("compact_hits", 1)`: hit lists carry 32-bit database indices; `dbHostTargets` is the target array as a direct buffer |
 
 An extension outside FlashFry's feature set, `ff_discover_bulge` (≤ k mismatches plus one 1-bp RNA or DNA bulge, defined
