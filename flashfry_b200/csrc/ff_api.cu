@@ -317,7 +317,7 @@ void ff_destroy(ff_ctx *c) {
   cudaStreamSynchronize(c->stream);
   c->db.release();
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-  DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys, &c->hit_keys_sorted, &c->counters, &c->seg_start, &c->n_keep, &c->pos_cnt,
+  DevBuf *bufs[] = {&c->cub_tmp, &c->hit_keys, &c->hit_keys_sorted, &c->counters, &c->hit_ranks, &c->seg_start, &c->n_keep, &c->pos_cnt,
                     &c->pos_ptr, &c->out_positions, &c->cfd_per_ot, &c->hsu_per_ot, &c->scratch_guides, &c->running, &c->active, &c->active2,
                     &c->act_flags, &c->seg_end, &c->kept_keys, &c->kept_sorted, &c->n_sel, &c->cell_ws, &c->idx32, &c->st_targets, &c->st_mm};
   for (DevBuf *b : bufs) b->release();

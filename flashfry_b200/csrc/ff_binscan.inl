@@ -129,6 +129,8 @@ struct HitSink {
   unsigned long long hit_cap;         // world > 1: keys per REGION (block capacity / world)
   int tbits;
   unsigned int *gcnt;  // per-guide candidate counts for the ordering that follows (nullptr: not wanted)
+  uint32_t *ranks;     // with gcnt: the rank of every candidate among its guide's (the value gcnt had), so that the ordering
+                       // places candidates without a second round of atomics (nullptr: not wanted)
   int world, rank;                    // ranks of the exchange (world <= 1: no exchange)
   float owner_scale;                  // world / all guides
   unsigned int first[kMaxPeers + 1];  // first guide owned by every rank (ff_shard_range), first[world] = all guides
@@ -203,7 +205,11 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
       }
       continue;
     }
-    if (c && hs.gcnt) atomicAdd(hs.gcnt + e.z, (unsigned int)c);
+    unsigned int r0 = 0;
+    if (c && hs.gcnt) {
+      if (hs.ranks) r0 = atomicAdd(hs.gcnt + e.z, (unsigned int)c);  // (in flight together with the position atomic below)
+      else atomicAdd(hs.gcnt + e.z, (unsigned int)c);
+    }
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -221,8 +227,11 @@ __device__ __forceinline__ void drain_queue(const HitSink &hs, uint32_t q_off, u
       const int b = __ffs((int)vm) - 1;
       vm &= vm - 1u;
       const uint32_t idx = e.y + (uint32_t)b;
-      if (pos < hs.hit_cap) hs.hits[pos] = gk | (canon ? canon[idx] : idx);
-      ++pos;
+      if (pos < hs.hit_cap) {
+        hs.hits[pos] = gk | (canon ? canon[idx] : idx);
+        if (hs.ranks) hs.ranks[pos] = r0;
+      }
+      ++pos; ++r0;
     }
   }
   __syncwarp();
@@ -1094,9 +1103,9 @@ static int bin_scan_prepare(ff_ctx *ctx, const ScanParams &sp, int hA, int nB, u
 }
 
 // (re)launch the two scan kernels of a prepared plan; hit buffer and counters come from `sp`
-static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, unsigned int *gcnt, int *launches) {
+static int bin_scan_launch(ff_ctx *ctx, BinScanPlan *pl, const ScanParams &sp, unsigned int *gcnt, int *launches, uint32_t *ranks = nullptr) {
   cudaStream_t st = ctx->stream;
-  pl->bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits, gcnt};
+  pl->bp.hs = HitSink{sp.hits, sp.hit_count, sp.hit_cap, sp.tbits, gcnt, gcnt ? ranks : nullptr};
   if (pl->shard) { pl->bp.hs = pl->sink; pl->bp.hs.tbits = sp.tbits; pl->bp.hs.gcnt = nullptr; }
   pl->pp.hs = pl->bp.hs;
   FF_CUDA(cudaMemsetAsync(pl->bp.next_bin, 0, 128, st));

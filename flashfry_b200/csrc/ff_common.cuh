@@ -151,7 +151,7 @@ struct ff_ctx {
 
   // ---- per-call workspaces (grow-only) ----
   ff::DevBuf cub_tmp;
-  ff::DevBuf hit_keys, hit_keys_sorted, counters;
+  ff::DevBuf hit_keys, hit_keys_sorted, counters, hit_ranks;
   ff::DevBuf seg_start, n_keep;
   ff::DevBuf idx32, st_targets, st_mm;  // per-guide ordering: scattered database indices, rows staged at their segment
   ff::HostBuf host_targets;             // host mirror of db.d_targets (ff_db_host_targets), made on first use

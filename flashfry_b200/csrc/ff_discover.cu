@@ -418,6 +418,18 @@ __global__ void k_guide_scatter(const uint64_t *__restrict__ keys, const unsigne
   }
 }
 
+// The same placement when the scan has recorded every candidate's rank among its guide's: no atomics.
+__global__ void k_guide_place(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ ranks, const unsigned long long *__restrict__ n_ptr,
+                              unsigned long long cap, int tbits, const int64_t *__restrict__ seg_start, uint32_t *__restrict__ out) {
+  if (*n_ptr > cap) return;
+  const unsigned long long n = *n_ptr;
+  const uint64_t low = (1ull << tbits) - 1ull;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    out[seg_start[key >> tbits] + (int64_t)ranks[i]] = (uint32_t)(key & low);
+  }
+}
+
 __global__ void k_widen_counts(const unsigned int *__restrict__ cnt, int64_t n, int64_t *__restrict__ out) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = (int64_t)cnt[i];
@@ -740,7 +752,8 @@ static void fill_scan_params(ff_ctx *ctx, const uint64_t *d_guides, int64_t G, i
 // `hits[0 .. min(d_stt->n_cand, cap))` (guide << tbits | database index) -> CSR rows in the output slot.  `cnt` holds the
 // per-guide candidate counts (need_hist: take them here), `cursor` is zeroed scratch of the same size + the long-segment list.
 static int order_grouped(ff_ctx *ctx, ff_ctx::OutSlot &os, const uint64_t *hits, PlainStatus *d_stt, size_t cap, int tbits, unsigned int *cnt,
-                         unsigned int *cursor, bool need_hist, const uint64_t *d_guides, int64_t G, int max_ot, int *launches_out) {
+                         unsigned int *cursor, bool need_hist, const uint64_t *d_guides, int64_t G, int max_ot, int *launches_out,
+                         const uint32_t *ranks = nullptr) {
   Database &db = ctx->db;
   cudaStream_t st = ctx->stream;
   const int64_t Gp = G > 0 ? G : 1;
@@ -758,7 +771,8 @@ static int order_grouped(ff_ctx *ctx, ff_ctx::OutSlot &os, const uint64_t *hits,
       FF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
       FF_TRY(ctx->cub_tmp.reserve(tmp_bytes));
       FF_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bytes, cnt64, ctx->seg_start.as<int64_t>(), G + 1, st));
-      k_guide_scatter<<<sgrid, 256, 0, st>>>(hits, &d_stt->n_cand, cap, tbits, ctx->seg_start.as<int64_t>(), cursor, ctx->idx32.as<uint32_t>());
+      if (ranks && !need_hist) k_guide_place<<<sgrid, 256, 0, st>>>(hits, ranks, &d_stt->n_cand, cap, tbits, ctx->seg_start.as<int64_t>(), ctx->idx32.as<uint32_t>());
+      else k_guide_scatter<<<sgrid, 256, 0, st>>>(hits, &d_stt->n_cand, cap, tbits, ctx->seg_start.as<int64_t>(), cursor, ctx->idx32.as<uint32_t>());
       k_mark_long<<<blocks_for(G, 256), 256, 0, st>>>(ctx->seg_start.as<int64_t>(), G, long_list, d_stt);
       k_sort_long<<<kLongCap, 512, kLongMax * 4, st>>>(ctx->idx32.as<uint32_t>(), ctx->seg_start.as<int64_t>(), long_list, d_stt);
       FF_CUDA(cudaEventRecord(ctx->ev[3], st));
@@ -870,7 +884,8 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
     }
     if (G > 0) {
       if (bin_major) {
-        FF_TRY(bin_scan_launch(ctx, &bpl, sp, cnt, &launches));  // (counts the candidates per guide as it emits them)
+        if (cnt) FF_TRY(ctx->hit_ranks.reserve(cap * 4));
+        FF_TRY(bin_scan_launch(ctx, &bpl, sp, cnt, &launches, cnt ? ctx->hit_ranks.as<uint32_t>() : nullptr));  // (counts and ranks the candidates per guide as it emits them)
       } else {
         k_seed_scan<<<grid, kScanThreads, 0, st>>>(sp);
         launches++;
@@ -878,7 +893,8 @@ static int discover_plain(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_guide
       scan_launches++;
     }
     FF_CUDA(cudaEventRecord(ctx->ev[2], st));
-    if (grouped) FF_TRY(order_grouped(ctx, os, sp.hits, d_stt, cap, tbits, cnt, cursor, !bin_major, d_guides, G, max_ot, &launches));
+    if (grouped) FF_TRY(order_grouped(ctx, os, sp.hits, d_stt, cap, tbits, cnt, cursor, !bin_major, d_guides, G, max_ot, &launches,
+                                      bin_major ? ctx->hit_ranks.as<uint32_t>() : nullptr));
     k_publish_status<<<1, 32, 0, st>>>(d_stt, nullptr, h_stt_dev, ++ctx->status_seq);
     FF_TRY(wait_status(ctx, st, ctx->status_seq));
     n_cand = (int64_t)h_stt->n_cand;
