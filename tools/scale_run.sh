@@ -11,6 +11,7 @@ tr --steps 20 --warmup 5 --no-extras --shard guides >> $out 2>> $err     # stron
 if [ "$n" = "8" ]; then
   tr --steps 20 --warmup 5 --workload fused --shard database >> $out 2>> $err   # configs[4]
   python bench.py --single-process --gpus $n --steps 20 --warmup 5 >> $out 2>> $err
+  tr --steps 20 --warmup 5 --no-extras --scaling weak >> $out 2>> $err     # 100 000 guides per GPU
   nvidia-smi topo -m > gpurun_out/r3_topo.txt 2>&1
 fi
 wc -l $out
