@@ -245,8 +245,6 @@ def run_native(args):
         db_sharded = bool(flag.item())
         if db_sharded:
             d_all = torch.from_numpy(all_guides.view(np.int64)).to(dev)
-            if os.environ.get("FF_PEER_LOCAL_ONLY"):
-                ctx.set_option("peer_local_only", 1)
             try:  # one trial step: a rank that fails (its peers then leave their barriers after 4 s) sends everyone to guide sharding
                 ctx.discover_sharded_device(d_all.data_ptr(), G_job, k, args.max_ot, 0)
             except Exception as e:  # noqa: BLE001
@@ -315,7 +313,7 @@ def run_native(args):
     n_hits, cand = int(r.n_hits), int(r.n_candidate_hits)
     ent1, ent2, req_bytes, scan_launches = int(tm.entries_part1), int(tm.entries_part2), int(tm.scan_bytes_read), int(tm.scan_launches)
     sharded_ok = None
-    if db_sharded and not os.environ.get("FF_PEER_LOCAL_ONLY"):  # the sharded rows of this rank's guides against the single-GPU call on the same shard, all ranks
+    if db_sharded:  # the sharded rows of this rank's guides against the single-GPU call on the same shard, all ranks
         def _rows(res):
             v = lambda ptr, n, ts: torch.as_tensor(_Dev(ptr, n, ts), device=dev).clone()  # noqa: E731
             return (v(res.d_row_ptr, G + 1, "<i8"), v(res.d_targets, max(int(res.n_hits), 1), "<i8")[:int(res.n_hits)],

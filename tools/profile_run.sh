@@ -1,3 +1,4 @@
+# The profile capture of the round (one B200): gpurun -- bash tools/profile_run.sh ; summaries: tools/make_scan_traffic.py, tools/ncu_summary.py
 set -x
 python -m pytest tests -m gpu -x -q > gpurun_out/r3_pytest.log 2>&1; tail -3 gpurun_out/r3_pytest.log
 python bench.py --impl reference > gpurun_out/r3_ref.json 2> gpurun_out/r3_ref.err
