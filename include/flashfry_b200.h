@@ -238,8 +238,9 @@ int ff_discover_bulge_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gu
  * Strong scaling of ONE guide set over the GPUs of a box (reference/traverser/Traverser.scala:52-59 hands a traverser all
  * guides and the whole database; the reference itself is single-process, OffTargetDiscovery.scala:117).  Every rank holds
  * an index replica, scans 1/world of the INDEX for ALL guides, and the scan kernels push each candidate straight into the
- * exchange block of the rank that owns the guide (ff_shard_range) -- P2P stores + remote atomics, barriers and the
- * all-gather of the per-guide totals included: no NCCL on this path.  Rows are identical to ff_discover's.
+ * exchange block of the rank that owns the guide (ff_shard_range) -- fire-and-forget P2P stores into the region the owner
+ * keeps for each source rank (positions from local atomics); the barriers (one remote atomic per peer) and the all-gather
+ * of the per-guide totals go through the same blocks: no NCCL on this path.  Rows are identical to ff_discover's.
  *   1. every rank: ff_peer_export        -> its block exists; handle = CUDA IPC handle (other processes), *block_out = pointer
  *   2. every rank: ff_peer_attach        with the handles of all ranks (one process per GPU) or their pointers (one process)
  *   3. every rank, same arguments:        ff_discover_sharded[_device](all guides) -> rows of ITS guides

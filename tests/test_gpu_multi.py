@@ -79,8 +79,8 @@ def _assert_shards_equal(ff, shards, totals, ref, n_guides, n_ranks):
 @pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0], [0, 1], [0, 1, 2, 3]])
 def test_database_sharded_discover_over_peer_memory(ff, oracle, devices):
     """shard_mode = 1 (ff_shard.inl): every rank scans 1/n of the INDEX for all guides; the scan kernels push each candidate
-    into the exchange block of the guide's owner (peer stores + remote atomics), barriers and the all-gather of the totals
-    go through the same blocks.  Rows must equal the oracle's.  Several ranks on ONE device exercise the same kernels
+    into the exchange block of the guide's owner (peer stores into one region per source rank), barriers and the all-gather
+    of the totals go through the same blocks.  Rows must equal the oracle's.  Several ranks on ONE device exercise the same kernels
     (the "peers" are then blocks in the same HBM), so the path is covered on a single-GPU box too."""
     if _n_gpus() <= max(devices):
         pytest.skip("needs %d GPUs" % (max(devices) + 1))
