@@ -448,7 +448,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)
 
 struct BinShared {
   unsigned long long mbar;
-  uint32_t bin, b0, b1, glob, g_base, bytes, use_vis, next_slice;
+  uint32_t bin, b0, b1, glob, g_base, bytes, use_vis, next_slice, early, pad0;
   uint32_t R[6], PB[6];
   uint32_t wtot[kBinWarps];
   uint32_t off[260], goff[260];  // entries / groups: first of every bucket of the bin
@@ -479,12 +479,33 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
   const uint32_t q_off = kShOff + (uint32_t)offsetof(BinShared, q) + (uint32_t)warp * kQCap * 16u;
   const uint32_t sbase = smem_addr(ff_smem), claim_addr = smem_addr(&sh.next_slice);
   uint32_t qcount = 0;
+  uint32_t claimed = 0;  // thread 0: the bin after the current one, claimed a whole bin ahead (its atomic is never waited for)
+  if (tid == 0) claimed = bp.bin_base + atomicAdd(bp.next_bin, 1u);
   for (;;) {
     __syncthreads();  // the previous bin is finished: its slice and tables may be overwritten
-    if (tid == 0) sh.bin = bp.bin_base + atomicAdd(bp.next_bin, 1u);
+    if (tid == 0) sh.bin = claimed;
     __syncthreads();
     const uint32_t bin = sh.bin;
     if (bin >= bp.n_bins) break;
+    if (tid == 0) claimed = bp.bin_base + atomicAdd(bp.next_bin, 1u);
+    if (tid == kBinThreads - 1) {  // (a thread that has no class to size below) start the copy of the bin's slice NOW when it fits the
+      const uint32_t gs = bp.goff[bin << 8] & ~1u, ge = bp.goff[(bin << 8) + 256];  // buffer: it lands during the set-up phases
+      const bool fits = ge - gs <= (uint32_t)kSliceGroups;
+      sh.early = fits ? 1u : 0u;
+      if (fits) {
+        const uint32_t bytes = ((ge - gs) * STRIDE * 4u + 15u) & ~15u;
+        sh.b1 = 256; sh.g_base = gs; sh.glob = 0u; sh.bytes = bytes;
+        if (bytes) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&sh.mbar)), "r"(bytes) : "memory");
+          const uint8_t *src = reinterpret_cast<const uint8_t *>(bp.planes + (size_t)gs * STRIDE);
+          for (uint32_t o = 0; o < bytes; o += 32768u) {
+            const uint32_t nb = min(32768u, bytes - o);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr(ff_smem + o)), "l"(src + o), "r"(nb), "r"(smem_addr(&sh.mbar)) : "memory");
+          }
+        }
+      }
+    }
     for (int i = tid; i <= 256; i += kBinThreads) { sh.off[i] = bp.off[(bin << 8) + i]; sh.goff[i] = bp.goff[(bin << 8) + i]; }
     // guide classes that reach this bin, and the exclusive prefix of their sizes ("visits" of the bin)
     uint32_t carry = 0;
@@ -540,7 +561,9 @@ __global__ void __launch_bounds__(kBinThreads, 2) k_bin_scan(BinParams bp) {
     // larger than the buffer is streamed from global memory
     for (;;) {
       __syncthreads();
-      if (tid == 0) {
+      if (tid == 0 && sh.early) {
+        sh.early = 0u;  // the whole bin is one run and its copy is already under way
+      } else if (tid == 0) {
         const uint32_t b0 = sh.b0;
         const uint32_t gs = sh.goff[b0] & ~1u;  // even group: 16-byte aligned source for any stride that is a multiple of 2 words
         uint32_t b1 = 256;
