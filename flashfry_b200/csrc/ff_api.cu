@@ -743,7 +743,7 @@ int ff_peer_export(ff_ctx *c, uint64_t hit_cap, int64_t guide_cap, void *handle_
     pl.block.release();
     FF_TRY(pl.block.reserve(kPeerHeadBytes + (size_t)hit_cap * 8 + (size_t)guide_cap * 4));
     FF_CUDA(cudaMemset(pl.block.p, 0, kPeerHeadBytes));
-    pl.hit_cap = (size_t)hit_cap; pl.g_cap = guide_cap; pl.epoch = 0;
+    pl.hit_cap = (size_t)hit_cap; pl.g_cap = guide_cap; pl.epoch = 0; pl.fresh = true;
     cudaIpcMemHandle_t h;
     FF_CUDA(cudaIpcGetMemHandle(&h, pl.block.p));
     memcpy(handle_out, &h, sizeof(h));
@@ -758,7 +758,7 @@ int ff_peer_attach(ff_ctx *c, int rank, int world, const void *handles, void *co
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("bad rank / world (at most %d ranks)", kMaxPeers); return FF_EINVAL; }
     if (world > 1 && !handles && !blocks) { set_error("neither IPC handles nor block pointers given"); return FF_EINVAL; }
     PeerLink &pl = c->peer;
-    if (!pl.block.p) { set_error("ff_peer_export first"); return FF_EINVAL; }
+    if (!pl.block.p || !pl.fresh) { set_error("ff_peer_export first (every attach needs a freshly exported block: its counters start at 0)"); return FF_EINVAL; }
     FF_CUDA(cudaSetDevice(c->device));
     peer_unmap(c);
     for (int r = 0; r < world; ++r) {
@@ -785,8 +785,9 @@ int ff_peer_attach(ff_ctx *c, int rank, int world, const void *handles, void *co
         pl.ipc_opened[r] = true;
       }
     }
-    pl.rank = rank; pl.world = world; pl.epoch = 0;
-    FF_CUDA(cudaMemset(pl.block.p, 0, kPeerHeadBytes));  // (every rank attaches before the first sharded call: counters start at 0)
+    // (the block's counters were zeroed by ff_peer_export, i.e. before any peer could know its handle: a peer that has
+    //  attached already may arrive at this rank's barrier counter at once)
+    pl.rank = rank; pl.world = world; pl.epoch = 0; pl.fresh = false;
     pl.ready = true;
     return FF_OK;
   });

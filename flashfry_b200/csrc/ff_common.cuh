@@ -130,7 +130,7 @@ struct Options {
 constexpr int kMaxPeers = 8;
 constexpr size_t kPeerHeadBytes = 256;  // PeerCtr at the head of an exchange block
 struct PeerLink {
-  bool ready = false;
+  bool ready = false, fresh = false;   // fresh: exported and not attached yet
   int rank = 0, world = 1;
   DevBuf block;                         // own block: PeerCtr (256 B) | candidate keys u64[hit_cap] in `world` regions | per-guide totals i32[g_cap]
   size_t hit_cap = 0;

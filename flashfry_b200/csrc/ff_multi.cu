@@ -298,6 +298,7 @@ int ff_multi_discover(ff_multi *m, const uint64_t *guides, int64_t n_guides, int
       return FF_OK;
     }
     for (int r = 0; r < n; ++r) { if (out[r]) ff_hits_free(out[r]); out[r] = nullptr; }
+    m->peers_ready = false;  // (after a failed call the ranks' barrier counters may disagree: fresh blocks next time)
     if (rc != FF_EUNSUPPORTED) return rc;
   }
   if (n > 1 && m->comm.empty()) { set_error("guide-sharded discover needs NCCL, i.e. distinct devices"); return FF_EUNSUPPORTED; }

@@ -244,7 +244,8 @@ int ff_discover_bulge_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gu
  *   1. every rank: ff_peer_export        -> its block exists; handle = CUDA IPC handle (other processes), *block_out = pointer
  *   2. every rank: ff_peer_attach        with the handles of all ranks (one process per GPU) or their pointers (one process)
  *   3. every rank, same arguments:        ff_discover_sharded[_device](all guides) -> rows of ITS guides
- * A call that fails on one rank makes the others return FF_ECUDA after a 4 s barrier time-out instead of hanging. */
+ * A call that fails on one rank makes the others return FF_ECUDA after a 4 s barrier time-out instead of hanging.  Every
+ * ff_peer_attach needs a fresh ff_peer_export on all ranks (the barrier counters live in the blocks and start at 0). */
 #define FF_PEER_HANDLE_BYTES 64
 int ff_peer_export(ff_ctx *ctx, uint64_t hit_cap /* candidate keys per block; 0 = 2^24 */, int64_t guide_cap /* all guides; 0 = 2^20 */,
                    void *handle_out /* FF_PEER_HANDLE_BYTES */, void **block_out /* may be NULL */);
