@@ -247,6 +247,7 @@ int ff_discover_bulge_device(ff_ctx *ctx, const uint64_t *d_guides, int64_t n_gu
  * A call that fails on one rank makes the others return FF_ECUDA after a 4 s barrier time-out instead of hanging.  Every
  * ff_peer_attach needs a fresh ff_peer_export on all ranks (the barrier counters live in the blocks and start at 0). */
 #define FF_PEER_HANDLE_BYTES 64
+/* (hit_cap and guide_cap must be the same on every rank: they fix the layout of the blocks the peers write into) */
 int ff_peer_export(ff_ctx *ctx, uint64_t hit_cap /* candidate keys per block; 0 = 2^24 */, int64_t guide_cap /* all guides; 0 = 2^20 */,
                    void *handle_out /* FF_PEER_HANDLE_BYTES */, void **block_out /* may be NULL */);
 int ff_peer_attach(ff_ctx *ctx, int rank, int world, const void *handles /* world x FF_PEER_HANDLE_BYTES, or NULL */,
