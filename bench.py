@@ -379,7 +379,10 @@ def run_native(args):
     per_hit = 10 if wl == "bulge" else 9
     e2e = {"value": G_job / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": 8 * (G_job if db_sharded and wl == "discover" else G),
            "d2h_bytes_per_step": (G + 1) * 8 + nh * per_hit + G * 5 + (24 * G if wl == "fused" else 0), "ms_per_step": e2e_s * 1e3,
-           "bytes_are": "per rank", "over_device_step": e2e_s * 1e3 / ms_per_step}
+           "bytes_are": "per rank", "over_device_step": e2e_s * 1e3 / ms_per_step,
+           "call": ("ff_discover_sharded (all guides in, this rank's rows out)" if db_sharded and wl == "discover" else
+                    "ff_discover_score on the rank's guides" if wl == "fused" else
+                    "ff_discover_bulge on the rank's guides" if wl == "bulge" else "ff_discover on the rank's guides")}
     if e2e_compact_s:
         e2e["with_compact_hits"] = {"value": G_job / e2e_compact_s, "ms_per_step": e2e_compact_s * 1e3,
                                     "d2h_bytes_per_step": (G + 1) * 8 + nh * 5 + G * 5,
