@@ -242,11 +242,19 @@ def test_library_carries_sm_100a_code_for_every_hot_kernel(built):
     assert archs == {"sm_100a"}, archs
     syms = subprocess.run([cuobjdump, "-symbols", built], capture_output=True, text=True).stdout
     for kernel in ("k_bin_scan", "k_pair_scan", "k_slice_planes", "k_seed_scan", "k_pattern_scan", "k_overflow_cut", "k_cut_window", "k_sort_cut", "k_sort_long", "k_compact_rows", "k_gather",
-                   "k_score", "k_hit_aggregates", "k_cell_offsets"):
+                   "k_score", "k_hit_aggregates", "k_cell_offsets", "k_pair_scan2", "k_guide_place",
+                   "k_peer_barrier", "k_peer_counts", "k_peer_compact", "k_peer_totals"):
         assert kernel in syms, "kernel missing from the library: " + kernel
     # the bin scan stages its bins with TMA bulk copies (cp.async.bulk -> UBLKCP in SASS) completing on an mbarrier
     sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN2ff10k_bin_scanILi9EEEvNS_9BinParamsE", built], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass, "k_bin_scan lost its TMA bulk copy / mbarrier"
+    # part two's ring: TMA bulk copies into two buffers, no CTA-wide barrier inside its bin loop (one BAR at the start only)
+    ring = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN2ff12k_pair_scan2ILi11EEEvNS_10PairParamsE", built], capture_output=True, text=True).stdout
+    assert "UBLKCP" in ring and "SYNCS" in ring, "k_pair_scan2 lost its TMA ring"
+    assert len(re.findall(r"\bBAR\.SYNC", ring)) <= 2, "k_pair_scan2 grew CTA-wide barriers"
+    # the database-sharded drain pushes candidates to peers with plain stores: the only system-scope atomic is the barrier's
+    bar = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN2ff14k_peer_barrierENS_8PeerPtrsEiijPjj", built], capture_output=True, text=True).stdout
+    assert "ATOM" in bar or "RED" in bar, "k_peer_barrier lost its arrival atomic"
 
 
 def test_c_abi_shard_range_is_the_one_definition_of_sharding(built):
