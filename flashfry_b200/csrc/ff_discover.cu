@@ -635,10 +635,20 @@ __global__ void k_compact_rows(const int64_t *__restrict__ seg_start, const int6
   const int lane = threadIdx.x & 31;
   if (g >= n_guides) return;
   const int64_t s0 = seg_start[g], r0 = row_ptr[g], n = row_ptr[g + 1] - r0;
-  for (int64_t i = lane; i < n; i += 32) {
-    out_targets[r0 + i] = st_targets[s0 + i];
-    out_mm[r0 + i] = st_mm[s0 + i];
-    out_tidx[r0 + i] = idx[s0 + i];
+  for (int64_t i0 = 0; i0 < n; i0 += 128) {  // four chunks of 32 at a time: their loads are in flight together
+    uint64_t t[4];
+    uint32_t x[4];
+    uint8_t m[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * 32 + lane;
+      if (i < n) { t[u] = st_targets[s0 + i]; m[u] = st_mm[s0 + i]; x[u] = idx[s0 + i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * 32 + lane;
+      if (i < n) { out_targets[r0 + i] = t[u]; out_mm[r0 + i] = m[u]; out_tidx[r0 + i] = x[u]; }
+    }
   }
   if (g == n_guides - 1 && lane == 0) stt->n_hits = row_ptr[n_guides];
 }
